@@ -1,0 +1,142 @@
+/*
+ * psg_b200.h -- C ABI of libpsgb200.so: the B200 (sm_100a) PSD / STI hot path of
+ * PySpectrogram's drfProc.py.
+ *
+ * The reference has no FFI of its own: its boundary is the Python surface of drfProc.py
+ * (drfview.py:89 `import drfProc as dp`).  Each entry point below replaces the arithmetic
+ * of the reference lines it cites; the Python module pyspectrogram_b200.drfProc keeps the
+ * reference's call signatures and binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes, no C++/torch types; every function returns 0 on success or a
+ *     negative psg_status; psg_last_error() gives a thread-local message for the last failure.
+ *   - "dev" pointers are CUDA device pointers on the plan's device; "host" pointers are
+ *     ordinary (preferably pinned) host memory.  The caller owns every buffer; the library
+ *     owns only the plan's tables and scratch.
+ *   - all device work is enqueued on the caller's stream (a cudaStream_t passed as void*;
+ *     NULL = legacy default stream) and is asynchronous unless stated otherwise.  A plan may be
+ *     used from one host thread at a time (it owns scratch); create one plan per worker thread.
+ *   - there is no CPU fallback anywhere: without a usable sm_100 device the calls fail.
+ *
+ * Data model
+ *   complex64 IQ element e(n, s) of sample n, sub-channel s lives at
+ *       iq[ n * sample_stride + s * sub_stride ]                 (strides in complex elements)
+ *   STI column c is the mean over k = 0..frames_per_col-1 of the periodograms of the frames that
+ *   start at element offset  col_offset[c] + k * hop * sample_stride :
+ *       P_c[j] = in_scale^2 / frames_per_col * sum_k | FFT_nfft( w/sum(w) * x_k ) [j] |^2
+ *   stored fftshifted (output index (j + nfft/2) mod nfft), laid out  out[s][c][i]  (i fastest).
+ *     Mode R (reference sti_proc_data as shipped, drfProc.py:364-403): frames_per_col = 1
+ *     Mode A (per-bin averaging north_star names / read_sti reads for, drfProc.py:158):
+ *             frames_per_col = nint, hop = nfft
+ *     Mode S (proc_data, drfProc.py:406-453): frames_per_col = n_int, hop = nfft - nfft/8
+ */
+#ifndef PSG_B200_H
+#define PSG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSG_ABI_VERSION 1
+
+typedef struct psg_plan psg_plan; /* opaque */
+
+typedef enum psg_status {
+    PSG_OK = 0,
+    PSG_ERR_ARG = -1,         /* bad argument (message says which) */
+    PSG_ERR_UNSUPPORTED = -2, /* nfft / layout not implemented on the GPU path */
+    PSG_ERR_CUDA = -3,        /* CUDA runtime error (message carries cudaGetErrorString) */
+    PSG_ERR_NODEVICE = -4,    /* no CUDA device, or device is not sm_100 */
+    PSG_ERR_NOMEM = -5
+} psg_status;
+
+enum { PSG_WINDOW_KAISER = 0, PSG_WINDOW_BOXCAR = 1 };
+
+/* Library / ABI version (PSG_ABI_VERSION). */
+int psg_version(void);
+
+/* Thread-local text of the last error on this thread ("" if none). */
+const char* psg_last_error(void);
+
+/* Number of CUDA devices visible, or a negative psg_status. */
+int psg_device_count(void);
+
+/*
+ * Build a plan for one FFT length on one device: the fp32 table w[n]/sum(w) of the periodic
+ * Kaiser window (drfProc.py:386 / :435 `sig.get_window(("kaiser", 1.7), nfft)`; scipy
+ * windows/_windows.py:1318-1320, :2551), computed in float64 on the host, the spectrum scaling
+ * 1/sum(w)^2 (scipy _spectral_py.py:2277) folded in, and the float64-accurate twiddle table.
+ * nfft must be a power of two in [PSG_MIN_NFFT, PSG_MAX_NFFT].
+ */
+#define PSG_MIN_NFFT 8
+#define PSG_MAX_NFFT 1048576
+int psg_plan_create(psg_plan** out, int nfft, int window_kind, double beta, int device);
+int psg_plan_destroy(psg_plan* plan);
+int psg_plan_nfft(const psg_plan* plan);
+
+/* Copy the plan's window table (w/sum(w), fp32, nfft values) to a host buffer (for tests). */
+int psg_plan_window(const psg_plan* plan, float* host_out);
+
+/*
+ * The fused hot path: frame -> window -> FFT -> |X|^2 -> mean over the bin's frames -> fftshift
+ * -> (linear and/or 10*log10(p + eps)), one read of every sample, one write of every column.
+ * Replaces sig.periodogram / welch (drfProc.py:387-396), fftshift (drfProc.py:398-399), the
+ * spectrogram+mean loop of proc_data (drfProc.py:436-449) and the dB step (drfProc.py:308-310).
+ *
+ *   iq_dev          complex64 (interleaved re,im fp32) on the device
+ *   col_offset_dev  int64[ncol] element offsets of every column's first sample (frame index
+ *                   table of DrfInput.read_sti, drfProc.py:158-159, times sample_stride)
+ *   out_lin_dev / out_db_dev   fp32 [nsub][ncol][nfft], either may be NULL (not both)
+ *   eps             added before the log (drfProc.py:308: 1e-15)
+ */
+int psg_sti_run(psg_plan* plan, const void* iq_dev,
+                int64_t sample_stride, int64_t sub_stride, int nsub,
+                const int64_t* col_offset_dev, int ncol,
+                int frames_per_col, int64_t hop,
+                float in_scale, float eps,
+                float* out_lin_dev, float* out_db_dev, void* cuda_stream);
+
+/*
+ * Median over the time axis of a finished linear-power image (np.median(sxx, axis=1),
+ * drfProc.py:401 / :451): img_dev is [nsub][ncol][nfft]; med_lin_dev / med_db_dev are
+ * [nsub][nfft] (either may be NULL).  Even ncol gives the fp32 mean of the two middle values,
+ * exactly like numpy.  Exact order statistic (radix select), no approximation.
+ */
+int psg_median_time(psg_plan* plan, const float* img_dev, int nsub, int ncol, int nfft,
+                    float eps, float* med_lin_dev, float* med_db_dev, void* cuda_stream);
+
+/*
+ * Host-buffer entry point (what drfProc.sti_proc_data / proc_data call): takes the IQ array in
+ * host memory, streams it to the device in column chunks overlapped with the kernels
+ * (two CUDA streams, double-buffered staging), runs psg_sti_run + psg_median_time and copies the
+ * results back.  Synchronous: results are valid on return.
+ *
+ *   iq_host         complex64 host array; element (n, s) of column c at
+ *                   col_offset_host[c] + n*sample_stride + s*sub_stride
+ *   iq_host_elems   number of complex elements addressable from iq_host (bounds check)
+ *   out_lin_host / out_db_host   fp32 [nsub][ncol][nfft] or NULL
+ *   med_lin_host / med_db_host   fp32 [nsub][nfft] or NULL
+ */
+int psg_sti_host(psg_plan* plan, const void* iq_host, int64_t iq_host_elems,
+                 int64_t sample_stride, int64_t sub_stride, int nsub,
+                 const int64_t* col_offset_host, int ncol,
+                 int frames_per_col, int64_t hop,
+                 float in_scale, float eps,
+                 float* out_lin_host, float* out_db_host,
+                 float* med_lin_host, float* med_db_host);
+
+/* Force the simple generic kernel (debug / cross-check) for subsequent psg_sti_run calls. */
+int psg_set_force_generic(int on);
+
+/* Counters since load: kernels launched by this library (all kinds) -- for bench "gpu_launches". */
+int64_t psg_launch_count(void);
+
+/* Name of the kernel variant psg_sti_run would use for this plan ("fused16x16x16", ...). */
+const char* psg_plan_variant(const psg_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSG_B200_H */

@@ -1,0 +1,130 @@
+// Packed complex fp32 arithmetic for sm_100a and register-resident DFT butterflies.
+//
+// Blackwell adds packed fp32x2 ALU ops (PTX add/sub/mul/fma .f32x2 -> SASS FADD2 / FMUL2 /
+// FFMA2).  ptxas folds half-swaps (".LO_HI"), per-half negation and scalar broadcast (".F32")
+// into the operand modifiers, so with (re, im) kept in one 64-bit register pair:
+//     complex add/sub         = 1 instruction
+//     multiply by +-j         = free (operand swizzle of the consuming add)
+//     real scalar * complex   = 1 instruction
+//     complex * complex       = 2 instructions (FMUL2 + FFMA2)
+//     |x|^2 accumulate        = 1 instruction (acc.re += re^2, acc.im += im^2)
+// That halves the issue slots of the FFT against scalar FADD/FFMA code.
+#pragma once
+#include <cuda_runtime.h>
+
+#define PSG_DEV __device__ __forceinline__
+
+typedef float2 cf;
+
+PSG_DEV cf cadd(cf a, cf b) {
+    cf r;
+    asm("{ .reg .b64 ra, rb, rd;\n\t mov.b64 ra, {%2, %3};\n\t mov.b64 rb, {%4, %5};\n\t"
+        " add.rn.f32x2 rd, ra, rb;\n\t mov.b64 {%0, %1}, rd; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+PSG_DEV cf csub(cf a, cf b) {
+    cf r;
+    asm("{ .reg .b64 ra, rb, rd;\n\t mov.b64 ra, {%2, %3};\n\t mov.b64 rb, {%4, %5};\n\t"
+        " sub.rn.f32x2 rd, ra, rb;\n\t mov.b64 {%0, %1}, rd; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+PSG_DEV cf mul2(cf a, cf b) {  // elementwise (a.x*b.x, a.y*b.y)
+    cf r;
+    asm("{ .reg .b64 ra, rb, rd;\n\t mov.b64 ra, {%2, %3};\n\t mov.b64 rb, {%4, %5};\n\t"
+        " mul.rn.f32x2 rd, ra, rb;\n\t mov.b64 {%0, %1}, rd; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+PSG_DEV cf fma2(cf a, cf b, cf c) {  // elementwise a*b+c
+    cf r;
+    asm("{ .reg .b64 ra, rb, rc, rd;\n\t mov.b64 ra, {%2, %3};\n\t mov.b64 rb, {%4, %5};\n\t"
+        " mov.b64 rc, {%6, %7};\n\t fma.rn.f32x2 rd, ra, rb, rc;\n\t mov.b64 {%0, %1}, rd; }"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
+PSG_DEV cf cscale(cf a, float s) { return mul2(a, make_float2(s, s)); }
+// a * w  (complex)
+PSG_DEV cf cmul(cf a, cf w) {
+    cf t = mul2(a, make_float2(w.x, w.x));
+    return fma2(make_float2(a.y, a.x), make_float2(-w.y, w.y), t);
+}
+// a * conj(w)
+PSG_DEV cf cmulc(cf a, cf w) {
+    cf t = mul2(a, make_float2(w.x, w.x));
+    return fma2(make_float2(a.y, a.x), make_float2(w.y, -w.y), t);
+}
+PSG_DEV cf mul_nj(cf a) { return make_float2(a.y, -a.x); }  // a * (-j)
+PSG_DEV cf mul_pj(cf a) { return make_float2(-a.y, a.x); }  // a * (+j)
+
+// ---- forward DFT butterflies, in place, natural-order outputs (exp(-2*pi*j*n*k/R)) -------------
+
+PSG_DEV void dft2(cf& a0, cf& a1) {
+    cf s = cadd(a0, a1);
+    a1 = csub(a0, a1);
+    a0 = s;
+}
+
+PSG_DEV void dft4(cf& a0, cf& a1, cf& a2, cf& a3) {
+    cf t0 = cadd(a0, a2), t1 = csub(a0, a2);
+    cf t2 = cadd(a1, a3), d = csub(a1, a3);
+    cf t3 = mul_nj(d);
+    a0 = cadd(t0, t2);
+    a2 = csub(t0, t2);
+    a1 = cadd(t1, t3);
+    a3 = csub(t1, t3);
+}
+
+#define PSG_SQRT1_2 0.70710678118654752440f
+#define PSG_C1_16 0.92387953251128675613f  // cos(pi/8)
+#define PSG_S1_16 0.38268343236508977173f  // sin(pi/8)
+
+PSG_DEV void dft8(cf* a) {
+    // radix-2 over (i, i+4), twiddle W8^i on the differences, then two 4-point DFTs
+    cf s0 = cadd(a[0], a[4]), d0 = csub(a[0], a[4]);
+    cf s1 = cadd(a[1], a[5]), d1 = csub(a[1], a[5]);
+    cf s2 = cadd(a[2], a[6]), d2 = csub(a[2], a[6]);
+    cf s3 = cadd(a[3], a[7]), d3 = csub(a[3], a[7]);
+    d1 = cmul(d1, make_float2(PSG_SQRT1_2, -PSG_SQRT1_2));
+    d2 = mul_nj(d2);
+    d3 = cmul(d3, make_float2(-PSG_SQRT1_2, -PSG_SQRT1_2));
+    dft4(s0, s1, s2, s3);  // X[0], X[2], X[4], X[6]
+    dft4(d0, d1, d2, d3);  // X[1], X[3], X[5], X[7]
+    a[0] = s0; a[2] = s1; a[4] = s2; a[6] = s3;
+    a[1] = d0; a[3] = d1; a[5] = d2; a[7] = d3;
+}
+
+PSG_DEV void dft16(cf* a) {
+    // DIF 4x4: X[c + 4d] = sum_i W4^{i d} ( W16^{i c} sum_m a[4m + i] W4^{m c} )
+    cf u[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        u[i][0] = a[i]; u[i][1] = a[i + 4]; u[i][2] = a[i + 8]; u[i][3] = a[i + 12];
+        dft4(u[i][0], u[i][1], u[i][2], u[i][3]);  // index c
+    }
+    // internal twiddles W16^{i*c}
+    u[1][1] = cmul(u[1][1], make_float2(PSG_C1_16, -PSG_S1_16));      // W16^1
+    u[1][2] = cmul(u[1][2], make_float2(PSG_SQRT1_2, -PSG_SQRT1_2));  // W16^2
+    u[1][3] = cmul(u[1][3], make_float2(PSG_S1_16, -PSG_C1_16));      // W16^3
+    u[2][1] = cmul(u[2][1], make_float2(PSG_SQRT1_2, -PSG_SQRT1_2));  // W16^2
+    u[2][2] = mul_nj(u[2][2]);                                        // W16^4
+    u[2][3] = cmul(u[2][3], make_float2(-PSG_SQRT1_2, -PSG_SQRT1_2)); // W16^6
+    u[3][1] = cmul(u[3][1], make_float2(PSG_S1_16, -PSG_C1_16));      // W16^3
+    u[3][2] = cmul(u[3][2], make_float2(-PSG_SQRT1_2, -PSG_SQRT1_2)); // W16^6
+    u[3][3] = cmul(u[3][3], make_float2(-PSG_C1_16, PSG_S1_16));      // W16^9
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        dft4(u[0][c], u[1][c], u[2][c], u[3][c]);  // index d
+        a[c] = u[0][c]; a[c + 4] = u[1][c]; a[c + 8] = u[2][c]; a[c + 12] = u[3][c];
+    }
+}
+
+template <int R>
+PSG_DEV void dftR(cf* a) {
+    if constexpr (R == 2) dft2(a[0], a[1]);
+    else if constexpr (R == 4) dft4(a[0], a[1], a[2], a[3]);
+    else if constexpr (R == 8) dft8(a);
+    else if constexpr (R == 16) dft16(a);
+}
