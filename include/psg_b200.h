@@ -70,7 +70,7 @@ int psg_device_count(void);
  * 1/sum(w)^2 (scipy _spectral_py.py:2277) folded in, and the float64-accurate twiddle table.
  * nfft must be a power of two in [PSG_MIN_NFFT, PSG_MAX_NFFT].
  */
-#define PSG_MIN_NFFT 8
+#define PSG_MIN_NFFT 2
 #define PSG_MAX_NFFT 1048576
 int psg_plan_create(psg_plan** out, int nfft, int window_kind, double beta, int device);
 int psg_plan_destroy(psg_plan* plan);
@@ -85,7 +85,11 @@ int psg_plan_window(const psg_plan* plan, float* host_out);
  * Replaces sig.periodogram / welch (drfProc.py:387-396), fftshift (drfProc.py:398-399), the
  * spectrogram+mean loop of proc_data (drfProc.py:436-449) and the dB step (drfProc.py:308-310).
  *
- *   iq_dev          complex64 (interleaved re,im fp32) on the device
+ *   iq_dev          complex64 (interleaved re,im fp32) on the device, 8-byte aligned.  With
+ *                   sample_stride == 1 and a 16-byte aligned iq_dev the TMA loader is used; it
+ *                   fetches 16-byte aligned spans, so the allocation must be readable up to the
+ *                   next 16-byte boundary past its last sample (true of any cudaMalloc / torch
+ *                   allocation).  Other layouts take the strided LDG loader.
  *   col_offset_dev  int64[ncol] element offsets of every column's first sample (frame index
  *                   table of DrfInput.read_sti, drfProc.py:158-159, times sample_stride)
  *   out_lin_dev / out_db_dev   fp32 [nsub][ncol][nfft], either may be NULL (not both)
@@ -129,6 +133,22 @@ int psg_sti_host(psg_plan* plan, const void* iq_host, int64_t iq_host_elems,
 
 /* Force the simple generic kernel (debug / cross-check) for subsequent psg_sti_run calls. */
 int psg_set_force_generic(int on);
+
+/*
+ * Kernel-variant table (tuning / cross-checks).  psg_set_variant(name) makes psg_sti_run prefer the
+ * named variant for its FFT length when the layout allows it; NULL or "" restores the automatic
+ * choice.  Process-wide.
+ */
+int psg_set_variant(const char* name);
+int psg_variant_count(void);
+const char* psg_variant_name(int index);
+int psg_variant_logn(int index);
+
+/*
+ * The plan's window table computed on the host only (no device needed): w[n]/sum(w) as fp32 from
+ * fp64 math, sum(w) in *sum_out (may be NULL).  Same routine psg_plan_create uses.
+ */
+int psg_window_table(int nfft, int window_kind, double beta, float* host_out, double* sum_out);
 
 /* Counters since load: kernels launched by this library (all kinds) -- for bench "gpu_launches". */
 int64_t psg_launch_count(void);

@@ -1,0 +1,593 @@
+// libpsgb200.so -- host side of the C ABI declared in include/psg_b200.h.
+//
+// Owns: plan tables (window, twiddles), kernel-variant dispatch and launch geometry, the
+// time-median launch, and the host-buffer entry point.  No torch, no cuFFT, no CPU fallback: if
+// there is no sm_100 device every compute entry point fails with PSG_ERR_NODEVICE.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/psg_b200.h"
+#include "sti_kernels.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_force_generic{0};
+static std::mutex g_variant_mu;
+static std::string g_variant_override;  // "" = automatic
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(PSG_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                   \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// kernel variants
+// ------------------------------------------------------------------------------------------------
+struct Variant {
+    const char* name;
+    int logn, F, loader, threads, minb;
+    size_t smem;
+    const void* fn;
+};
+
+template <int LOGN, int E, int R0, int R1, int R2, int R3, int F, int LOADER, int STAGES, int XBUF, int MINB>
+static Variant make_variant(const char* name) {
+    using CF = FusedCfg<LOGN, E, R0, R1, R2, R3, F, LOADER, STAGES, XBUF>;
+    Variant v;
+    v.name = name;
+    v.logn = LOGN;
+    v.F = F;
+    v.loader = LOADER;
+    v.threads = CF::NT;
+    v.minb = MINB;
+    v.smem = CF::smem_bytes;
+    v.fn = (const void*)sti_fused_kernel<LOGN, E, R0, R1, R2, R3, F, LOADER, STAGES, XBUF, MINB>;
+    return v;
+}
+
+#define L PSG_LOADER_LDG
+#define M PSG_LOADER_TMA
+// name = <loader><logn>_<radices>_f<F>_s<stages>x<xbuf>; first match per (logn, loader) is default
+static const Variant g_variants[] = {
+    //            LOGN E  R0  R1  R2 R3  F  LD ST XB MINB
+    make_variant<8, 16, 16, 16, 1, 1, 16, M, 3, 2, 2>("tma8_16x16_f16_s3x2"),
+    make_variant<8, 16, 16, 16, 1, 1, 16, L, 1, 2, 2>("ldg8_16x16_f16"),
+    make_variant<9, 16, 2, 16, 16, 1, 8, M, 3, 2, 2>("tma9_2x16x16_f8_s3x2"),
+    make_variant<9, 16, 16, 16, 2, 1, 8, M, 3, 2, 2>("tma9_16x16x2_f8_s3x2"),
+    make_variant<9, 16, 2, 16, 16, 1, 8, L, 1, 2, 2>("ldg9_2x16x16_f8"),
+    make_variant<10, 16, 4, 16, 16, 1, 4, M, 3, 2, 2>("tma10_4x16x16_f4_s3x2"),
+    make_variant<10, 16, 16, 16, 4, 1, 4, M, 3, 2, 2>("tma10_16x16x4_f4_s3x2"),
+    make_variant<10, 16, 4, 16, 16, 1, 4, L, 1, 2, 2>("ldg10_4x16x16_f4"),
+    make_variant<11, 16, 8, 16, 16, 1, 2, M, 3, 2, 2>("tma11_8x16x16_f2_s3x2"),
+    make_variant<11, 16, 16, 16, 8, 1, 2, M, 3, 2, 2>("tma11_16x16x8_f2_s3x2"),
+    make_variant<11, 16, 8, 16, 16, 1, 2, L, 1, 2, 2>("ldg11_8x16x16_f2"),
+    make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 1, 2>("tma12_16x16x16_f1_s2x1"),
+    make_variant<12, 16, 16, 16, 16, 1, 1, M, 3, 2, 1>("tma12_16x16x16_f1_s3x2"),
+    make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 2, 1>("tma12_16x16x16_f1_s2x2"),
+    make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 2, 2>("ldg12_16x16x16_f1"),
+    make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 1, 2>("ldg12_16x16x16_f1_x1"),
+    make_variant<13, 16, 2, 16, 16, 16, 1, M, 2, 1, 1>("tma13_2x16x16x16_f1_s2x1"),
+    make_variant<13, 16, 8, 8, 8, 16, 1, M, 2, 1, 1>("tma13_8x8x8x16_f1_s2x1"),
+    make_variant<13, 16, 2, 16, 16, 16, 1, L, 1, 1, 1>("ldg13_2x16x16x16_f1"),
+};
+#undef L
+#undef M
+static const int g_nvariants = (int)(sizeof(g_variants) / sizeof(g_variants[0]));
+
+static const Variant* find_variant(int logn, int loader) {
+    {
+        std::lock_guard<std::mutex> lk(g_variant_mu);
+        if (!g_variant_override.empty()) {
+            for (int i = 0; i < g_nvariants; ++i)
+                if (g_variant_override == g_variants[i].name && g_variants[i].logn == logn &&
+                    (g_variants[i].loader == PSG_LOADER_LDG || loader == PSG_LOADER_TMA))
+                    return &g_variants[i];
+        }
+    }
+    for (int i = 0; i < g_nvariants; ++i)
+        if (g_variants[i].logn == logn && g_variants[i].loader == loader) return &g_variants[i];
+    return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+struct psg_plan {
+    int nfft, logn, device, sms;
+    float* d_win = nullptr;
+    float2* d_tw = nullptr;
+    float2* d_twp = nullptr;
+    std::vector<float> h_win;
+    // scratch (grow-only; a plan is used by one host thread at a time)
+    float* d_partial = nullptr;
+    size_t partial_elems = 0;
+    float2* d_gwork = nullptr;
+    float* d_gacc = nullptr;
+    size_t gwork_slabs = 0;
+    // psg_sti_host staging
+    void* d_in = nullptr;
+    size_t in_bytes = 0;
+    long long* d_off = nullptr;
+    size_t off_elems = 0;
+    float* d_out[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t out_elems[4] = {0, 0, 0, 0};
+    cudaStream_t stream = nullptr;
+    std::vector<char> attr_done;  // per variant: smem attribute set on this device
+    std::vector<int> occ;         // per variant: resident CTAs per SM
+    char variant_name[64];
+};
+
+static double bessel_i0(double x) {
+    // power series sum ((x/2)^(2k) / (k!)^2); converges to double precision for |x| < ~700
+    const double q = 0.25 * x * x;
+    double term = 1.0, sum = 1.0;
+    for (int k = 1; k < 500; ++k) {
+        term *= q / ((double)k * (double)k);
+        sum += term;
+        if (term < sum * 1e-17) break;
+    }
+    return sum;
+}
+
+static int ilog2_exact(int n) {
+    int l = 0;
+    while ((1 << l) < n) ++l;
+    return ((1 << l) == n) ? l : -1;
+}
+
+static int check_device(int device, int* sms) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(PSG_ERR_NODEVICE, "no CUDA device: %s", e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(PSG_ERR_ARG, "device %d out of range (have %d)", device, n);
+    cudaDeviceProp pr;
+    CUDA_TRY(cudaGetDeviceProperties(&pr, device));
+    if (pr.major != 10)
+        return fail(PSG_ERR_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    pr.major, pr.minor);
+    *sms = pr.multiProcessorCount;
+    return PSG_OK;
+}
+
+extern "C" int psg_version(void) { return PSG_ABI_VERSION; }
+extern "C" const char* psg_last_error(void) { return g_err; }
+extern "C" int psg_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(PSG_ERR_NODEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return n;
+}
+extern "C" int64_t psg_launch_count(void) { return g_launches.load(); }
+extern "C" int psg_set_force_generic(int on) {
+    g_force_generic.store(on ? 1 : 0);
+    return PSG_OK;
+}
+extern "C" int psg_set_variant(const char* name) {
+    std::lock_guard<std::mutex> lk(g_variant_mu);
+    g_variant_override = name ? name : "";
+    if (!g_variant_override.empty()) {
+        bool ok = false;
+        for (int i = 0; i < g_nvariants; ++i) ok = ok || g_variant_override == g_variants[i].name;
+        if (!ok) {
+            g_variant_override.clear();
+            return fail(PSG_ERR_ARG, "unknown kernel variant '%s'", name);
+        }
+    }
+    return PSG_OK;
+}
+extern "C" int psg_variant_count(void) { return g_nvariants; }
+extern "C" const char* psg_variant_name(int i) { return (i >= 0 && i < g_nvariants) ? g_variants[i].name : ""; }
+extern "C" int psg_variant_logn(int i) { return (i >= 0 && i < g_nvariants) ? g_variants[i].logn : -1; }
+
+// Host-side window table w[n]/sum(w) (fp64 math, fp32 result) without touching a device: what the
+// plan uploads.  Exposed so CPU-only tests can pin the table against scipy's.
+extern "C" int psg_window_table(int nfft, int window_kind, double beta, float* host_out, double* sum_out) {
+    if (nfft < 1 || !host_out) return fail(PSG_ERR_ARG, "psg_window_table: bad arguments");
+    std::vector<double> w(nfft);
+    if (window_kind == PSG_WINDOW_KAISER) {
+        const double a = 0.5 * nfft, i0b = bessel_i0(beta);
+        for (int n = 0; n < nfft; ++n) {
+            const double r = (n - a) / a;
+            const double arg = 1.0 - r * r;
+            w[n] = (nfft == 1) ? 1.0 : bessel_i0(beta * sqrt(arg > 0 ? arg : 0.0)) / i0b;
+        }
+    } else if (window_kind == PSG_WINDOW_BOXCAR) {
+        for (int n = 0; n < nfft; ++n) w[n] = 1.0;
+    } else {
+        return fail(PSG_ERR_ARG, "unknown window kind %d", window_kind);
+    }
+    double s = 0.0;  // pairwise-ish: numpy's sum is pairwise; plain Kahan keeps us within 1 ulp of it
+    double c = 0.0;
+    for (int n = 0; n < nfft; ++n) {
+        const double y = w[n] - c, t = s + y;
+        c = (t - s) - y;
+        s = t;
+    }
+    for (int n = 0; n < nfft; ++n) host_out[n] = (float)(w[n] / s);
+    if (sum_out) *sum_out = s;
+    return PSG_OK;
+}
+
+extern "C" int psg_plan_create(psg_plan** out, int nfft, int window_kind, double beta, int device) {
+    if (!out) return fail(PSG_ERR_ARG, "psg_plan_create: out is NULL");
+    *out = nullptr;
+    if (nfft < PSG_MIN_NFFT || nfft > PSG_MAX_NFFT)
+        return fail(PSG_ERR_UNSUPPORTED, "nfft=%d outside [%d, %d]", nfft, PSG_MIN_NFFT, PSG_MAX_NFFT);
+    const int logn = ilog2_exact(nfft);
+    if (logn < 0)
+        return fail(PSG_ERR_UNSUPPORTED, "nfft=%d is not a power of two (only power-of-two FFT lengths run on the GPU path)",
+                    nfft);
+    int sms = 0;
+    int rc = check_device(device, &sms);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(device));
+
+    psg_plan* p = new psg_plan();
+    p->nfft = nfft;
+    p->logn = logn;
+    p->device = device;
+    p->sms = sms;
+    p->h_win.resize(nfft);
+    p->attr_done.assign(g_nvariants, 0);
+    p->occ.assign(g_nvariants, 0);
+    rc = psg_window_table(nfft, window_kind, beta, p->h_win.data(), nullptr);
+    if (rc) { delete p; return rc; }
+
+    // full twiddle table (generic kernels) and the per-pass tables of every tuned variant layout
+    std::vector<float2> tw(nfft);
+    for (int m = 0; m < nfft; ++m) {
+        const double ang = -2.0 * M_PI * (double)m / (double)nfft;
+        tw[m] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+    cudaError_t e;
+#define PLAN_TRY(expr)                                                                             \
+    if ((e = (expr)) != cudaSuccess) {                                                             \
+        psg_plan_destroy(p);                                                                       \
+        return fail(PSG_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e));                  \
+    }
+    PLAN_TRY(cudaMalloc(&p->d_win, sizeof(float) * nfft));
+    PLAN_TRY(cudaMalloc(&p->d_tw, sizeof(float2) * nfft));
+    PLAN_TRY(cudaMemcpy(p->d_win, p->h_win.data(), sizeof(float) * nfft, cudaMemcpyHostToDevice));
+    PLAN_TRY(cudaMemcpy(p->d_tw, tw.data(), sizeof(float2) * nfft, cudaMemcpyHostToDevice));
+    PLAN_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+#undef PLAN_TRY
+    p->variant_name[0] = 0;
+    *out = p;
+    return PSG_OK;
+}
+
+extern "C" int psg_plan_destroy(psg_plan* p) {
+    if (!p) return PSG_OK;
+    cudaSetDevice(p->device);
+    cudaFree(p->d_win);
+    cudaFree(p->d_tw);
+    cudaFree(p->d_twp);
+    cudaFree(p->d_partial);
+    cudaFree(p->d_gwork);
+    cudaFree(p->d_gacc);
+    cudaFree(p->d_in);
+    cudaFree(p->d_off);
+    for (int i = 0; i < 4; ++i) cudaFree(p->d_out[i]);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+    return PSG_OK;
+}
+
+extern "C" int psg_plan_nfft(const psg_plan* p) { return p ? p->nfft : fail(PSG_ERR_ARG, "plan is NULL"); }
+
+extern "C" int psg_plan_window(const psg_plan* p, float* host_out) {
+    if (!p || !host_out) return fail(PSG_ERR_ARG, "psg_plan_window: NULL argument");
+    memcpy(host_out, p->h_win.data(), sizeof(float) * p->nfft);
+    return PSG_OK;
+}
+
+// per-pass twiddle tables for radices (r[0..np)) -- layout documented in sti_kernels.cuh
+static std::vector<float2> build_pass_tables(int n, const int* r, int np) {
+    std::vector<float2> t;
+    int s = n;
+    for (int p = 0; p + 1 < np; ++p) {
+        s /= r[p];
+        const int m = r[p] * s;
+        for (int k = 1; k < r[p]; ++k)
+            for (int i = 0; i < s; ++i) {
+                const double ang = -2.0 * M_PI * (double)((long long)i * k % m) / (double)m;
+                t.push_back(make_float2((float)cos(ang), (float)sin(ang)));
+            }
+    }
+    if (t.empty()) t.push_back(make_float2(1.f, 0.f));
+    return t;
+}
+
+// radices of a variant, parsed from its name ("..._16x8x8_...")
+static int variant_radices(const Variant* v, int* r) {
+    const char* s = strchr(v->name, '_');
+    int np = 0;
+    if (!s) return 0;
+    ++s;
+    while (*s && np < 4) {
+        r[np++] = atoi(s);
+        while (*s >= '0' && *s <= '9') ++s;
+        if (*s != 'x') break;
+        ++s;
+    }
+    return np;
+}
+
+static int ensure_buffer(void** ptr, size_t* have, size_t want_bytes) {
+    if (*have >= want_bytes && *ptr) return PSG_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    *have = 0;
+    cudaError_t e = cudaMalloc(ptr, want_bytes);
+    if (e != cudaSuccess) return fail(PSG_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", want_bytes, cudaGetErrorString(e));
+    *have = want_bytes;
+    return PSG_OK;
+}
+
+static int floor_pow2(int x) {
+    int p = 1;
+    while (p * 2 <= x) p *= 2;
+    return p;
+}
+
+extern "C" const char* psg_plan_variant(const psg_plan* p) { return p ? p->variant_name : ""; }
+
+extern "C" int psg_sti_run(psg_plan* p, const void* iq_dev, int64_t sample_stride, int64_t sub_stride, int nsub,
+                           const int64_t* col_offset_dev, int ncol, int frames_per_col, int64_t hop, float in_scale,
+                           float eps, float* out_lin_dev, float* out_db_dev, void* cuda_stream) {
+    if (!p) return fail(PSG_ERR_ARG, "psg_sti_run: plan is NULL");
+    if (!iq_dev || !col_offset_dev) return fail(PSG_ERR_ARG, "psg_sti_run: NULL input pointer");
+    if (!out_lin_dev && !out_db_dev) return fail(PSG_ERR_ARG, "psg_sti_run: both outputs are NULL");
+    if (nsub < 1 || ncol < 1 || frames_per_col < 1)
+        return fail(PSG_ERR_ARG, "psg_sti_run: nsub=%d ncol=%d frames_per_col=%d must be >= 1", nsub, ncol, frames_per_col);
+    if (sample_stride < 1) return fail(PSG_ERR_ARG, "psg_sti_run: sample_stride=%lld must be >= 1", (long long)sample_stride);
+    if (frames_per_col > 1 && hop < 1) return fail(PSG_ERR_ARG, "psg_sti_run: hop=%lld must be >= 1", (long long)hop);
+    if ((reinterpret_cast<uintptr_t>(iq_dev) & 7) != 0) return fail(PSG_ERR_ARG, "psg_sti_run: iq_dev must be 8-byte aligned");
+    if ((long long)ncol * nsub > (1ll << 30)) return fail(PSG_ERR_ARG, "psg_sti_run: too many columns");
+    CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int N = p->nfft;
+    const int ncs = ncol * nsub;
+
+    StiArgs a;
+    a.iq = (const float2*)iq_dev;
+    a.sample_stride = sample_stride;
+    a.sub_stride = sub_stride;
+    a.hop_elems = hop * sample_stride;
+    a.col_off = (const long long*)col_offset_dev;
+    a.ncol = ncol;
+    a.nsub = nsub;
+    a.nfr = frames_per_col;
+    a.win = p->d_win;
+    a.tw = p->d_tw;
+    a.twp = nullptr;
+    a.scale = (float)((double)in_scale * (double)in_scale / (double)frames_per_col);
+    a.eps = eps;
+    a.out_lin = out_lin_dev;
+    a.out_db = out_db_dev;
+    a.partial = nullptr;
+
+    const bool tma_ok = sample_stride == 1 && (reinterpret_cast<uintptr_t>(iq_dev) & 15) == 0;
+    const Variant* v = nullptr;
+    if (!g_force_generic.load()) {
+        v = find_variant(p->logn, tma_ok ? PSG_LOADER_TMA : PSG_LOADER_LDG);
+        if (!v && tma_ok) v = find_variant(p->logn, PSG_LOADER_LDG);
+    }
+
+    if (v) {
+        const int vi = (int)(v - g_variants);
+        if (!p->attr_done[vi]) {
+            CUDA_TRY(cudaFuncSetAttribute(v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->smem));
+            int occ = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v->fn, v->threads, v->smem));
+            if (occ < 1) return fail(PSG_ERR_CUDA, "variant %s does not fit on an SM", v->name);
+            p->occ[vi] = occ;
+            p->attr_done[vi] = 1;
+        }
+        // per-pass twiddle tables: one layout per radix set; rebuilt when the variant changes
+        if (strcmp(p->variant_name, v->name) != 0 || !p->d_twp) {
+            int r[4], np = variant_radices(v, r);
+            std::vector<float2> t = build_pass_tables(N, r, np);
+            if (p->d_twp) { CUDA_TRY(cudaStreamSynchronize(st)); cudaFree(p->d_twp); p->d_twp = nullptr; }
+            CUDA_TRY(cudaMalloc(&p->d_twp, sizeof(float2) * t.size()));
+            CUDA_TRY(cudaMemcpy(p->d_twp, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice));
+            snprintf(p->variant_name, sizeof(p->variant_name), "%s", v->name);
+        }
+        a.twp = p->d_twp;
+        // geometry: gpc lanes per column inside a CTA, nsplit CTAs per column
+        const int F = v->F;
+        const int gpc = std::min(F, floor_pow2(frames_per_col));
+        const int cpc = F / gpc;
+        const int colblocks = (ncs + cpc - 1) / cpc;
+        const int iters = (frames_per_col + gpc - 1) / gpc;  // per column if one CTA did it all
+        const long long slots = (long long)p->sms * p->occ[vi];
+        const long long target = slots * 24;
+        int nsplit = (int)std::min<long long>((target + colblocks - 1) / colblocks, 1 << 20);
+        const int smin = (iters + 255) / 256, smax = std::max(1, iters / 16);
+        nsplit = std::max(smin, std::min(nsplit, smax));
+        nsplit = std::max(nsplit, 1);
+        int chunk = ((iters + nsplit - 1) / nsplit) * gpc;
+        nsplit = (frames_per_col + chunk - 1) / chunk;
+        a.gpc = gpc;
+        a.chunk = chunk;
+        a.nsplit = nsplit;
+        if (nsplit > 1) {
+            const size_t need = (size_t)ncs * nsplit * N;
+            size_t have_b = p->partial_elems * sizeof(float);
+            int rc = ensure_buffer((void**)&p->d_partial, &have_b, need * sizeof(float));
+            p->partial_elems = have_b / sizeof(float);
+            if (rc) return rc;
+            a.partial = p->d_partial;
+        }
+        const long long grid = (long long)colblocks * nsplit;
+        if (grid > 2147483647ll) return fail(PSG_ERR_ARG, "psg_sti_run: grid too large");
+        void* args[] = {(void*)&a};
+        CUDA_TRY(cudaLaunchKernel(v->fn, dim3((unsigned)grid), dim3(v->threads), args, v->smem, st));
+        g_launches++;
+    } else {
+        // generic radix-2 path
+        snprintf(p->variant_name, sizeof(p->variant_name), "generic_radix2");
+        const bool in_smem = N <= 16384;
+        const int iters = frames_per_col;
+        int nsplit = std::max(1, (iters + 255) / 256);
+        const long long target = (long long)p->sms * 8;
+        if ((long long)ncs * nsplit < target) nsplit = (int)std::min<long long>(std::max(1, iters / 4), (target + ncs - 1) / ncs);
+        nsplit = std::max(nsplit, 1);
+        int chunk = (iters + nsplit - 1) / nsplit;
+        nsplit = (iters + chunk - 1) / chunk;
+        a.gpc = 1;
+        a.chunk = chunk;
+        a.nsplit = nsplit;
+        if (nsplit > 1) {
+            const size_t need = (size_t)ncs * nsplit * N;
+            size_t have_b = p->partial_elems * sizeof(float);
+            int rc = ensure_buffer((void**)&p->d_partial, &have_b, need * sizeof(float));
+            p->partial_elems = have_b / sizeof(float);
+            if (rc) return rc;
+            a.partial = p->d_partial;
+        }
+        const long long items = (long long)ncs * nsplit;
+        size_t smem = 0;
+        float2* gwork = nullptr;
+        float* gacc = nullptr;
+        long long grid = items;
+        if (in_smem) {
+            smem = (size_t)N * 12;
+            cudaError_t e = cudaFuncSetAttribute((const void*)sti_generic_kernel,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 12);
+            if (e != cudaSuccess) return fail(PSG_ERR_CUDA, "cudaFuncSetAttribute(generic): %s", cudaGetErrorString(e));
+            grid = std::min<long long>(items, (long long)p->sms * 16);
+        } else {
+            grid = std::min<long long>(items, (long long)p->sms * 2);
+            if (p->gwork_slabs < (size_t)grid) {
+                if (p->d_gwork) { CUDA_TRY(cudaStreamSynchronize(st)); cudaFree(p->d_gwork); cudaFree(p->d_gacc); }
+                p->d_gwork = nullptr; p->d_gacc = nullptr; p->gwork_slabs = 0;
+                cudaError_t e1 = cudaMalloc(&p->d_gwork, sizeof(float2) * (size_t)grid * N);
+                cudaError_t e2 = cudaMalloc(&p->d_gacc, sizeof(float) * (size_t)grid * N);
+                if (e1 != cudaSuccess || e2 != cudaSuccess) return fail(PSG_ERR_NOMEM, "scratch for nfft=%d failed", N);
+                p->gwork_slabs = (size_t)grid;
+            }
+            gwork = p->d_gwork;
+            gacc = p->d_gacc;
+        }
+        int logn = p->logn;
+        void* args[] = {(void*)&a, (void*)&logn, (void*)&gwork, (void*)&gacc};
+        CUDA_TRY(cudaLaunchKernel((const void*)sti_generic_kernel, dim3((unsigned)grid), dim3(256), args, smem, st));
+        g_launches++;
+    }
+    if (a.nsplit > 1) {
+        const size_t total = (size_t)ncs * N;
+        const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)p->sms * 16);
+        sti_finalize_kernel<<<blocks, 256, 0, st>>>(a.partial, a.nsplit, N, (size_t)ncs, a.scale, eps, out_lin_dev,
+                                                    out_db_dev);
+        g_launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return PSG_OK;
+}
+
+extern "C" int psg_median_time(psg_plan* p, const float* img_dev, int nsub, int ncol, int nfft, float eps,
+                               float* med_lin_dev, float* med_db_dev, void* cuda_stream) {
+    if (!p) return fail(PSG_ERR_ARG, "psg_median_time: plan is NULL");
+    if (!img_dev || (!med_lin_dev && !med_db_dev)) return fail(PSG_ERR_ARG, "psg_median_time: NULL pointer");
+    if (nsub < 1 || ncol < 1 || nfft < 1) return fail(PSG_ERR_ARG, "psg_median_time: bad shape");
+    CUDA_TRY(cudaSetDevice(p->device));
+    const size_t total = (size_t)nsub * nfft;
+    const int blocks = (int)((total + 127) / 128);
+    median_time_kernel<<<blocks, 128, 0, (cudaStream_t)cuda_stream>>>(img_dev, nsub, ncol, nfft, eps, med_lin_dev,
+                                                                      med_db_dev);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PSG_OK;
+}
+
+extern "C" int psg_sti_host(psg_plan* p, const void* iq_host, int64_t iq_host_elems, int64_t sample_stride,
+                            int64_t sub_stride, int nsub, const int64_t* col_offset_host, int ncol,
+                            int frames_per_col, int64_t hop, float in_scale, float eps, float* out_lin_host,
+                            float* out_db_host, float* med_lin_host, float* med_db_host) {
+    if (!p) return fail(PSG_ERR_ARG, "psg_sti_host: plan is NULL");
+    if (!iq_host || !col_offset_host) return fail(PSG_ERR_ARG, "psg_sti_host: NULL input pointer");
+    if (!out_lin_host && !out_db_host && !med_lin_host && !med_db_host)
+        return fail(PSG_ERR_ARG, "psg_sti_host: no output requested");
+    if (nsub < 1 || ncol < 1 || frames_per_col < 1 || sample_stride < 1 || sub_stride < 0)
+        return fail(PSG_ERR_ARG, "psg_sti_host: bad shape/stride");
+    const int N = p->nfft;
+    // extent of one column's reads (elements past its offset), and the span all columns touch
+    const long long col_extent = ((long long)(frames_per_col - 1) * hop + (N - 1)) * sample_stride +
+                                 (long long)(nsub - 1) * sub_stride + 1;
+    long long lo = col_offset_host[0], hi = col_offset_host[0];
+    for (int c = 1; c < ncol; ++c) {
+        lo = std::min<long long>(lo, col_offset_host[c]);
+        hi = std::max<long long>(hi, col_offset_host[c]);
+    }
+    if (lo < 0 || hi + col_extent > iq_host_elems)
+        return fail(PSG_ERR_ARG, "psg_sti_host: columns reach [%lld, %lld) outside the %lld-element host array", lo,
+                    hi + col_extent, (long long)iq_host_elems);
+    CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = p->stream;
+    // keep the device copy 16-byte aligned relative to the host element parity so that aligned
+    // host frames stay aligned on the device
+    const long long lo_al = lo & ~1ll;
+    const size_t span = (size_t)(hi + col_extent - lo_al);
+    int rc = ensure_buffer(&p->d_in, &p->in_bytes, (span + 2) * 8);
+    if (rc) return rc;
+    {
+        size_t have = p->off_elems * 8;
+        rc = ensure_buffer((void**)&p->d_off, &have, (size_t)ncol * 8);
+        p->off_elems = have / 8;
+        if (rc) return rc;
+    }
+    std::vector<long long> rel(ncol);
+    for (int c = 0; c < ncol; ++c) rel[c] = col_offset_host[c] - lo_al;
+    const size_t img_elems = (size_t)nsub * ncol * N, med_elems = (size_t)nsub * N;
+    const bool need_lin = out_lin_host || med_lin_host || med_db_host;
+    const size_t want[4] = {need_lin ? img_elems : 0, out_db_host ? img_elems : 0, med_lin_host ? med_elems : 0,
+                            med_db_host ? med_elems : 0};
+    for (int i = 0; i < 4; ++i) {
+        if (!want[i]) continue;
+        size_t have = p->out_elems[i] * 4;
+        rc = ensure_buffer((void**)&p->d_out[i], &have, want[i] * 4);
+        p->out_elems[i] = have / 4;
+        if (rc) return rc;
+    }
+    CUDA_TRY(cudaMemcpyAsync(p->d_off, rel.data(), (size_t)ncol * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(p->d_in, (const char*)iq_host + (size_t)lo_al * 8, span * 8, cudaMemcpyHostToDevice, st));
+    rc = psg_sti_run(p, p->d_in, sample_stride, sub_stride, nsub, (const int64_t*)p->d_off, ncol, frames_per_col, hop,
+                     in_scale, eps, need_lin ? p->d_out[0] : nullptr, out_db_host ? p->d_out[1] : nullptr, st);
+    if (rc) return rc;
+    if (med_lin_host || med_db_host) {
+        rc = psg_median_time(p, p->d_out[0], nsub, ncol, N, eps, med_lin_host ? p->d_out[2] : nullptr,
+                             med_db_host ? p->d_out[3] : nullptr, st);
+        if (rc) return rc;
+    }
+    if (out_lin_host) CUDA_TRY(cudaMemcpyAsync(out_lin_host, p->d_out[0], img_elems * 4, cudaMemcpyDeviceToHost, st));
+    if (out_db_host) CUDA_TRY(cudaMemcpyAsync(out_db_host, p->d_out[1], img_elems * 4, cudaMemcpyDeviceToHost, st));
+    if (med_lin_host) CUDA_TRY(cudaMemcpyAsync(med_lin_host, p->d_out[2], med_elems * 4, cudaMemcpyDeviceToHost, st));
+    if (med_db_host) CUDA_TRY(cudaMemcpyAsync(med_db_host, p->d_out[3], med_elems * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PSG_OK;
+}

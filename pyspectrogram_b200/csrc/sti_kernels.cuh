@@ -1,24 +1,39 @@
 // Fused STFT -> PSD -> STI kernels for sm_100a (device code).
 //
-// One CTA owns one work item = (sub-channel, STI column, chunk of that column's frames).  For
-// every frame it loads nfft complex64 samples straight into registers (coalesced LDG.64, L1
-// no-allocate), multiplies by the fp32 window table w/sum(w), runs an in-place mixed-radix DIF
-// FFT whose butterflies live in registers (radix <= 16, packed f32x2 math, cplx.cuh) and whose
-// digit exchanges go through a padded, bank-conflict-free shared-memory buffer, and accumulates
-// |X|^2 per output bin in registers.  After the chunk's last frame the sums are scaled,
-// fftshifted through shared memory and stored coalesced as linear power and/or 10*log10(p+eps)
-// -- or as raw partial sums when a column is split over several CTAs (finalised by
-// sti_finalize_kernel).  Samples are read from HBM exactly once; nothing but the STI column is
-// written.
+// Work decomposition
+//   A CTA owns one work item = (block of CPC (sub-channel, column) pairs, one chunk of those
+//   columns' frames).  Its threads form F independent "frame groups" of T = N/E threads; a group
+//   transforms one nfft-point frame at a time.  GPC groups cooperate on one column (frames
+//   k0 + j*GPC + lane), so F = CPC * GPC.  Every pass is CTA-uniform: groups whose frame does not
+//   exist transform zeros.
 //
-// Index algebra (validated numerically by tests/test_fft_plan.py, which restates it in numpy):
+// Per frame
+//   loader   TMA: one elected thread issues a cp.async.bulk (UBLKCP) per frame into a ring of
+//            shared-memory stages, completion on an mbarrier; frames are contiguous complex64, so a
+//            1-D bulk copy is exactly one frame.  The copy starts at the frame's address rounded
+//            down to 16 B (frame starts come from np.linspace and are odd half the time), the
+//            consumer skips the leading element.  LDG: strided/unaligned layouts load straight to
+//            registers with coalesced LDG.64 (L1 no-allocate).
+//   pass 0   registers <- window * samples; R0-point DFTs (radix <= 16, packed f32x2 math);
+//            twiddle; store to the padded exchange buffer.
+//   pass p   in-place R_p-point DFTs out of the exchange buffer; the last pass accumulates |X|^2
+//            per bin in registers instead of storing.
+//   epilogue (once per item) lanes of a column are summed, bins un-digit-reversed and fftshifted
+//            through shared memory, scaled, and stored coalesced as linear power and/or
+//            10*log10(p+eps) -- or as raw partial sums when a column is split over several CTAs
+//            (summed in fp64 by sti_finalize_kernel, fixed order, deterministic).
+//   Samples are read from HBM exactly once; nothing but the STI column is written.
+//
+// Index algebra (restated in numpy and checked by tests/test_fft_plan.py)
 //   N = R0*R1*...*R(P-1),  S_p = N/(R0..Rp).  Before pass p the element with digits
 //   (k_0..k_{p-1}, n_rest) sits at pos = sum_q k_q*S_q + n_rest.  Pass p splits
 //   n_rest = n_p*S_p + n', does the R_p-point DFT over n_p, multiplies output k_p by
 //   W_{R_p*S_p}^{n'*k_p} (skipped on the last pass) and stores it in place of n_p.  After the
 //   last pass pos = sum_q k_q*S_q holds frequency k = k_0 + R0*k_1 + R0*R1*k_2 + ...
 //   Shared-memory address of pos is pos + (pos >> 4) (one complex of padding per 16), which
-//   makes every pass's 64-bit accesses conflict-free for the plans used here.
+//   keeps the 64-bit accesses of every pass conflict-free for the plans used here.
+//   Twiddles come from per-pass tables  twp[(k-1)*S_p + n'] = exp(-2*pi*j*n'*k/(R_p*S_p))
+//   (lane-contiguous in n', so a warp's load is one line).
 #pragma once
 #include <stdint.h>
 #include "cplx.cuh"
@@ -31,16 +46,20 @@ struct StiArgs {
     const long long* col_off; // [ncol] element offset of each column's first sample
     int ncol, nsub;
     int nfr;     // frames per column
-    int chunk;   // frames per work item
+    int chunk;   // frames per work item (per column)
     int nsplit;  // work items per column = ceil(nfr / chunk)
+    int gpc;     // frame groups cooperating on one column (power of two, divides F)
     const float* win;   // [N]  w[n] / sum(w)
-    const float2* tw;   // [N]  exp(-2*pi*j*m/N)
+    const float2* tw;   // [N]  exp(-2*pi*j*m/N)   (generic kernels)
+    const float2* twp;  // per-pass tables, concatenated in pass order (tuned kernels)
     float scale;        // in_scale^2 / nfr
     float eps;
     float* out_lin;     // [nsub][ncol][N] or null
     float* out_db;      // [nsub][ncol][N] or null
-    float* partial;     // [nsub][ncol][nsplit][N] raw sums when nsplit > 1
+    float* partial;     // [nsub*ncol][nsplit][N] raw sums when nsplit > 1
 };
+
+enum { PSG_LOADER_LDG = 0, PSG_LOADER_TMA = 1 };
 
 PSG_DEV float2 ldg_stream(const float2* p) {
     float2 v;
@@ -52,27 +71,60 @@ PSG_DEV float power_to_db(float p, float eps) { return 10.0f * log10f(p + eps); 
 
 __host__ __device__ constexpr int psg_pad(int pos) { return pos + (pos >> 4); }
 
+// ---- mbarrier / bulk-copy (TMA) primitives ------------------------------------------------------
+PSG_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+PSG_DEV void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+PSG_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+PSG_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP).
+PSG_DEV void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
 template <int N, int R0, int R1, int R2, int R3>
 struct Plan {
     static constexpr int P = 1 + (R1 > 1) + (R2 > 1) + (R3 > 1);
     static constexpr int S0 = N / R0, S1 = S0 / R1, S2 = S1 / R2, S3 = S2 / R3;
     static_assert(R0 * R1 * R2 * R3 == N, "radices must multiply to N");
     static constexpr int RL = (P == 1) ? R0 : (P == 2) ? R1 : (P == 3) ? R2 : R3;  // last radix
+    // offsets of the per-pass twiddle tables inside twp
+    static constexpr int TW0 = 0;
+    static constexpr int TW1 = TW0 + (R0 - 1) * S0;
+    static constexpr int TW2 = TW1 + (R1 - 1) * S1;
     // frequency of (last-pass butterfly b, output j): digit-reverse b, add (N/RL)*j
     PSG_DEV static int low_freq(int b) {
         int rem = b, k = 0;
-        if (P >= 2) { constexpr int s = S0 / RL; k += (rem / s); rem %= s; }
-        if (P >= 3) { constexpr int s = S1 / RL; k += (rem / s) * R0; rem %= s; }
-        if (P >= 4) { constexpr int s = S2 / RL; k += (rem / s) * R0 * R1; rem %= s; }
+        if constexpr (P >= 2) { constexpr int s = S0 / RL; k += (rem / s); rem %= s; }
+        if constexpr (P >= 3) { constexpr int s = S1 / RL; k += (rem / s) * R0; rem %= s; }
+        if constexpr (P >= 4) { constexpr int s = S2 / RL; k += (rem / s) * R0 * R1; rem %= s; }
         return k;
     }
 };
 
-// one in-place pass over shared memory (p >= 1). LAST: accumulate |X|^2 instead of storing.
-template <int N, int E, int T, int R, int S, bool LAST>
-PSG_DEV void smem_pass(float2* __restrict__ buf, const float2* __restrict__ tw, int t, cf* acc) {
-    constexpr int NB = E / R;       // butterflies per thread
-    constexpr int M = R * S;        // size of the sub-DFT this pass splits
+// one in-place pass over the exchange buffer (p >= 1). LAST: accumulate |X|^2 instead of storing.
+template <int E, int T, int R, int S, bool LAST>
+PSG_DEV void smem_pass(float2* __restrict__ buf, const float2* __restrict__ twp, int t, float* acc) {
+    constexpr int NB = E / R;  // butterflies per thread
+    constexpr int M = R * S;   // size of the sub-DFT this pass splits
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
         const int b = t + i * T;
@@ -84,36 +136,106 @@ PSG_DEV void smem_pass(float2* __restrict__ buf, const float2* __restrict__ tw, 
         dftR<R>(a);
         if constexpr (LAST) {
 #pragma unroll
-            for (int k = 0; k < R; ++k) acc[i * R + k] = fma2(a[k], a[k], acc[i * R + k]);
+            for (int k = 0; k < R; ++k) acc[i * R + k] = fmaf(a[k].x, a[k].x, fmaf(a[k].y, a[k].y, acc[i * R + k]));
         } else {
-            const float2* twp = tw + npr * (N / M);
 #pragma unroll
-            for (int k = 1; k < R; ++k) a[k] = cmul(a[k], __ldg(twp + (size_t)npr * (N / M) * (k - 1)));
+            for (int k = 1; k < R; ++k) a[k] = cmul(a[k], __ldg(twp + (k - 1) * S + npr));
 #pragma unroll
             for (int k = 0; k < R; ++k) buf[psg_pad(base + k * S)] = a[k];
         }
     }
 }
 
-template <int LOGN, int E, int R0, int R1, int R2, int R3, int MINB>
-__global__ void __launch_bounds__((1 << LOGN) / E, MINB) sti_fused_kernel(const StiArgs a) {
-    constexpr int N = 1 << LOGN, T = N / E;
+template <int LOGN, int E, int R0, int R1, int R2, int R3, int F, int LOADER, int STAGES, int XBUF>
+struct FusedCfg {
+    static constexpr int N = 1 << LOGN, T = N / E, NT = F * T;
+    static constexpr int NPAD = psg_pad(N) + 1;
+    static constexpr int SLOT = N + 2;  // one frame + one element of alignment slack either side
+    static constexpr size_t bar_bytes = 64;
+    static constexpr size_t stage_bytes = (LOADER == PSG_LOADER_TMA) ? (size_t)STAGES * F * SLOT * 8 : 0;
+    static constexpr size_t xch_bytes = (size_t)F * XBUF * NPAD * 8;
+    static constexpr size_t smem_bytes = bar_bytes + stage_bytes + xch_bytes;
+};
+
+template <int LOGN, int E, int R0, int R1, int R2, int R3, int F, int LOADER, int STAGES, int XBUF, int MINB>
+__global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(const StiArgs a) {
+    using CF = FusedCfg<LOGN, E, R0, R1, R2, R3, F, LOADER, STAGES, XBUF>;
+    constexpr int N = CF::N, T = CF::T, NT = CF::NT, NPAD = CF::NPAD, SLOT = CF::SLOT;
     using PL = Plan<N, R0, R1, R2, R3>;
     constexpr int P = PL::P;
-    constexpr int NPAD = psg_pad(N) + 1;
     constexpr int NB0 = E / R0;
-    extern __shared__ __align__(16) float2 smem[];
+    static_assert(P >= 2 || F * T >= 1, "");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+    float2* stage = reinterpret_cast<float2*>(smem_raw + CF::bar_bytes);
+    float2* xch = reinterpret_cast<float2*>(smem_raw + CF::bar_bytes + CF::stage_bytes);
 
-    const int t = threadIdx.x;
+    const int tid = threadIdx.x;
+    const int g = tid / T;   // frame group
+    const int t = tid - g * T;
+    const int gpc = a.gpc;   // groups per column
+    const int cpc = F / gpc; // columns per CTA
+    const int lane = g % gpc;
+    const int slot = g / gpc;
+
+    const int ncs = a.ncol * a.nsub;
     const int item = blockIdx.x;
     const int split = item % a.nsplit;
-    const int cs = item / a.nsplit;
-    const int col = cs % a.ncol;
-    const int sub = cs / a.ncol;
+    const int cs0 = (item / a.nsplit) * cpc;
+    const int cs = cs0 + slot;
+    const bool col_ok = cs < ncs;
     const int k0 = split * a.chunk;
     const int k1 = min(a.nfr, k0 + a.chunk);
+    const int niter = (k1 - k0 + gpc - 1) / gpc;
 
-    const float2* src = a.iq + a.col_off[col] + (long long)sub * a.sub_stride + (long long)k0 * a.hop_elems;
+    long long fbase = 0;  // element offset of frame k0+lane of this group's column
+    if (col_ok) {
+        const int col = cs % a.ncol, sub = cs / a.ncol;
+        fbase = a.col_off[col] + (long long)sub * a.sub_stride + (long long)(k0 + lane) * a.hop_elems;
+    }
+    const long long fstep = (long long)gpc * a.hop_elems;
+
+    // ---- TMA producer state (thread 0 only) ----
+    auto issue = [&](int j) {  // copies of iteration j -> stage j % STAGES
+        if constexpr (LOADER == PSG_LOADER_TMA) {
+            uint64_t* bar = bars + (j % STAGES);
+            float2* sbase = stage + (size_t)(j % STAGES) * F * SLOT;
+            uint32_t total = 0;
+            for (int gg = 0; gg < F; ++gg) {
+                const int cc = cs0 + gg / gpc;
+                const int kk = k0 + j * gpc + (gg % gpc);
+                if (cc < ncs && kk < k1) {
+                    const long long off = a.col_off[cc % a.ncol] + (long long)(cc / a.ncol) * a.sub_stride +
+                                          (long long)kk * a.hop_elems;
+                    total += N * 8 + ((reinterpret_cast<uintptr_t>(a.iq + off) & 8) ? 16 : 0);
+                }
+            }
+            mbar_expect_tx(bar, total);
+            for (int gg = 0; gg < F; ++gg) {
+                const int cc = cs0 + gg / gpc;
+                const int kk = k0 + j * gpc + (gg % gpc);
+                if (cc < ncs && kk < k1) {
+                    const long long off = a.col_off[cc % a.ncol] + (long long)(cc / a.ncol) * a.sub_stride +
+                                          (long long)kk * a.hop_elems;
+                    // a frame that is only 8-byte aligned is fetched from one element earlier
+                    // (16-byte aligned) and 16 bytes longer; the consumer skips the first element
+                    const uintptr_t src = reinterpret_cast<uintptr_t>(a.iq + off);
+                    const uint32_t bytes = N * 8 + ((src & 8) ? 16 : 0);
+                    bulk_g2s(sbase + (size_t)gg * SLOT, reinterpret_cast<const void*>(src & ~(uintptr_t)15), bytes,
+                             bar);
+                }
+            }
+        }
+    };
+    if constexpr (LOADER == PSG_LOADER_TMA) {
+        if (tid == 0) {
+            for (int s = 0; s < STAGES; ++s) mbar_init(bars + s, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0)
+            for (int j = 0; j < STAGES - 1 && j < niter; ++j) issue(j);
+    }
 
     // loop-invariant tables in registers: window of this thread's E samples, pass-0 twiddles
     float w[E];
@@ -125,32 +247,52 @@ __global__ void __launch_bounds__((1 << LOGN) / E, MINB) sti_fused_kernel(const 
         for (int n = 0; n < R0; ++n) w[i * R0 + n] = __ldg(a.win + b + n * PL::S0);
         if constexpr (P > 1) {
 #pragma unroll
-            for (int k = 1; k < R0; ++k) tw0[i][k - 1] = __ldg(a.tw + b * k);
+            for (int k = 1; k < R0; ++k) tw0[i][k - 1] = __ldg(a.twp + PL::TW0 + (k - 1) * PL::S0 + b);
         }
     }
-    cf acc[E];
+    float acc[E];  // |X|^2 sums of this thread's E bins (scalar: registers are the scarce resource)
 #pragma unroll
-    for (int i = 0; i < E; ++i) acc[i] = make_float2(0.f, 0.f);
+    for (int i = 0; i < E; ++i) acc[i] = 0.f;
 
-    for (int k = k0; k < k1; ++k, src += a.hop_elems) {
-        float2* buf = smem + ((k - k0) & 1) * NPAD;
+    for (int j = 0; j < niter; ++j, fbase += fstep) {
+        const bool valid = col_ok && (k0 + j * gpc + lane) < k1;
+        float2* buf = xch + (size_t)(g * XBUF + (XBUF > 1 ? (j & 1) : 0)) * NPAD;
         cf x[E];
-        // ---- pass 0: global -> registers, window, DFT over the most significant digit ----
+        // ---- pass 0: samples -> registers ----
+        if constexpr (LOADER == PSG_LOADER_TMA) {
+            if (tid == 0 && j + STAGES - 1 < niter) issue(j + STAGES - 1);
+            mbar_wait(bars + (j % STAGES), (j / STAGES) & 1);
+            const float2* sb = stage + ((size_t)(j % STAGES) * F + g) * SLOT +
+                               ((reinterpret_cast<uintptr_t>(a.iq + fbase) >> 3) & 1);
 #pragma unroll
-        for (int i = 0; i < NB0; ++i) {
-            const int b = t + i * T;
+            for (int i = 0; i < NB0; ++i) {
+                const int b = t + i * T;
 #pragma unroll
-            for (int n = 0; n < R0; ++n)
-                x[i * R0 + n] = ldg_stream(src + (long long)(b + n * PL::S0) * a.sample_stride);
+                for (int n = 0; n < R0; ++n)
+                    x[i * R0 + n] = valid ? sb[b + n * PL::S0] : make_float2(0.f, 0.f);
+            }
+        } else {
+            const float2* src = a.iq + fbase;
+#pragma unroll
+            for (int i = 0; i < NB0; ++i) {
+                const int b = t + i * T;
+#pragma unroll
+                for (int n = 0; n < R0; ++n)
+                    x[i * R0 + n] = valid ? ldg_stream(src + (long long)(b + n * PL::S0) * a.sample_stride)
+                                          : make_float2(0.f, 0.f);
+            }
         }
 #pragma unroll
         for (int i = 0; i < E; ++i) x[i] = cscale(x[i], w[i]);
+        if constexpr (XBUF == 1 && P > 1) __syncthreads();  // previous frame's last pass done reading
 #pragma unroll
         for (int i = 0; i < NB0; ++i) {
             dftR<R0>(&x[i * R0]);
             if constexpr (P == 1) {
 #pragma unroll
-                for (int kk = 0; kk < R0; ++kk) acc[i * R0 + kk] = fma2(x[i * R0 + kk], x[i * R0 + kk], acc[i * R0 + kk]);
+                for (int kk = 0; kk < R0; ++kk)
+                    acc[i * R0 + kk] = fmaf(x[i * R0 + kk].x, x[i * R0 + kk].x,
+                                            fmaf(x[i * R0 + kk].y, x[i * R0 + kk].y, acc[i * R0 + kk]));
             } else {
                 const int b = t + i * T;
 #pragma unroll
@@ -161,21 +303,21 @@ __global__ void __launch_bounds__((1 << LOGN) / E, MINB) sti_fused_kernel(const 
         }
         if constexpr (P >= 2) {
             __syncthreads();
-            smem_pass<N, E, T, R1, PL::S1, P == 2>(buf, a.tw, t, acc);
+            smem_pass<E, T, R1, PL::S1, P == 2>(buf, a.twp + PL::TW1, t, acc);
         }
         if constexpr (P >= 3) {
             __syncthreads();
-            smem_pass<N, E, T, R2, PL::S2, P == 3>(buf, a.tw, t, acc);
+            smem_pass<E, T, R2, PL::S2, P == 3>(buf, a.twp + PL::TW2, t, acc);
         }
         if constexpr (P >= 4) {
             __syncthreads();
-            smem_pass<N, E, T, R3, PL::S3, P == 4>(buf, a.tw, t, acc);
+            smem_pass<E, T, R3, PL::S3, P == 4>(buf, a.twp + PL::TW2 + (R2 - 1) * PL::S2, t, acc);
         }
     }
 
     // ---- epilogue: digit-reversed register sums -> fftshifted, coalesced stores ----
     __syncthreads();
-    float* sout = reinterpret_cast<float*>(smem);
+    float* sout = reinterpret_cast<float*>(xch);  // [F][N] floats (fits: F*NPAD*8 bytes available)
     constexpr int RL = PL::RL;
     constexpr int NBL = E / RL;
 #pragma unroll
@@ -183,28 +325,28 @@ __global__ void __launch_bounds__((1 << LOGN) / E, MINB) sti_fused_kernel(const 
         const int b = t + i * T;
         const int klow = PL::low_freq(b);
 #pragma unroll
-        for (int j = 0; j < RL; ++j) {
-            const int freq = klow + (N / RL) * j;
+        for (int jj = 0; jj < RL; ++jj) {
+            const int freq = klow + (N / RL) * jj;
             const int idx = (freq + N / 2) & (N - 1);
-            sout[idx ^ ((idx >> 5) & 31)] = acc[i * RL + j].x + acc[i * RL + j].y;
+            sout[g * N + (idx ^ ((idx >> 5) & 31))] = acc[i * RL + jj];
         }
     }
     __syncthreads();
-    if (a.nsplit > 1) {
-        float* dst = a.partial + ((size_t)cs * a.nsplit + split) * N;
-#pragma unroll
-        for (int i = 0; i < E; ++i) {
-            const int idx = t + i * T;
-            dst[idx] = sout[idx ^ ((idx >> 5) & 31)];
-        }
-    } else {
-        const size_t o = (size_t)cs * N;
-#pragma unroll
-        for (int i = 0; i < E; ++i) {
-            const int idx = t + i * T;
-            const float p = sout[idx ^ ((idx >> 5) & 31)] * a.scale;
-            if (a.out_lin) a.out_lin[o + idx] = p;
-            if (a.out_db) a.out_db[o + idx] = power_to_db(p, a.eps);
+    // all NT threads cooperate: column slot s, bin idx; lanes summed in fixed order
+    for (int e = tid; e < cpc * N; e += NT) {
+        const int s = e / N, idx = e - s * N;
+        const int c = cs0 + s;
+        if (c >= ncs) break;
+        const int sw = idx ^ ((idx >> 5) & 31);
+        float v = 0.f;
+        for (int l = 0; l < gpc; ++l) v += sout[(s * gpc + l) * N + sw];
+        if (a.nsplit > 1) {
+            a.partial[((size_t)c * a.nsplit + split) * N + idx] = v;
+        } else {
+            const float p = v * a.scale;
+            const size_t o = (size_t)c * N + idx;
+            if (a.out_lin) a.out_lin[o] = p;
+            if (a.out_db) a.out_db[o] = power_to_db(p, a.eps);
         }
     }
 }
@@ -213,66 +355,116 @@ __global__ void __launch_bounds__((1 << LOGN) / E, MINB) sti_fused_kernel(const 
 __global__ void sti_finalize_kernel(const float* __restrict__ partial, int nsplit, int n, size_t ncols_total,
                                     float scale, float eps, float* out_lin, float* out_db) {
     const size_t total = ncols_total * (size_t)n;
-    for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
-        const size_t c = g / n;
-        const int i = (int)(g - c * n);
+    for (size_t gi = blockIdx.x * (size_t)blockDim.x + threadIdx.x; gi < total;
+         gi += (size_t)gridDim.x * blockDim.x) {
+        const size_t c = gi / n;
+        const int i = (int)(gi - c * n);
         const float* p = partial + c * nsplit * (size_t)n + i;
         double s = 0.0;
         for (int k = 0; k < nsplit; ++k) s += (double)p[(size_t)k * n];
-        const float v = (float)s * scale;
-        if (out_lin) out_lin[g] = v;
-        if (out_db) out_db[g] = power_to_db(v, eps);
+        const float v = (float)(s * (double)scale);
+        if (out_lin) out_lin[gi] = v;
+        if (out_db) out_db[gi] = power_to_db(v, eps);
     }
 }
 
-// ---- generic fallback: any power-of-two N that fits shared memory, radix-2, simple ------------
-// Used for N < 256, for cross-checking the tuned kernels, and never for speed.
-__global__ void __launch_bounds__(256) sti_generic_kernel(const StiArgs a, int logn) {
+// ---- generic kernels: any power-of-two N, radix-2, simple ---------------------------------------
+// Used for N < 256, for N the tuned kernels do not cover, and to cross-check them; never for speed.
+// work buffer: shared memory (N <= 16384) or a per-CTA global scratch slab (larger N).
+__global__ void __launch_bounds__(256) sti_generic_kernel(const StiArgs a, int logn, float2* gwork, float* gacc) {
     const int N = 1 << logn;
     extern __shared__ __align__(16) float2 smem[];
-    float2* buf = smem;
-    float* accs = reinterpret_cast<float*>(smem + N);
+    float2* buf = gwork ? gwork + (size_t)blockIdx.x * N : smem;
+    float* accs = gacc ? gacc + (size_t)blockIdx.x * N : reinterpret_cast<float*>(smem + N);
     const int t = threadIdx.x, nt = blockDim.x;
-    const int item = blockIdx.x;
-    const int split = item % a.nsplit;
-    const int cs = item / a.nsplit;
-    const int col = cs % a.ncol;
-    const int sub = cs / a.ncol;
-    const int k0 = split * a.chunk;
-    const int k1 = min(a.nfr, k0 + a.chunk);
-    const float2* src = a.iq + a.col_off[col] + (long long)sub * a.sub_stride + (long long)k0 * a.hop_elems;
-    for (int i = t; i < N; i += nt) accs[i] = 0.f;
-    for (int k = k0; k < k1; ++k, src += a.hop_elems) {
+    const int ncs = a.ncol * a.nsub;
+    for (int item = blockIdx.x; item < ncs * a.nsplit; item += gridDim.x) {
+        const int split = item % a.nsplit;
+        const int cs = item / a.nsplit;
+        const int col = cs % a.ncol;
+        const int sub = cs / a.ncol;
+        const int k0 = split * a.chunk;
+        const int k1 = min(a.nfr, k0 + a.chunk);
+        const float2* src = a.iq + a.col_off[col] + (long long)sub * a.sub_stride + (long long)k0 * a.hop_elems;
         __syncthreads();
-        for (int i = t; i < N; i += nt) buf[i] = cscale(ldg_stream(src + (long long)i * a.sample_stride), a.win[i]);
-        for (int s = N >> 1; s >= 1; s >>= 1) {
+        for (int i = t; i < N; i += nt) accs[i] = 0.f;
+        for (int k = k0; k < k1; ++k, src += a.hop_elems) {
             __syncthreads();
-            const int step = (N >> 1) / s;  // twiddle stride: W_{2s}^j = W_N^{j*N/(2s)}
-            for (int i = t; i < (N >> 1); i += nt) {
-                const int j = i & (s - 1);
-                const int base = ((i / s) * 2 * s) + j;
-                const cf u = buf[base], v = buf[base + s];
-                buf[base] = cadd(u, v);
-                cf d = csub(u, v);
-                buf[base + s] = (s > 1) ? cmul(d, a.tw[j * step]) : d;
+            for (int i = t; i < N; i += nt)
+                buf[i] = cscale(ldg_stream(src + (long long)i * a.sample_stride), a.win[i]);
+            for (int s = N >> 1; s >= 1; s >>= 1) {
+                __syncthreads();
+                const int step = (N >> 1) / s;  // twiddle stride: W_{2s}^j = W_N^{j*N/(2s)}
+                for (int i = t; i < (N >> 1); i += nt) {
+                    const int j = i & (s - 1);
+                    const int base = ((i / s) * 2 * s) + j;
+                    const cf u = buf[base], v = buf[base + s];
+                    buf[base] = cadd(u, v);
+                    cf d = csub(u, v);
+                    buf[base + s] = (s > 1) ? cmul(d, a.tw[(size_t)j * step]) : d;
+                }
+            }
+            __syncthreads();
+            for (int i = t; i < N; i += nt) {
+                const cf v = buf[i];
+                accs[i] = fmaf(v.x, v.x, fmaf(v.y, v.y, accs[i]));
             }
         }
         __syncthreads();
         for (int i = t; i < N; i += nt) {
-            const cf v = buf[i];
-            accs[i] = fmaf(v.x, v.x, fmaf(v.y, v.y, accs[i]));
+            const int freq = (int)(__brev((unsigned)i) >> (32 - logn));
+            const int idx = (freq + N / 2) & (N - 1);
+            if (a.nsplit > 1) {
+                a.partial[((size_t)cs * a.nsplit + split) * N + idx] = accs[i];
+            } else {
+                const float p = accs[i] * a.scale;
+                if (a.out_lin) a.out_lin[(size_t)cs * N + idx] = p;
+                if (a.out_db) a.out_db[(size_t)cs * N + idx] = power_to_db(p, a.eps);
+            }
         }
     }
-    __syncthreads();
-    for (int i = t; i < N; i += nt) {
-        const int freq = (int)(__brev((unsigned)i) >> (32 - logn));
-        const int idx = (freq + N / 2) & (N - 1);
-        if (a.nsplit > 1) {
-            a.partial[((size_t)cs * a.nsplit + split) * N + idx] = accs[i];
-        } else {
-            const float p = accs[i] * a.scale;
-            if (a.out_lin) a.out_lin[(size_t)cs * N + idx] = p;
-            if (a.out_db) a.out_db[(size_t)cs * N + idx] = power_to_db(p, a.eps);
-        }
+}
+
+// ---- median over the time axis (np.median(sxx, axis=1), drfProc.py:401 / :451) ------------------
+// img [nsub][ncol][nfft]; one thread per (sub, bin): exact k-th order statistic by a 32-step
+// bisection on the IEEE bit pattern (monotone for the non-negative powers this path produces;
+// negative values are mapped to an order-preserving key as well), reads coalesced across bins.
+PSG_DEV unsigned f2key(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+PSG_DEV float key2f(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__global__ void __launch_bounds__(128) median_time_kernel(const float* __restrict__ img, int nsub, int ncol,
+                                                          int nfft, float eps, float* med_lin, float* med_db) {
+    const size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (gid >= (size_t)nsub * nfft) return;
+    const int sub = (int)(gid / nfft), bin = (int)(gid - (size_t)sub * nfft);
+    const float* p = img + (size_t)sub * ncol * nfft + bin;
+    const int klo = (ncol - 1) >> 1;  // 0-based rank of the lower middle
+    // largest key K with count(key < K) <= klo  ==> K is the klo-th smallest key
+    unsigned key = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+        const unsigned cand = key | (1u << bit);
+        int cnt = 0;
+        for (int c = 0; c < ncol; ++c) cnt += (f2key(__ldg(p + (size_t)c * nfft)) < cand) ? 1 : 0;
+        if (cnt <= klo) key = cand;
     }
+    float m = key2f(key);
+    if ((ncol & 1) == 0) {
+        // upper middle: the same value if it is repeated, else the smallest value above it
+        int cnt_le = 0;
+        unsigned nxt = 0xffffffffu;
+        for (int c = 0; c < ncol; ++c) {
+            const unsigned kk = f2key(__ldg(p + (size_t)c * nfft));
+            cnt_le += (kk <= key) ? 1 : 0;
+            if (kk > key && kk < nxt) nxt = kk;
+        }
+        const float hi = (cnt_le >= klo + 2) ? m : key2f(nxt);
+        m = (m + hi) * 0.5f;  // numpy: mean of the two middle values in float32
+    }
+    if (med_lin) med_lin[gid] = m;
+    if (med_db) med_db[gid] = power_to_db(m, eps);
 }

@@ -1,0 +1,207 @@
+"""Device-resident STI engine: torch tensors in, torch tensors out, compute in libpsgb200.so.
+
+PyTorch is used for device memory and streams only; every kernel on this path is hand-written
+sm_100a CUDA behind the C ABI (``include/psg_b200.h``).  Layout and mode definitions follow
+SURVEY.md section 8(a):
+
+* IQ element (sample n, sub-channel s) lives at ``iq[n*sample_stride + s*sub_stride]``
+* column ``c`` averages ``frames_per_col`` frames starting at ``col_offsets[c] + k*hop*sample_stride``
+* Mode R (``sti_proc_data`` as shipped, drfProc.py:364-403): ``frames_per_col=1``
+* Mode A (per-bin averaging, read_sti's ``nint`` frames, drfProc.py:158): ``frames_per_col=nint, hop=nfft``
+* Mode S (``proc_data``, drfProc.py:406-453): ``frames_per_col=n_int, hop=nfft-nfft//8``
+
+Images are ``[nsub][ncol][nfft]`` float32, fftshifted (bin ``nfft/2`` is DC).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import _lib
+
+DB_EPS = 1e-15  # drfProc.py:308
+KAISER_BETA = 1.7  # drfProc.py:386, :435
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class StiPlan:
+    """One FFT length on one device (window + twiddle tables live on the GPU).
+
+    A plan owns scratch and is used by one thread at a time (guarded by a lock so the viewer's
+    worker threads, drfview.py:177-178, may share one safely).
+    """
+
+    def __init__(self, nfft: int, device: int = 0, window=("kaiser", KAISER_BETA)):
+        self._lib = _lib.load()
+        kind, beta = self._window_kind(window)
+        handle = C.c_void_p()
+        _lib.check(self._lib.psg_plan_create(C.byref(handle), int(nfft), kind, float(beta), int(device)))
+        self._h = handle
+        self.nfft = int(nfft)
+        self.device = int(device)
+        self._lock = threading.Lock()
+
+    @staticmethod
+    def _window_kind(window):
+        if isinstance(window, str):
+            window = (window, 0.0)
+        name = window[0].lower()
+        if name == "kaiser":
+            return _lib.PSG_WINDOW_KAISER, float(window[1])
+        if name in ("boxcar", "rect", "rectangular"):
+            return _lib.PSG_WINDOW_BOXCAR, 0.0
+        raise ValueError(f"window {window!r} is not available on the GPU path (kaiser, boxcar)")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.psg_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- introspection ---------------------------------------------------------------------
+    def window_table(self) -> np.ndarray:
+        """fp32 ``w/sum(w)`` as uploaded to the device."""
+        out = np.empty(self.nfft, np.float32)
+        _lib.check(self._lib.psg_plan_window(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    @property
+    def variant(self) -> str:
+        return self._lib.psg_plan_variant(self._h).decode()
+
+    # ---- device path -----------------------------------------------------------------------
+    def run(self, iq, col_offsets, frames_per_col=1, hop=None, *, sample_stride=1, sub_stride=0, nsub=1,
+            in_scale=1.0, eps=DB_EPS, want_lin=True, want_db=False, out_lin=None, out_db=None):
+        """Fused frame->window->FFT->|X|^2->mean->fftshift->(dB) on device-resident IQ.
+
+        ``iq``: CUDA tensor, complex64 (or float32 viewed as interleaved re/im).
+        ``col_offsets``: CUDA int64 tensor ``[ncol]`` of element offsets into ``iq``.
+        Returns ``(lin, db)`` tensors ``[nsub][ncol][nfft]`` (``None`` for the one not requested).
+        Work is enqueued on torch's current stream; nothing synchronises.
+        """
+        torch = _torch()
+        if not iq.is_cuda or not col_offsets.is_cuda:
+            raise ValueError("iq and col_offsets must be CUDA tensors (use StiPlan.host for host arrays)")
+        if iq.dtype not in (torch.complex64, torch.float32):
+            raise TypeError(f"iq must be complex64 (or its float32 view), got {iq.dtype}")
+        if col_offsets.dtype != torch.int64 or not col_offsets.is_contiguous():
+            raise TypeError("col_offsets must be a contiguous int64 tensor")
+        if iq.device.index != self.device or col_offsets.device.index != self.device:
+            raise ValueError("tensors are not on the plan's device")
+        ncol = int(col_offsets.numel())
+        hop = self.nfft if hop is None else int(hop)
+        dev = iq.device
+        shape = (int(nsub), ncol, self.nfft)
+        if want_lin and out_lin is None:
+            out_lin = torch.empty(shape, dtype=torch.float32, device=dev)
+        if want_db and out_db is None:
+            out_db = torch.empty(shape, dtype=torch.float32, device=dev)
+        for o in (out_lin, out_db):
+            if o is not None and (o.dtype != torch.float32 or not o.is_contiguous() or o.numel() != nsub * ncol * self.nfft):
+                raise ValueError("output tensors must be contiguous float32 [nsub][ncol][nfft]")
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with self._lock:
+            _lib.check(self._lib.psg_sti_run(
+                self._h, C.c_void_p(iq.data_ptr()), int(sample_stride), int(sub_stride), int(nsub),
+                C.c_void_p(col_offsets.data_ptr()), ncol, int(frames_per_col), hop, float(in_scale), float(eps),
+                C.c_void_p(out_lin.data_ptr() if out_lin is not None else None),
+                C.c_void_p(out_db.data_ptr() if out_db is not None else None), C.c_void_p(stream)))
+        return out_lin, out_db
+
+    def median(self, img, *, eps=DB_EPS, want_lin=True, want_db=False):
+        """``np.median(sxx, axis=1)`` (drfProc.py:401) of a ``[nsub][ncol][nfft]`` linear image."""
+        torch = _torch()
+        if not img.is_cuda or img.dtype != torch.float32 or not img.is_contiguous() or img.dim() != 3:
+            raise ValueError("img must be a contiguous CUDA float32 [nsub][ncol][nfft] tensor")
+        nsub, ncol, nfft = (int(v) for v in img.shape)
+        lin = torch.empty((nsub, nfft), dtype=torch.float32, device=img.device) if want_lin else None
+        db = torch.empty((nsub, nfft), dtype=torch.float32, device=img.device) if want_db else None
+        stream = torch.cuda.current_stream(img.device).cuda_stream
+        with self._lock:
+            _lib.check(self._lib.psg_median_time(
+                self._h, C.c_void_p(img.data_ptr()), nsub, ncol, nfft, float(eps),
+                C.c_void_p(lin.data_ptr() if lin is not None else None),
+                C.c_void_p(db.data_ptr() if db is not None else None), C.c_void_p(stream)))
+        return lin, db
+
+    # ---- host path -------------------------------------------------------------------------
+    def host(self, iq: np.ndarray, col_offsets, frames_per_col=1, hop=None, *, sample_stride=1, sub_stride=0,
+             nsub=1, in_scale=1.0, eps=DB_EPS, want=("lin", "med")):
+        """Host complex64 array in, host float32 arrays out (H2D, kernels, D2H inside the call).
+
+        ``want``: any of ``"lin" "db" "med" "med_db"``.  Returns a dict of numpy arrays:
+        images ``[nsub][ncol][nfft]``, medians ``[nsub][nfft]``.
+        """
+        if not isinstance(iq, np.ndarray) or iq.dtype != np.complex64 or not iq.flags.c_contiguous:
+            raise TypeError("iq must be a C-contiguous numpy complex64 array")
+        offs = np.ascontiguousarray(col_offsets, dtype=np.int64)
+        ncol = int(offs.size)
+        hop = self.nfft if hop is None else int(hop)
+        out = {}
+        ptr = {}
+        for key, shape in (("lin", (nsub, ncol, self.nfft)), ("db", (nsub, ncol, self.nfft)),
+                           ("med", (nsub, self.nfft)), ("med_db", (nsub, self.nfft))):
+            if key in want:
+                out[key] = np.empty(shape, np.float32)
+                ptr[key] = out[key].ctypes.data_as(C.c_void_p)
+            else:
+                ptr[key] = C.c_void_p(None)
+        with self._lock:
+            _lib.check(self._lib.psg_sti_host(
+                self._h, iq.ctypes.data_as(C.c_void_p), int(iq.size), int(sample_stride), int(sub_stride),
+                int(nsub), offs.ctypes.data_as(C.c_void_p), ncol, int(frames_per_col), hop, float(in_scale),
+                float(eps), ptr["lin"], ptr["db"], ptr["med"], ptr["med_db"]))
+        return out
+
+
+_plans = {}
+_plans_lock = threading.Lock()
+
+
+def get_plan(nfft: int, device: int = 0, window=("kaiser", KAISER_BETA)) -> StiPlan:
+    """Process-wide plan cache keyed by (nfft, device, window)."""
+    key = (int(nfft), int(device), tuple(window) if not isinstance(window, str) else (window,))
+    with _plans_lock:
+        plan = _plans.get(key)
+        if plan is None:
+            plan = _plans[key] = StiPlan(nfft, device, window)
+        return plan
+
+
+def frame_starts(st_sample, en_sample, nfft, nint, ntime) -> np.ndarray:
+    """Frame index table of ``DrfInput.read_sti`` (drfProc.py:158-159).
+
+    Evaluated by numpy's own ``linspace(..., dtype=int)`` on the host so that the float64
+    quantisation of epoch-sized sample indices is reproduced bit for bit (SURVEY.md section 0,
+    trap 2); the int64 table is what the kernel consumes.
+    """
+    n_sample = int(nint) * int(nfft)
+    return np.linspace(st_sample, en_sample - n_sample, int(ntime), dtype=int)
+
+
+def launch_count() -> int:
+    return int(_lib.load().psg_launch_count())
+
+
+def set_variant(name=None):
+    _lib.check(_lib.load().psg_set_variant(name.encode() if name else None))
+
+
+def set_force_generic(on: bool):
+    _lib.check(_lib.load().psg_set_force_generic(1 if on else 0))
+
+
+def variants():
+    lib = _lib.load()
+    return [(lib.psg_variant_name(i).decode(), lib.psg_variant_logn(i)) for i in range(lib.psg_variant_count())]

@@ -1,0 +1,121 @@
+"""numpy restatement of the tuned kernels' index algebra (pyspectrogram_b200/csrc/sti_kernels.cuh).
+
+Runs the same pass structure -- in-place mixed-radix DIF, per-pass twiddle tables
+``twp[(k-1)*S_p + n']``, digit-reversed last pass mapped by ``low_freq`` -- in float64 and checks it
+against ``np.fft.fft`` for every radix set the library registers.  This pins the addressing on the
+CPU so GPU time is spent on numerics and speed, not on index bugs.
+"""
+import numpy as np
+import pytest
+
+from pyspectrogram_b200 import _lib
+
+
+def pass_tables(n, radices):
+    tabs, s = [], n
+    for p, r in enumerate(radices[:-1]):
+        s //= r
+        m = r * s
+        k = np.arange(1, r)[:, None]
+        i = np.arange(s)[None, :]
+        tabs.append(np.exp(-2j * np.pi * ((i * k) % m) / m).reshape(-1))
+    return tabs
+
+
+def low_freq(b, n, radices):
+    P = len(radices)
+    RL = radices[-1]
+    S = [n // int(np.prod(radices[:p + 1])) for p in range(P)]
+    rem, k = b.copy(), np.zeros_like(b)
+    mult = 1
+    for p in range(P - 1):
+        s = S[p] // RL
+        k += (rem // s) * mult
+        rem = rem % s
+        mult *= radices[p]
+    return k
+
+
+def model_fft(x, radices):
+    n = x.shape[0]
+    buf = x.astype(np.complex128).copy()
+    tabs = pass_tables(n, radices)
+    s = n
+    P = len(radices)
+    for p, r in enumerate(radices):
+        s //= r
+        m = r * s
+        b = np.arange(n // r)
+        npr = b & (s - 1)
+        base = (b // s) * m + npr
+        idx = base[:, None] + np.arange(r)[None, :] * s        # [butterfly][n]
+        a = buf[idx]
+        dft = np.exp(-2j * np.pi * np.outer(np.arange(r), np.arange(r)) / r)
+        out = a @ dft.T                                         # out[:, k] = sum_n a[:, n] W_r^{nk}
+        if p < P - 1:
+            tw = np.ones((n // r, r), np.complex128)
+            tw[:, 1:] = tabs[p].reshape(r - 1, s)[:, npr].T
+            buf[idx] = out * tw
+        else:
+            freq = low_freq(b, n, radices)[:, None] + (n // r) * np.arange(r)[None, :]
+            res = np.empty(n, np.complex128)
+            res[freq] = out
+            return res
+
+
+def registered_radix_sets():
+    lib = _lib.load()
+    seen = set()
+    for i in range(lib.psg_variant_count()):
+        name = lib.psg_variant_name(i).decode()
+        logn = lib.psg_variant_logn(i)
+        radices = tuple(int(v) for v in name.split("_")[1].split("x"))
+        seen.add((logn, radices))
+    return sorted(seen)
+
+
+@pytest.mark.parametrize("logn,radices", registered_radix_sets())
+def test_variant_index_algebra(logn, radices):
+    n = 1 << logn
+    assert int(np.prod(radices)) == n
+    rng = np.random.default_rng(logn)
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    got = model_fft(x, list(radices))
+    ref = np.fft.fft(x)
+    assert np.abs(got - ref).max() <= 1e-9 * np.abs(ref).max()
+
+
+def conflict_degree(n, radices, E=16):
+    """Worst number of half-warp lanes sharing an 8-byte bank, per pass, under pos + (pos >> 4)."""
+    T = n // E
+    s = n
+    out = []
+    for p, r in enumerate(radices):
+        s //= r
+        m = r * s
+        worst = 0
+        for i in range(E // r):
+            for half in range(0, min(T, 32), 16):
+                t = np.arange(half, min(half + 16, T))
+                b = t + i * T
+                base = b if p == 0 else (b // s) * m + (b & (s - 1))  # pass 0: its stores
+                for nn in range(r):
+                    pos = base + nn * s
+                    worst = max(worst, int(np.bincount((pos + (pos >> 4)) % 16).max()))
+        out.append(worst)
+    return out
+
+
+def test_padding_is_conflict_free_for_default_variants():
+    """pos + (pos >> 4): in every pass of every default plan the 16 lanes of a half-warp hit 16
+    distinct 8-byte banks."""
+    lib = _lib.load()
+    seen = set()
+    for i in range(lib.psg_variant_count()):
+        name = lib.psg_variant_name(i).decode()
+        key = (lib.psg_variant_logn(i), name[:3])
+        if key in seen:
+            continue  # only the first variant per (nfft, loader) is a default
+        seen.add(key)
+        radices = [int(v) for v in name.split("_")[1].split("x")]
+        assert conflict_degree(1 << key[0], radices) == [1] * len(radices), name

@@ -1,0 +1,305 @@
+"""GPU parity tests (run with ``-m gpu`` on a B200): the CUDA path through the C ABI against the
+golden fixtures made from the unmodified reference functions, and against the CPU oracle on the
+same seeded inputs.  Tolerances are the ones in tests/parity.py (north_star: PSD 1e-5 relative,
+1e-3 dB, frame indexing and bin order exact)."""
+import json
+import os
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+from tests.parity import assert_db_close, assert_psd_close, psd_errors
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+
+
+@pytest.fixture(scope="module")
+def dp():
+    from pyspectrogram_b200 import drfProc
+    return drfProc
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+# ---------------------------------------------------------------------------------------------
+# golden fixtures from the reference's own functions
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,noise_like", [
+    ("sti_r_64x7", False), ("sti_r_256x10x3", False), ("sti_r_1024x100", False), ("sti_r_4096x4", True),
+    ("sti_r_hdr2048", False), ("sti_r_impulse16", True), ("sti_r_tone1024", False)])
+def test_sti_proc_data_matches_reference_golden(dp, name, noise_like):
+    g = load(name)
+    f, sxx, med = dp.sti_proc_data(g["d1"], float(g["sr"]), int(g["nfft"]))
+    assert np.array_equal(f, g["f"])
+    assert sxx.dtype == g["sxx"].dtype and med.dtype == g["med"].dtype
+    assert sxx.shape == g["sxx"].shape and med.shape == g["med"].shape
+    assert_psd_close(sxx, g["sxx"], noise_like=noise_like, what=name)
+    assert_psd_close(med, g["med"], noise_like=noise_like, what=name + " median")
+    if "sxx_db" in g:
+        f2, sdb, mdb = dp.sti_proc_data_db(g["d1"], float(g["sr"]), int(g["nfft"]))
+        assert_db_close(sdb, g["sxx_db"], ref_lin=g["sxx"], what=name + " dB")
+        assert_db_close(mdb, g["med_db"], ref_lin=g["med"], what=name + " median dB")
+
+
+def test_complex128_input_returns_float64(dp):
+    g = load("sti_r_128x6_c128")
+    f, sxx, med = dp.sti_proc_data(g["d1"], float(g["sr"]), int(g["nfft"]))
+    assert sxx.dtype == np.float64 and med.dtype == np.float64 and np.array_equal(f, g["f"])
+    assert_psd_close(sxx, g["sxx"], noise_like=False, what="c128")
+
+
+def test_fraction_sample_rate(dp):
+    g = load("sti_r_fraction_sr")
+    f, sxx, med = dp.sti_proc_data(g["d1"], Fraction(int(g["sr_num"]), int(g["sr_den"])), int(g["nfft"]))
+    assert np.array_equal(f, g["f"])
+    assert_psd_close(sxx, g["sxx"], what="fraction sr")
+
+
+def test_zero_input_hits_db_floor(dp):
+    g = load("sti_r_zeros32")
+    f, sxx, med = dp.sti_proc_data(g["d1"], 1.0, 32)
+    assert np.array_equal(sxx, g["sxx"]) and not sxx.any()
+    f, sdb, mdb = dp.sti_proc_data_db(g["d1"], 1.0, 32)
+    assert np.abs(sdb - g["sxx_db"]).max() <= 1e-4  # -150.00002 dB
+    assert sdb.dtype == np.float32
+
+
+def test_non_power_of_two_fails_loudly(dp):
+    g = load("sti_r_96x5_nonpow2")
+    with pytest.raises(NotImplementedError):
+        dp.sti_proc_data(g["d1"], float(g["sr"]), 96)
+
+
+def test_short_input_raises_value_error(dp):
+    with pytest.raises(ValueError):
+        dp.sti_proc_data(np.zeros((100, 4), np.complex64), 1.0, 128)
+
+
+@pytest.mark.parametrize("name", ["sti_a_128x5x6x2", "sti_a_512x9x4"])
+def test_mode_a_matches_welch_golden(dp, name):
+    g = load(name)
+    f, sxx, med = dp.sti_proc_data(g["d1"], float(g["sr"]), int(g["nfft"]), integrate=True)
+    assert np.array_equal(f, g["f"]) and sxx.shape == g["sxx"].shape and sxx.dtype == np.float32
+    assert_psd_close(sxx, g["sxx"], noise_like=False, what=name)
+    assert_psd_close(med, g["med"], noise_like=False, what=name + " median")
+
+
+@pytest.mark.parametrize("name", ["proc_256", "proc_1024"])
+def test_proc_data_matches_reference_golden(dp, name):
+    g = load(name)
+    t_out, f, sxx, med = dp.proc_data(g["x"], float(g["sr"]), int(g["nfft"]), float(g["dt"]))
+    assert np.array_equal(t_out, g["t_out"]) and np.array_equal(f, g["f"])
+    assert sxx.shape == g["sxx"].shape and sxx.dtype == g["sxx"].dtype
+    assert_psd_close(sxx, g["sxx"], noise_like=False, what=name)
+    assert_psd_close(med, g["med"], noise_like=False, what=name + " median")
+
+
+# ---------------------------------------------------------------------------------------------
+# every kernel variant against the float64 oracle, device-resident path
+# ---------------------------------------------------------------------------------------------
+def _recording(rng, n, tone=0.123):
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)) * (1e-2 / np.sqrt(2))
+    x += 0.1 * np.exp(2j * np.pi * tone * np.arange(n))
+    return x.astype(np.complex64)
+
+
+def _oracle_columns(x, starts, nfft, nfr, hop):
+    from oracle import np_oracle
+    return np.stack([np_oracle.column_power(x[s:], nfft, nfr, hop) for s in starts])
+
+
+def _all_variants():
+    from pyspectrogram_b200 import engine
+    return engine.variants()
+
+
+def _variant_ids():
+    try:
+        return [v[0] for v in _all_variants()]
+    except Exception:
+        return []
+
+
+@pytest.mark.parametrize("variant", _variant_ids() or ["none"])
+def test_every_variant_matches_float64_oracle(torch, variant):
+    from pyspectrogram_b200 import engine
+    logn = dict(_all_variants())[variant]
+    nfft = 1 << logn
+    rng = np.random.default_rng(logn * 7 + 1)
+    nfr, ncol = 5, 7
+    n = nfft * (nfr * ncol + 3) + 11
+    x = _recording(rng, n)
+    starts = np.sort(rng.choice(n - nfr * nfft, ncol, replace=False)).astype(np.int64)
+    starts[0] = 0
+    starts[1] |= 1  # an odd (8-byte aligned only) start
+    starts[-1] = n - nfr * nfft  # a column that ends at the last sample
+    plan = engine.StiPlan(nfft)
+    dx, ds = torch.from_numpy(x).cuda(), torch.from_numpy(starts).cuda()
+    try:
+        engine.set_variant(variant)
+        lin, db = plan.run(dx, ds, nfr, nfft, want_lin=True, want_db=True)
+        torch.cuda.synchronize()
+        assert plan.variant == variant
+    finally:
+        engine.set_variant(None)
+    ref = _oracle_columns(x, starts, nfft, nfr, nfft)
+    got = lin.cpu().numpy()[0]
+    assert_psd_close(got.T, ref.T, noise_like=False, what=variant)
+    assert_db_close(db.cpu().numpy()[0].T, 10 * np.log10(ref.T.astype(np.float32) + np.float32(1e-15)),
+                    ref_lin=ref.T, what=variant + " dB")
+
+
+@pytest.mark.parametrize("nfft", [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536])
+@pytest.mark.parametrize("mode", ["R", "A", "S"])
+def test_default_path_all_sizes_and_modes(torch, nfft, mode):
+    from pyspectrogram_b200 import engine
+    rng = np.random.default_rng(nfft + ord(mode))
+    ncol = 5 if nfft >= 16384 else 9
+    nfr = {"R": 1, "A": 4, "S": 3}[mode]
+    hop = nfft - nfft // 8 if mode == "S" else nfft
+    n = (nfr * nfft) * ncol + 5 * nfft + 3
+    x = _recording(rng, n)
+    span = (nfr - 1) * hop + nfft
+    starts = engine.frame_starts(1, n, nfft, -(-span // nfft), ncol).astype(np.int64)
+    plan = engine.StiPlan(nfft)
+    lin, _ = plan.run(torch.from_numpy(x).cuda(), torch.from_numpy(starts).cuda(), nfr, hop)
+    ref = _oracle_columns(x, starts, nfft, nfr, hop)
+    assert_psd_close(lin.cpu().numpy()[0].T, ref.T, noise_like=False, what=f"nfft={nfft} mode {mode} {plan.variant}")
+
+
+def test_generic_kernel_cross_checks_tuned(torch):
+    from pyspectrogram_b200 import engine
+    rng = np.random.default_rng(5)
+    nfft, nfr, ncol = 4096, 6, 12
+    x = _recording(rng, nfft * nfr * ncol + 17)
+    starts = (np.arange(ncol) * nfft * nfr + (np.arange(ncol) % 2)).astype(np.int64)
+    plan = engine.StiPlan(nfft)
+    dx, ds = torch.from_numpy(x).cuda(), torch.from_numpy(starts).cuda()
+    a, _ = plan.run(dx, ds, nfr, nfft)
+    try:
+        engine.set_force_generic(True)
+        b, _ = plan.run(dx, ds, nfr, nfft)
+        assert plan.variant == "generic_radix2"
+    finally:
+        engine.set_force_generic(False)
+    e = psd_errors(a.cpu().numpy()[0].T, b.cpu().numpy()[0].T)
+    assert e["col"] <= 2e-6, e
+
+
+def test_split_columns_and_strided_subchannels(torch):
+    """Long integration (column split over several CTAs + finalize) on an interleaved
+    [sample][nsub] recording (strided LDG loader), against the oracle."""
+    from pyspectrogram_b200 import engine
+    from oracle import np_oracle
+    rng = np.random.default_rng(11)
+    nfft, nfr, ncol, nsub = 1024, 700, 3, 2
+    n = nfft * nfr * ncol + 9
+    x = (rng.standard_normal((n, nsub)) + 1j * rng.standard_normal((n, nsub))).astype(np.complex64) * np.float32(1e-2)
+    starts = (np.arange(ncol) * nfft * nfr + np.array([0, 5, 9])).astype(np.int64)
+    plan = engine.StiPlan(nfft)
+    lin, _ = plan.run(torch.from_numpy(x).cuda(), torch.from_numpy(starts * nsub).cuda(), nfr, nfft,
+                      sample_stride=nsub, sub_stride=1, nsub=nsub, in_scale=0.5)
+    got = lin.cpu().numpy()
+    for s in range(nsub):
+        ref = np.stack([np_oracle.column_power(x[st:, s] * 0.5, nfft, nfr) for st in starts])
+        assert_psd_close(got[s].T, ref.T, what=f"split sub {s}")
+
+
+def test_median_is_exact_order_statistic(torch):
+    from pyspectrogram_b200 import engine
+    rng = np.random.default_rng(3)
+    plan = engine.StiPlan(256)
+    for ncol in (1, 2, 3, 100, 101, 1000):
+        img = rng.random((2, ncol, 256), dtype=np.float32) ** 4
+        img[0, : ncol // 2, 7] = img[0, 0, 7]  # repeated values
+        lin, db = plan.median(torch.from_numpy(img).cuda(), want_lin=True, want_db=True)
+        ref = np.median(img, axis=1)
+        assert np.array_equal(lin.cpu().numpy(), ref), ncol
+        assert np.abs(db.cpu().numpy() - 10 * np.log10(ref + np.float32(1e-15))).max() <= 1e-4
+
+
+def test_epoch_sized_frame_starts_are_reproduced(torch):
+    """np.linspace(..., dtype=int) at ~1.7e17 quantises starts to multiples of 32 (SURVEY section 0,
+    trap 2): the table the kernel consumes is numpy's own, and columns land exactly there."""
+    from pyspectrogram_b200 import engine
+    meta = json.load(open(os.path.join(GOLDEN, "meta.json")))
+    case = [c for c in meta["frame_starts"] if c["st"] > 1e15][0]
+    n_st = engine.frame_starts(case["st"], case["en"], case["nfft"], case["nint"], case["ntime"])
+    assert [int(v) for v in n_st[:4]] == case["first"] and [int(v) for v in n_st[-4:]] == case["last"]
+    # a small recording addressed with epoch-sized absolute indices
+    nfft, nint, ntime = 256, 2, 16
+    st = 170000000000000000
+    en = st + 40 * nfft * nint + 77
+    starts = engine.frame_starts(st, en, nfft, nint, ntime)
+    rng = np.random.default_rng(9)
+    x = _recording(rng, en - st)
+    plan = engine.StiPlan(nfft)
+    rel = (starts - st).astype(np.int64)
+    lin, _ = plan.run(torch.from_numpy(x).cuda(), torch.from_numpy(rel).cuda(), nint, nfft)
+    ref = _oracle_columns(x, rel, nfft, nint, nfft)
+    assert_psd_close(lin.cpu().numpy()[0].T, ref.T, noise_like=False, what="epoch starts")
+
+
+def test_drfprocessor_iteration_with_fake_reader(dp):
+    from tests.fake_drf import FakeReader
+    from oracle import ref_port
+    rng = np.random.default_rng(21)
+    n, nsub = 1 << 18, 2
+    data = ((rng.standard_normal((n, nsub)) + 1j * rng.standard_normal((n, nsub))) * 3000).astype(np.complex64)
+    reader = FakeReader({"ch0": data}, sample_rate=1000000, first_sample=1_700_000_000 * 1000000, int16=True)
+    proc = dp.DrfProcessor("file", "/nonexistent", 3, 1024.0, 2.0, 20.0, reader=reader)
+    got = {}
+    proc.signals.iterated.connect(lambda i, tab, t, f, s, m: got.update(i=i, tab=tab, t=t, f=f, s=s, m=m))
+    time_ar, f, sdb, mdb = proc.iterate_once(0)
+    assert got["tab"] == 3 and got["s"] is sdb and sdb.shape == (1024, 20, nsub) and mdb.shape == (1024, nsub)
+    # the reference pipeline on the CPU: read_sti -> sti_proc_data -> dB
+    sr = proc.drfIn.sr_dict["ch0"]
+    s_samp = dp._time_to_sample(proc.bnds[0], sr)
+    e_samp = dp._time_to_sample(proc.bnds[1], sr)
+    oin = ref_port.read_sti_from_array(data, s_samp, e_samp, 1024, 2, 20, ref=2 ** 15.5,
+                                       first_sample=reader.first)
+    fr, sr_, mr = ref_port.sti_mode_r(oin[1].astype(np.complex64), Fraction(1000000, 1), 1024)
+    assert np.array_equal(f, fr)
+    assert_db_close(sdb, ref_port.to_dbfs(sr_), ref_lin=sr_, what="processor dB")
+    assert_db_close(mdb, ref_port.to_dbfs(mr), ref_lin=mr, what="processor median dB")
+
+
+def test_large_workload_properties(torch):
+    """Size-independent properties at a bench-like size (1 GiB of IQ, nfft=4096, nint=128):
+    Parseval (sum of the PSD column == mean windowed frame energy * N / sum(w)^2), a unit tone
+    lands at exactly bin nfft/2+k with 0 dBFS, and linearity in the input scale."""
+    from pyspectrogram_b200 import engine
+    nfft, nint, ntime = 4096, 128, 256
+    n = nfft * nint * ntime
+    dev = torch.device("cuda")
+    gen = torch.Generator(device=dev).manual_seed(1)
+    iq = torch.empty(n, dtype=torch.complex64, device=dev)
+    v = torch.view_as_real(iq)
+    v.normal_(0.0, 1e-2, generator=gen)
+    k = 37
+    ph = (torch.arange(n, device=dev, dtype=torch.int64) * k % nfft).to(torch.float32) * (2 * np.pi / nfft)
+    v[:, 0] += torch.cos(ph)
+    v[:, 1] += torch.sin(ph)
+    starts = torch.arange(ntime, device=dev, dtype=torch.int64) * (nfft * nint)
+    plan = engine.StiPlan(nfft)
+    lin, db = plan.run(iq, starts, nint, nfft, want_lin=True, want_db=True)
+    w = torch.from_numpy(plan.window_table().astype(np.float64)).to(dev)  # w / sum(w)
+    energy = (torch.view_as_real(iq).double().pow(2).sum(-1).reshape(ntime, nint, nfft) * w.pow(2)).sum(-1).mean(-1)
+    pars = lin[0].double().sum(-1)
+    assert float(((pars - nfft * energy).abs() / (nfft * energy)).max()) <= 1e-5
+    assert int(lin[0].argmax(-1).unique().item()) == nfft // 2 + k
+    assert float((db[0, :, nfft // 2 + k]).abs().max()) <= 2e-3  # unit tone + noise -> 0 dBFS
+    lin2, _ = plan.run(iq, starts, nint, nfft, in_scale=0.25)
+    assert float(((lin2 - lin * 0.0625).abs() / lin).max()) <= 1e-6

@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""Time every registered kernel variant on device-resident IQ (tuning aid; GPU box only).
+
+    python tools/kernel_sweep.py [--gb 2] [--reps 5] [--only tma12] [--out gpurun_out/sweep.json]
+
+Workload per variant: one channel of ``gb`` GB complex64, ntime=1000 bins, nint = full coverage
+(Mode A), dB image out.  Reports Gsamples/s and the fraction of the measured HBM peak using the
+algorithmic bytes of SURVEY.md section 8(d).
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gb", type=float, default=2.0)
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--ntime", type=int, default=1000)
+    ap.add_argument("--only", default="")
+    ap.add_argument("--odd", action="store_true", help="odd (8-byte aligned) frame starts")
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.json"))
+    args = ap.parse_args()
+    import torch
+    from pyspectrogram_b200 import engine
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        peak = 6650.0
+    dev = torch.device("cuda")
+    n = int(args.gb * 1e9 / 8)
+    iq = torch.empty(n + 8, dtype=torch.complex64, device=dev)
+    torch.view_as_real(iq).normal_(0.0, 1e-2)
+    rows = []
+    for name, logn in engine.variants() + [("generic", 12)]:
+        if args.only and args.only not in name:
+            continue
+        nfft = 1 << logn
+        nint = n // args.ntime // nfft
+        starts = engine.frame_starts(0, n, nfft, nint, args.ntime).astype(np.int64)
+        if args.odd:
+            starts |= 1
+        ds = torch.from_numpy(starts).to(dev)
+        plan = engine.StiPlan(nfft)
+        out = torch.empty((1, args.ntime, nfft), dtype=torch.float32, device=dev)
+        try:
+            if name == "generic":
+                engine.set_force_generic(True)
+            else:
+                engine.set_variant(name)
+            for _ in range(2):
+                plan.run(iq, ds, nint, nfft, want_lin=False, want_db=True, out_db=out)
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(args.reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                plan.run(iq, ds, nint, nfft, want_lin=False, want_db=True, out_db=out)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            used = plan.variant
+        finally:
+            engine.set_variant(None)
+            engine.set_force_generic(False)
+        ms = float(np.median(ts))
+        nbytes = 8 * nfft * nint * args.ntime + 4 * nfft * args.ntime
+        row = {"variant": used, "nfft": nfft, "nint": nint, "ms": ms, "best_ms": float(min(ts)),
+               "gsamples_s": nfft * nint * args.ntime / ms / 1e6, "gbs": nbytes / ms / 1e6,
+               "frac": nbytes / ms / 1e6 / peak}
+        rows.append(row)
+        print(f"{used:32s} nfft={nfft:6d} nint={nint:5d} {ms:8.3f} ms  {row['gsamples_s']:7.1f} Gs/s  "
+              f"{row['gbs']:7.0f} GB/s  {100 * row['frac']:5.1f}% of {peak:.0f}", flush=True)
+        del plan
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    json.dump(rows, open(args.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
