@@ -85,6 +85,7 @@ static const Variant g_variants[] = {
     make_variant<11, 16, 16, 16, 8, 1, 2, M, 3, 2, 2>("tma11_16x16x8_f2_s3x2"),
     make_variant<11, 16, 8, 16, 16, 1, 2, L, 1, 2, 2>("ldg11_8x16x16_f2"),
     make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 1, 2>("tma12_16x16x16_f1_s2x1"),
+    make_variant<12, 16, 16, 16, 16, 1, 1, M, 1, 2, 2>("tma12_16x16x16_f1_s1x2"),
     make_variant<12, 16, 16, 16, 16, 1, 1, M, 3, 2, 1>("tma12_16x16x16_f1_s3x2"),
     make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 2, 1>("tma12_16x16x16_f1_s2x2"),
     make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 2, 2>("ldg12_16x16x16_f1"),
@@ -305,18 +306,26 @@ extern "C" int psg_plan_window(const psg_plan* p, float* host_out) {
     return PSG_OK;
 }
 
-// per-pass twiddle tables for radices (r[0..np)) -- layout documented in sti_kernels.cuh
+// per-pass twiddle tables for radices (r[0..np)) -- layouts documented in sti_kernels.cuh:
+// pass 0 and mid passes with stride > 32 use the column layout, mid passes with stride <= 32 the
+// row layout (R+2 complex per row, entry k of row n' = W^{n'*k}).
 static std::vector<float2> build_pass_tables(int n, const int* r, int np) {
     std::vector<float2> t;
     int s = n;
     for (int p = 0; p + 1 < np; ++p) {
         s /= r[p];
         const int m = r[p] * s;
-        for (int k = 1; k < r[p]; ++k)
-            for (int i = 0; i < s; ++i) {
-                const double ang = -2.0 * M_PI * (double)((long long)i * k % m) / (double)m;
-                t.push_back(make_float2((float)cos(ang), (float)sin(ang)));
-            }
+        auto w = [&](int i, int k) {
+            const double ang = -2.0 * M_PI * (double)((long long)i * k % m) / (double)m;
+            return make_float2((float)cos(ang), (float)sin(ang));
+        };
+        if (p >= 1 && s <= 32) {
+            for (int i = 0; i < s; ++i)
+                for (int k = 0; k < r[p] + 2; ++k) t.push_back(k < r[p] ? w(i, k) : make_float2(0.f, 0.f));
+        } else {
+            for (int k = 1; k < r[p]; ++k)
+                for (int i = 0; i < s; ++i) t.push_back(w(i, k));
+        }
     }
     if (t.empty()) t.push_back(make_float2(1.f, 0.f));
     return t;

@@ -30,10 +30,15 @@
 //   n_rest = n_p*S_p + n', does the R_p-point DFT over n_p, multiplies output k_p by
 //   W_{R_p*S_p}^{n'*k_p} (skipped on the last pass) and stores it in place of n_p.  After the
 //   last pass pos = sum_q k_q*S_q holds frequency k = k_0 + R0*k_1 + R0*R1*k_2 + ...
-//   Shared-memory address of pos is pos + (pos >> 4) (one complex of padding per 16), which
-//   keeps the 64-bit accesses of every pass conflict-free for the plans used here.
-//   Twiddles come from per-pass tables  twp[(k-1)*S_p + n'] = exp(-2*pi*j*n'*k/(R_p*S_p))
-//   (lane-contiguous in n', so a warp's load is one line).
+//   Shared-memory address of pos is pos + 2*(pos >> 4) (two complex of padding per 16): 64-bit
+//   accesses of every pass stay conflict-free for the default plans, and a thread's run of
+//   consecutive positions in the last pass is 16-byte aligned, so it is read with LDS.128 (the
+//   LSU issues one warp instruction per 2 clocks whatever the width -- measured, tools/ubench).
+//   Twiddles W_{R_p*S_p}^{n'*k} come from per-pass tables in one of two layouts:
+//     column  twp[(k-1)*S_p + n']      lane-contiguous in n' (pass 0: loaded once into registers;
+//                                      mid passes with S_p > 32: coalesced LDG.64 per frame)
+//     row     twp[n'*(R_p+2) + k]      (mid passes with S_p <= 32) copied to shared memory once
+//                                      per CTA, a thread's R_p-1 twiddles are one LDS.128 run.
 #pragma once
 #include <stdint.h>
 #include "cplx.cuh"
@@ -69,7 +74,7 @@ PSG_DEV float2 ldg_stream(const float2* p) {
 
 PSG_DEV float power_to_db(float p, float eps) { return 10.0f * log10f(p + eps); }
 
-__host__ __device__ constexpr int psg_pad(int pos) { return pos + (pos >> 4); }
+__host__ __device__ constexpr int psg_pad(int pos) { return pos + 2 * (pos >> 4); }
 
 // ---- mbarrier / bulk-copy (TMA) primitives ------------------------------------------------------
 PSG_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -107,9 +112,13 @@ struct Plan {
     static_assert(R0 * R1 * R2 * R3 == N, "radices must multiply to N");
     static constexpr int RL = (P == 1) ? R0 : (P == 2) ? R1 : (P == 3) ? R2 : R3;  // last radix
     // offsets of the per-pass twiddle tables inside twp
+    static constexpr bool ROW1 = (P >= 3) && (S1 <= 32), ROW2 = (P >= 4) && (S2 <= 32);
     static constexpr int TW0 = 0;
     static constexpr int TW1 = TW0 + (R0 - 1) * S0;
-    static constexpr int TW2 = TW1 + (R1 - 1) * S1;
+    static constexpr int TW1_LEN = (P >= 3) ? (ROW1 ? S1 * (R1 + 2) : (R1 - 1) * S1) : 0;
+    static constexpr int TW2 = TW1 + TW1_LEN;
+    static constexpr int TW2_LEN = (P >= 4) ? (ROW2 ? S2 * (R2 + 2) : (R2 - 1) * S2) : 0;
+    static constexpr int TW_TOTAL = TW2 + TW2_LEN;
     // frequency of (last-pass butterfly b, output j): digit-reverse b, add (N/RL)*j
     PSG_DEV static int low_freq(int b) {
         int rem = b, k = 0;
@@ -120,38 +129,97 @@ struct Plan {
     }
 };
 
+// psg_pad(base + n*S) == psg_pad(base) + pad_off(n*S) for every (base, S) the passes generate
+// (n*S is either a multiple of 16 or added to a base whose low 4 bits leave room for it), so the
+// per-element part of every shared-memory address is a compile-time immediate.
+__host__ __device__ constexpr int pad_off(int d) { return d + 2 * (d >> 4); }
+
+// twiddles of one mid pass for this thread's butterflies -> registers (issued before the barrier
+// that precedes the pass, so their latency overlaps the wait).  ROW: from the shared-memory row
+// table with LDS.128; else coalesced LDG.64 from the column table in global memory (L1 hits).
+template <int E, int T, int R, int S, bool ROW>
+PSG_DEV void load_pass_tw(const float2* __restrict__ tab, int t, cf* tw) {
+    constexpr int NB = E / R;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        const int npr = (t + i * T) & (S - 1);
+        if constexpr (ROW) {
+            const float4* row = reinterpret_cast<const float4*>(tab + npr * (R + 2));
+            cf tmp[R];
+#pragma unroll
+            for (int k = 0; k < R / 2; ++k) {
+                const float4 v = row[k];
+                tmp[2 * k] = make_float2(v.x, v.y);
+                tmp[2 * k + 1] = make_float2(v.z, v.w);
+            }
+#pragma unroll
+            for (int k = 1; k < R; ++k) tw[i * (R - 1) + k - 1] = tmp[k];
+        } else {
+#pragma unroll
+            for (int k = 1; k < R; ++k) tw[i * (R - 1) + k - 1] = __ldg(tab + (k - 1) * S + npr);
+        }
+    }
+}
+
 // one in-place pass over the exchange buffer (p >= 1). LAST: accumulate |X|^2 instead of storing.
 template <int E, int T, int R, int S, bool LAST>
-PSG_DEV void smem_pass(float2* __restrict__ buf, const float2* __restrict__ twp, int t, float* acc) {
+PSG_DEV void smem_pass(float2* __restrict__ buf, const cf* tw, int t, float* acc) {
     constexpr int NB = E / R;  // butterflies per thread
     constexpr int M = R * S;   // size of the sub-DFT this pass splits
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
         const int b = t + i * T;
         const int npr = b & (S - 1);
-        const int base = (b / S) * M + npr;
+        float2* p = buf + psg_pad((b / S) * M + npr);
         cf a[R];
+        if constexpr (LAST && S == 1 && R >= 2) {
+            // R consecutive positions inside one padded 16-block: 16-byte aligned, read as float4
+            const float4* p4 = reinterpret_cast<const float4*>(p);
 #pragma unroll
-        for (int n = 0; n < R; ++n) a[n] = buf[psg_pad(base + n * S)];
+            for (int n = 0; n < R / 2; ++n) {
+                const float4 v = p4[n];
+                a[2 * n] = make_float2(v.x, v.y);
+                a[2 * n + 1] = make_float2(v.z, v.w);
+            }
+        } else {
+#pragma unroll
+            for (int n = 0; n < R; ++n) a[n] = p[pad_off(n * S)];
+        }
         dftR<R>(a);
         if constexpr (LAST) {
 #pragma unroll
             for (int k = 0; k < R; ++k) acc[i * R + k] = fmaf(a[k].x, a[k].x, fmaf(a[k].y, a[k].y, acc[i * R + k]));
         } else {
 #pragma unroll
-            for (int k = 1; k < R; ++k) a[k] = cmul(a[k], __ldg(twp + (k - 1) * S + npr));
+            for (int k = 1; k < R; ++k) a[k] = cmul(a[k], tw[i * (R - 1) + k - 1]);
 #pragma unroll
-            for (int k = 0; k < R; ++k) buf[psg_pad(base + k * S)] = a[k];
+            for (int k = 0; k < R; ++k) p[pad_off(k * S)] = a[k];
         }
     }
+}
+
+// The exchange between pass p (radix Ra, stride Sa) and pass p+1 (radix Rb) stays inside aligned
+// groups of Sa consecutive threads when both passes run one butterfly per thread (Ra == Rb == E):
+// pass p's threads [q*Sa, (q+1)*Sa) write exactly the blocks those same threads read in pass p+1.
+// With Sa <= 32 that group lives in one warp and __syncwarp() replaces the CTA barrier.
+template <int E, int Ra, int Rb, int Sa>
+struct WarpLocal {
+    static constexpr bool value = (Ra == E) && (Rb == E) && (Sa <= 32);
+};
+template <bool LOCAL>
+PSG_DEV void exchange_sync() {
+    if constexpr (LOCAL) __syncwarp();
+    else __syncthreads();
 }
 
 template <int LOGN, int E, int R0, int R1, int R2, int R3, int F, int LOADER, int STAGES, int XBUF>
 struct FusedCfg {
     static constexpr int N = 1 << LOGN, T = N / E, NT = F * T;
-    static constexpr int NPAD = psg_pad(N) + 1;
+    using PLN = Plan<N, R0, R1, R2, R3>;
+    static constexpr int NPAD = psg_pad(N) + 2;  // even: every group's buffer stays 16-byte aligned
     static constexpr int SLOT = N + 2;  // one frame + one element of alignment slack either side
-    static constexpr size_t bar_bytes = 64;
+    static constexpr int TWSM = (PLN::ROW1 ? PLN::TW1_LEN : 0) + (PLN::ROW2 ? PLN::TW2_LEN : 0);  // complex
+    static constexpr size_t bar_bytes = 64 + (size_t)TWSM * 8;
     static constexpr size_t stage_bytes = (LOADER == PSG_LOADER_TMA) ? (size_t)STAGES * F * SLOT * 8 : 0;
     static constexpr size_t xch_bytes = (size_t)F * XBUF * NPAD * 8;
     static constexpr size_t smem_bytes = bar_bytes + stage_bytes + xch_bytes;
@@ -164,9 +232,17 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
     using PL = Plan<N, R0, R1, R2, R3>;
     constexpr int P = PL::P;
     constexpr int NB0 = E / R0;
-    static_assert(P >= 2 || F * T >= 1, "");
+    static_assert(P >= 2, "tuned kernels need at least two passes");
+    static_assert(STAGES <= 8, "one mbarrier per stage in a 64-byte header");
+    constexpr bool L01 = WarpLocal<E, R0, R1, PL::S0>::value;
+    constexpr bool L12 = WarpLocal<E, R1, R2, PL::S1>::value;
+    constexpr bool L23 = WarpLocal<E, R2, R3, PL::S2>::value;
+    // true when no exchange needs a CTA barrier: every frame group then owns its buffers privately
+    constexpr bool ALL_LOCAL = L01 && (P < 3 || L12) && (P < 4 || L23);
+    static_assert(ALL_LOCAL ? (T <= 32) : true, "");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+    float2* twsm = reinterpret_cast<float2*>(smem_raw + 64);  // row-layout twiddle tables
     float2* stage = reinterpret_cast<float2*>(smem_raw + CF::bar_bytes);
     float2* xch = reinterpret_cast<float2*>(smem_raw + CF::bar_bytes + CF::stage_bytes);
 
@@ -195,60 +271,53 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
     }
     const long long fstep = (long long)gpc * a.hop_elems;
 
-    // ---- TMA producer state (thread 0 only) ----
-    auto issue = [&](int j) {  // copies of iteration j -> stage j % STAGES
+    // ---- TMA producer: thread 0 of every frame group fetches its own group's frames ----
+    // iteration pj -> stage pj % STAGES, slot g; every group leader arrives once per phase
+    long long pbase = fbase;  // producer cursor: frame of the next iteration to fetch
+    int pj = 0;               // next iteration to fetch
+    auto produce = [&]() {
         if constexpr (LOADER == PSG_LOADER_TMA) {
-            uint64_t* bar = bars + (j % STAGES);
-            float2* sbase = stage + (size_t)(j % STAGES) * F * SLOT;
-            uint32_t total = 0;
-            for (int gg = 0; gg < F; ++gg) {
-                const int cc = cs0 + gg / gpc;
-                const int kk = k0 + j * gpc + (gg % gpc);
-                if (cc < ncs && kk < k1) {
-                    const long long off = a.col_off[cc % a.ncol] + (long long)(cc / a.ncol) * a.sub_stride +
-                                          (long long)kk * a.hop_elems;
-                    total += N * 8 + ((reinterpret_cast<uintptr_t>(a.iq + off) & 8) ? 16 : 0);
-                }
+            uint64_t* bar = bars + (pj % STAGES);
+            if (col_ok && (k0 + pj * gpc + lane) < k1) {
+                const uintptr_t src = reinterpret_cast<uintptr_t>(a.iq + pbase);
+                const uint32_t bytes = N * 8 + ((src & 8) ? 16 : 0);
+                mbar_expect_tx(bar, bytes);
+                bulk_g2s(stage + ((size_t)(pj % STAGES) * F + g) * SLOT, reinterpret_cast<const void*>(src & ~(uintptr_t)15),
+                         bytes, bar);
+            } else {
+                mbar_expect_tx(bar, 0);
             }
-            mbar_expect_tx(bar, total);
-            for (int gg = 0; gg < F; ++gg) {
-                const int cc = cs0 + gg / gpc;
-                const int kk = k0 + j * gpc + (gg % gpc);
-                if (cc < ncs && kk < k1) {
-                    const long long off = a.col_off[cc % a.ncol] + (long long)(cc / a.ncol) * a.sub_stride +
-                                          (long long)kk * a.hop_elems;
-                    // a frame that is only 8-byte aligned is fetched from one element earlier
-                    // (16-byte aligned) and 16 bytes longer; the consumer skips the first element
-                    const uintptr_t src = reinterpret_cast<uintptr_t>(a.iq + off);
-                    const uint32_t bytes = N * 8 + ((src & 8) ? 16 : 0);
-                    bulk_g2s(sbase + (size_t)gg * SLOT, reinterpret_cast<const void*>(src & ~(uintptr_t)15), bytes,
-                             bar);
-                }
-            }
+            ++pj;
+            pbase += fstep;
         }
     };
+    if constexpr (CF::TWSM > 0) {
+        const float2* src = a.twp + (PL::ROW1 ? PL::TW1 : PL::TW2);
+        for (int i = tid; i < CF::TWSM; i += NT) twsm[i] = __ldg(src + i);
+    }
     if constexpr (LOADER == PSG_LOADER_TMA) {
         if (tid == 0) {
-            for (int s = 0; s < STAGES; ++s) mbar_init(bars + s, 1);
+            for (int s = 0; s < STAGES; ++s) mbar_init(bars + s, F);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        __syncthreads();
-        if (tid == 0)
-            for (int j = 0; j < STAGES - 1 && j < niter; ++j) issue(j);
+    }
+    if constexpr (LOADER == PSG_LOADER_TMA || CF::TWSM > 0) __syncthreads();
+    if constexpr (LOADER == PSG_LOADER_TMA) {
+        // prefetch distance: STAGES-1 iterations; a single stage is refilled right after its reads
+        if (t == 0)
+            for (int jj = 0; jj < (STAGES == 1 ? 1 : STAGES - 1) && jj < niter; ++jj) produce();
     }
 
     // loop-invariant tables in registers: window of this thread's E samples, pass-0 twiddles
     float w[E];
-    cf tw0[NB0][R0 - 1];
+    cf tw0[NB0 * (R0 - 1)];
 #pragma unroll
     for (int i = 0; i < NB0; ++i) {
         const int b = t + i * T;
 #pragma unroll
         for (int n = 0; n < R0; ++n) w[i * R0 + n] = __ldg(a.win + b + n * PL::S0);
-        if constexpr (P > 1) {
 #pragma unroll
-            for (int k = 1; k < R0; ++k) tw0[i][k - 1] = __ldg(a.twp + PL::TW0 + (k - 1) * PL::S0 + b);
-        }
+        for (int k = 1; k < R0; ++k) tw0[i * (R0 - 1) + k - 1] = __ldg(a.twp + PL::TW0 + (k - 1) * PL::S0 + b);
     }
     float acc[E];  // |X|^2 sums of this thread's E bins (scalar: registers are the scarce resource)
 #pragma unroll
@@ -260,58 +329,68 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
         cf x[E];
         // ---- pass 0: samples -> registers ----
         if constexpr (LOADER == PSG_LOADER_TMA) {
-            if (tid == 0 && j + STAGES - 1 < niter) issue(j + STAGES - 1);
+            // slot g of stage (j-1) % STAGES was last read by this group in iteration j-1; all its
+            // threads are past those reads (CTA barrier of iteration j-1, or the group is one warp)
+            if constexpr (ALL_LOCAL) __syncwarp();
+            if (STAGES > 1 && t == 0 && pj < niter) produce();
             mbar_wait(bars + (j % STAGES), (j / STAGES) & 1);
             const float2* sb = stage + ((size_t)(j % STAGES) * F + g) * SLOT +
                                ((reinterpret_cast<uintptr_t>(a.iq + fbase) >> 3) & 1);
+            if (valid) {
 #pragma unroll
-            for (int i = 0; i < NB0; ++i) {
-                const int b = t + i * T;
+                for (int i = 0; i < NB0; ++i)
 #pragma unroll
-                for (int n = 0; n < R0; ++n)
-                    x[i * R0 + n] = valid ? sb[b + n * PL::S0] : make_float2(0.f, 0.f);
+                    for (int n = 0; n < R0; ++n) x[i * R0 + n] = sb[t + i * T + n * PL::S0];
+            } else {
+#pragma unroll
+                for (int i = 0; i < E; ++i) x[i] = make_float2(0.f, 0.f);
             }
         } else {
             const float2* src = a.iq + fbase;
+            if (valid) {
 #pragma unroll
-            for (int i = 0; i < NB0; ++i) {
-                const int b = t + i * T;
+                for (int i = 0; i < NB0; ++i)
 #pragma unroll
-                for (int n = 0; n < R0; ++n)
-                    x[i * R0 + n] = valid ? ldg_stream(src + (long long)(b + n * PL::S0) * a.sample_stride)
-                                          : make_float2(0.f, 0.f);
+                    for (int n = 0; n < R0; ++n)
+                        x[i * R0 + n] = ldg_stream(src + (long long)(t + i * T + n * PL::S0) * a.sample_stride);
+            } else {
+#pragma unroll
+                for (int i = 0; i < E; ++i) x[i] = make_float2(0.f, 0.f);
             }
         }
 #pragma unroll
         for (int i = 0; i < E; ++i) x[i] = cscale(x[i], w[i]);
-        if constexpr (XBUF == 1 && P > 1) __syncthreads();  // previous frame's last pass done reading
+        // previous frame's last pass must be done reading before this buffer is overwritten
+        if constexpr (XBUF == 1) exchange_sync<ALL_LOCAL>();
 #pragma unroll
         for (int i = 0; i < NB0; ++i) {
             dftR<R0>(&x[i * R0]);
-            if constexpr (P == 1) {
+            float2* p0 = buf + psg_pad(t + i * T);
 #pragma unroll
-                for (int kk = 0; kk < R0; ++kk)
-                    acc[i * R0 + kk] = fmaf(x[i * R0 + kk].x, x[i * R0 + kk].x,
-                                            fmaf(x[i * R0 + kk].y, x[i * R0 + kk].y, acc[i * R0 + kk]));
-            } else {
-                const int b = t + i * T;
+            for (int kk = 1; kk < R0; ++kk) x[i * R0 + kk] = cmul(x[i * R0 + kk], tw0[i * (R0 - 1) + kk - 1]);
 #pragma unroll
-                for (int kk = 1; kk < R0; ++kk) x[i * R0 + kk] = cmul(x[i * R0 + kk], tw0[i][kk - 1]);
-#pragma unroll
-                for (int kk = 0; kk < R0; ++kk) buf[psg_pad(b + kk * PL::S0)] = x[i * R0 + kk];
-            }
+            for (int kk = 0; kk < R0; ++kk) p0[pad_off(kk * PL::S0)] = x[i * R0 + kk];
         }
-        if constexpr (P >= 2) {
-            __syncthreads();
-            smem_pass<E, T, R1, PL::S1, P == 2>(buf, a.twp + PL::TW1, t, acc);
+        {
+            cf tw1[(P >= 3) ? (E / R1) * (R1 - 1) : 1];
+            if constexpr (P >= 3) load_pass_tw<E, T, R1, PL::S1, PL::ROW1>(PL::ROW1 ? twsm : a.twp + PL::TW1, t, tw1);
+            exchange_sync<L01>();
+            if constexpr (LOADER == PSG_LOADER_TMA && STAGES == 1) {
+                static_assert(LOADER != PSG_LOADER_TMA || STAGES > 1 || !L01, "single stage needs a CTA barrier");
+                if (t == 0 && pj < niter) produce();  // the stage has been read by everyone: refill it
+            }
+            smem_pass<E, T, R1, PL::S1, P == 2>(buf, tw1, t, acc);
         }
         if constexpr (P >= 3) {
-            __syncthreads();
-            smem_pass<E, T, R2, PL::S2, P == 3>(buf, a.twp + PL::TW2, t, acc);
+            cf tw2[(P >= 4) ? (E / R2) * (R2 - 1) : 1];
+            if constexpr (P >= 4)
+                load_pass_tw<E, T, R2, PL::S2, PL::ROW2>(PL::ROW2 ? twsm + (PL::ROW1 ? PL::TW1_LEN : 0) : a.twp + PL::TW2, t, tw2);
+            exchange_sync<L12>();
+            smem_pass<E, T, R2, PL::S2, P == 3>(buf, tw2, t, acc);
         }
         if constexpr (P >= 4) {
-            __syncthreads();
-            smem_pass<E, T, R3, PL::S3, P == 4>(buf, a.twp + PL::TW2 + (R2 - 1) * PL::S2, t, acc);
+            exchange_sync<L23>();
+            smem_pass<E, T, R3, PL::S3, true>(buf, nullptr, t, acc);
         }
     }
 

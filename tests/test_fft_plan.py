@@ -86,28 +86,38 @@ def test_variant_index_algebra(logn, radices):
 
 
 def conflict_degree(n, radices, E=16):
-    """Worst number of half-warp lanes sharing an 8-byte bank, per pass, under pos + (pos >> 4)."""
+    """Worst number of lanes of one shared-memory phase that share a bank group, per pass, under
+    pos + 2*(pos >> 4).  64-bit accesses: 16 lanes per phase, 16 groups of 8 bytes.  The last pass
+    (S == 1) reads float4: 8 lanes per phase, 8 groups of 16 bytes."""
     T = n // E
     s = n
     out = []
     for p, r in enumerate(radices):
         s //= r
         m = r * s
+        wide = (p == len(radices) - 1) and s == 1 and r >= 2
+        lanes = 8 if wide else 16
         worst = 0
         for i in range(E // r):
-            for half in range(0, min(T, 32), 16):
-                t = np.arange(half, min(half + 16, T))
+            for ph in range(0, min(T, 32), lanes):
+                t = np.arange(ph, min(ph + lanes, T))
                 b = t + i * T
                 base = b if p == 0 else (b // s) * m + (b & (s - 1))  # pass 0: its stores
-                for nn in range(r):
+                for nn in range(0, r, 2 if wide else 1):
                     pos = base + nn * s
-                    worst = max(worst, int(np.bincount((pos + (pos >> 4)) % 16).max()))
+                    addr = pos + 2 * (pos >> 4)
+                    if wide:
+                        assert not (addr & 1).any()  # 16-byte aligned
+                        grp = (addr // 2) % 8
+                    else:
+                        grp = addr % 16
+                    worst = max(worst, int(np.bincount(grp).max()))
         out.append(worst)
     return out
 
 
 def test_padding_is_conflict_free_for_default_variants():
-    """pos + (pos >> 4): in every pass of every default plan the 16 lanes of a half-warp hit 16
+    """pos + 2 * (pos >> 4): in every pass of every default plan the 16 lanes of a half-warp hit 16
     distinct 8-byte banks."""
     lib = _lib.load()
     seen = set()
