@@ -137,9 +137,12 @@ int psg_set_force_generic(int on);
 /*
  * Kernel-variant table (tuning / cross-checks).  psg_set_variant(name) makes psg_sti_run prefer the
  * named variant for its FFT length when the layout allows it; NULL or "" restores the automatic
- * choice.  Process-wide.
+ * choice.  "split" selects the two-phase large-nfft path for nfft = 8192..65536.  Process-wide.
  */
 int psg_set_variant(const char* name);
+/* Bytes of the L2-resident scratch the large-nfft split path (nfft >= 16384) works through per
+ * chunk (default 64 MiB).  Process-wide; tuning / tests. */
+int psg_set_split_scratch(int64_t bytes);
 int psg_variant_count(void);
 const char* psg_variant_name(int index);
 int psg_variant_logn(int index);

@@ -27,6 +27,7 @@ static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_force_generic{0};
 static std::mutex g_variant_mu;
 static std::string g_variant_override;  // "" = automatic
+static std::atomic<long long> g_split_scratch_bytes{64ll << 20};  // L2-resident scratch of the split path
 
 static int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -98,13 +99,13 @@ static const Variant g_variants[] = {
 #undef M
 static const int g_nvariants = (int)(sizeof(g_variants) / sizeof(g_variants[0]));
 
-static const Variant* find_variant(int logn, int loader) {
+static const Variant* find_variant(int logn, int loader, bool tma_allowed) {
     {
         std::lock_guard<std::mutex> lk(g_variant_mu);
         if (!g_variant_override.empty()) {
             for (int i = 0; i < g_nvariants; ++i)
                 if (g_variant_override == g_variants[i].name && g_variants[i].logn == logn &&
-                    (g_variants[i].loader == PSG_LOADER_LDG || loader == PSG_LOADER_TMA))
+                    (g_variants[i].loader == PSG_LOADER_LDG || tma_allowed))
                     return &g_variants[i];
         }
     }
@@ -122,6 +123,21 @@ struct psg_plan {
     float2* d_tw = nullptr;
     float2* d_twp = nullptr;
     std::vector<float> h_win;
+    // large-nfft split path (nfft = r0 * 4096): first-pass twiddles, the 4096-point sub-transform's
+    // tables, the L2-sized scratch of first-pass outputs, the sub-spectra and carried sums
+    float2* d_twa = nullptr;
+    float* d_ones = nullptr;
+    float2* d_twp_sub = nullptr;
+    float2* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    float* d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    float* d_carry = nullptr;
+    size_t carry_bytes = 0;
+    long long* d_colb = nullptr;
+    size_t colb_bytes = 0;
+    std::vector<long long> h_colb;
+    long long colb_stride = 0;
     // scratch (grow-only; a plan is used by one host thread at a time)
     float* d_partial = nullptr;
     size_t partial_elems = 0;
@@ -191,13 +207,18 @@ extern "C" int psg_set_variant(const char* name) {
     std::lock_guard<std::mutex> lk(g_variant_mu);
     g_variant_override = name ? name : "";
     if (!g_variant_override.empty()) {
-        bool ok = false;
+        bool ok = g_variant_override == "split";
         for (int i = 0; i < g_nvariants; ++i) ok = ok || g_variant_override == g_variants[i].name;
         if (!ok) {
             g_variant_override.clear();
             return fail(PSG_ERR_ARG, "unknown kernel variant '%s'", name);
         }
     }
+    return PSG_OK;
+}
+extern "C" int psg_set_split_scratch(int64_t bytes) {
+    if (bytes < (1 << 20)) return fail(PSG_ERR_ARG, "psg_set_split_scratch: at least 1 MiB");
+    g_split_scratch_bytes.store(bytes);
     return PSG_OK;
 }
 extern "C" int psg_variant_count(void) { return g_nvariants; }
@@ -287,6 +308,13 @@ extern "C" int psg_plan_destroy(psg_plan* p) {
     cudaFree(p->d_win);
     cudaFree(p->d_tw);
     cudaFree(p->d_twp);
+    cudaFree(p->d_twa);
+    cudaFree(p->d_ones);
+    cudaFree(p->d_twp_sub);
+    cudaFree(p->d_scratch);
+    cudaFree(p->d_tmp);
+    cudaFree(p->d_carry);
+    cudaFree(p->d_colb);
     cudaFree(p->d_partial);
     cudaFree(p->d_gwork);
     cudaFree(p->d_gacc);
@@ -365,6 +393,192 @@ static int floor_pow2(int x) {
 
 extern "C" const char* psg_plan_variant(const psg_plan* p) { return p ? p->variant_name : ""; }
 
+// Launch one tuned fused kernel (+ the fixed-order finalize when columns are split over CTAs).
+// `a` carries everything but the launch geometry; min_iters = fewest frame iterations worth a
+// work item of its own (bounds the share of the per-item epilogue).
+static int launch_fused(psg_plan* p, const Variant* v, StiArgs a, int ncs, int frames_per_col, int min_iters,
+                        cudaStream_t st) {
+    const int vi = (int)(v - g_variants);
+    const int N = 1 << v->logn;
+    if (!p->attr_done[vi]) {
+        CUDA_TRY(cudaFuncSetAttribute(v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->smem));
+        int occ = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v->fn, v->threads, v->smem));
+        if (occ < 1) return fail(PSG_ERR_CUDA, "variant %s does not fit on an SM", v->name);
+        p->occ[vi] = occ;
+        p->attr_done[vi] = 1;
+    }
+    // geometry: gpc lanes per column inside a CTA, nsplit CTAs per column
+    const int F = v->F;
+    const int gpc = std::min(F, floor_pow2(frames_per_col));
+    const int cpc = F / gpc;
+    const int colblocks = (ncs + cpc - 1) / cpc;
+    const int iters = (frames_per_col + gpc - 1) / gpc;  // per column if one CTA did it all
+    const long long slots = (long long)p->sms * p->occ[vi];
+    const long long target = slots * 24;
+    int nsplit = (int)std::min<long long>((target + colblocks - 1) / colblocks, 1 << 20);
+    const int smin = (iters + 255) / 256, smax = std::max(1, iters / min_iters);
+    nsplit = std::max(smin, std::min(nsplit, smax));
+    nsplit = std::max(nsplit, 1);
+    int chunk = ((iters + nsplit - 1) / nsplit) * gpc;
+    nsplit = (frames_per_col + chunk - 1) / chunk;
+    a.gpc = gpc;
+    a.chunk = chunk;
+    a.nsplit = nsplit;
+    a.nfr = frames_per_col;
+    if (nsplit > 1) {
+        const size_t need = (size_t)ncs * nsplit * N;
+        size_t have_b = p->partial_elems * sizeof(float);
+        int rc = ensure_buffer((void**)&p->d_partial, &have_b, need * sizeof(float));
+        p->partial_elems = have_b / sizeof(float);
+        if (rc) return rc;
+        a.partial = p->d_partial;
+    }
+    const long long grid = (long long)colblocks * nsplit;
+    if (grid > 2147483647ll) return fail(PSG_ERR_ARG, "psg_sti_run: grid too large");
+    void* args[] = {(void*)&a};
+    CUDA_TRY(cudaLaunchKernel(v->fn, dim3((unsigned)grid), dim3(v->threads), args, v->smem, st));
+    g_launches++;
+    if (nsplit > 1) {
+        const size_t total = (size_t)ncs * N;
+        const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)p->sms * 16);
+        sti_finalize_kernel<<<blocks, 256, 0, st>>>(a.partial, nsplit, N, (size_t)ncs, a.scale, a.eps, a.out_lin,
+                                                    a.out_db);
+        g_launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return PSG_OK;
+}
+
+// upload (once per plan) the per-pass twiddle tables of a variant
+static int upload_pass_tables(const Variant* v, float2** d_out) {
+    int r[4], np = variant_radices(v, r);
+    std::vector<float2> t = build_pass_tables(1 << v->logn, r, np);
+    CUDA_TRY(cudaMalloc(d_out, sizeof(float2) * t.size()));
+    CUDA_TRY(cudaMemcpy(*d_out, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice));
+    return PSG_OK;
+}
+
+// nfft = r0 * 4096 (r0 = 2..16): streaming first pass -> L2-resident scratch -> tuned 4096-point
+// fused kernel over the r0 sub-sequences -> interleave.  See sti_kernels.cuh.
+static int run_split(psg_plan* p, StiArgs a, int ncs, int frames_per_col, cudaStream_t st) {
+    constexpr int N2 = 4096;
+    const int N = p->nfft, r0 = N / N2;
+    const Variant* v = find_variant(12, PSG_LOADER_TMA, true);
+    if (!v) return fail(PSG_ERR_UNSUPPORTED, "no 4096-point variant for the split path");
+    if (!p->d_twa) {
+        std::vector<float2> t((size_t)(r0 - 1) * N2);
+        for (int k = 1; k < r0; ++k)
+            for (int n = 0; n < N2; ++n) {
+                const double ang = -2.0 * M_PI * (double)((long long)n * k) / (double)N;
+                t[(size_t)(k - 1) * N2 + n] = make_float2((float)cos(ang), (float)sin(ang));
+            }
+        std::vector<float> ones(N2, 1.0f);
+        CUDA_TRY(cudaMalloc(&p->d_twa, sizeof(float2) * t.size()));
+        CUDA_TRY(cudaMemcpy(p->d_twa, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&p->d_ones, sizeof(float) * N2));
+        CUDA_TRY(cudaMemcpy(p->d_ones, ones.data(), sizeof(float) * N2, cudaMemcpyHostToDevice));
+        int rc = upload_pass_tables(v, &p->d_twp_sub);
+        if (rc) return rc;
+    }
+    snprintf(p->variant_name, sizeof(p->variant_name), "split%dx4096+%s", r0, v->name);
+    // chunking: whole columns per chunk when a column's frames fit the scratch, else one column at a
+    // time in frame blocks whose raw sums are carried in d_carry
+    const long long cap_frames = std::max<long long>(1, (long long)((size_t)g_split_scratch_bytes.load() / ((size_t)N * 8)));
+    const int cols_per_chunk = (int)std::max<long long>(1, std::min<long long>(ncs, cap_frames / frames_per_col));
+    const int frames_per_block = (int)std::min<long long>(frames_per_col, cap_frames);
+    const bool carried = frames_per_block < frames_per_col;
+    int rc = ensure_buffer((void**)&p->d_scratch, &p->scratch_bytes, (size_t)cols_per_chunk * frames_per_block * N * 8);
+    if (rc) return rc;
+    rc = ensure_buffer((void**)&p->d_tmp, &p->tmp_bytes, (size_t)cols_per_chunk * N * 4);
+    if (rc) return rc;
+    if (carried) {
+        rc = ensure_buffer((void**)&p->d_carry, &p->carry_bytes, (size_t)cols_per_chunk * N * 4);
+        if (rc) return rc;
+    }
+    // column c of a chunk starts at frame c * frames_per_block of the scratch (fixed stride, so the
+    // offset table phase B reads is uploaded once per geometry)
+    if (p->h_colb.size() != (size_t)cols_per_chunk || p->colb_stride != (long long)frames_per_block * N) {
+        rc = ensure_buffer((void**)&p->d_colb, &p->colb_bytes, (size_t)cols_per_chunk * 8);
+        if (rc) return rc;
+        p->colb_stride = (long long)frames_per_block * N;
+        p->h_colb.resize(cols_per_chunk);
+        for (int c = 0; c < cols_per_chunk; ++c) p->h_colb[c] = (long long)c * p->colb_stride;
+        CUDA_TRY(cudaMemcpyAsync(p->d_colb, p->h_colb.data(), (size_t)cols_per_chunk * 8, cudaMemcpyHostToDevice, st));
+    }
+    const float scale = a.scale, eps = a.eps;
+    float* out_lin = a.out_lin;
+    float* out_db = a.out_db;
+    for (int cs_lo = 0; cs_lo < ncs; cs_lo += cols_per_chunk) {
+        const int nc = std::min(cols_per_chunk, ncs - cs_lo);
+        for (int k_lo = 0; k_lo < frames_per_col; k_lo += frames_per_block) {
+            const int nf = std::min(frames_per_block, frames_per_col - k_lo);
+            // phase A
+            SplitArgs sa;
+            sa.iq = a.iq;
+            sa.sample_stride = a.sample_stride;
+            sa.sub_stride = a.sub_stride;
+            sa.hop_elems = a.hop_elems;
+            sa.col_off = a.col_off;
+            sa.ncol = a.ncol;
+            sa.cs_lo = cs_lo;
+            sa.ncs_chunk = nc;
+            sa.k_lo = k_lo;
+            sa.nfr_chunk = nf;
+            sa.col_frames = frames_per_block;
+            sa.win = p->d_win;
+            sa.twa = p->d_twa;
+            sa.scratch = p->d_scratch;
+            constexpr int FPB = 4;
+            const dim3 ga(N2 / 256, (unsigned)((nc * (long long)nf + FPB - 1) / FPB));
+            switch (r0) {
+                case 2: sti_split_pass_kernel<2, FPB><<<ga, 256, 0, st>>>(sa); break;
+                case 4: sti_split_pass_kernel<4, FPB><<<ga, 256, 0, st>>>(sa); break;
+                case 8: sti_split_pass_kernel<8, FPB><<<ga, 256, 0, st>>>(sa); break;
+                case 16: sti_split_pass_kernel<16, FPB><<<ga, 256, 0, st>>>(sa); break;
+                default: return fail(PSG_ERR_UNSUPPORTED, "split path: r0=%d", r0);
+            }
+            g_launches++;
+            // phase B: r0 * nc virtual columns of nf frames each
+            StiArgs b;
+            b.iq = p->d_scratch;
+            b.sample_stride = 1;
+            b.sub_stride = N2;
+            b.hop_elems = N;
+            b.col_off = p->d_colb;
+            b.ncol = nc;
+            b.nsub = r0;
+            b.win = p->d_ones;
+            b.tw = nullptr;
+            b.twp = p->d_twp_sub;
+            b.scale = 1.0f;
+            b.eps = eps;
+            b.out_lin = p->d_tmp;
+            b.out_db = nullptr;
+            b.partial = nullptr;
+            rc = launch_fused(p, v, b, nc * r0, nf, 8, st);
+            if (rc) return rc;
+            // phase C
+            InterleaveArgs ia;
+            ia.tmp = p->d_tmp;
+            ia.r0 = r0;
+            ia.ncs_chunk = nc;
+            ia.cs_lo = cs_lo;
+            ia.first = k_lo == 0;
+            ia.last = k_lo + nf >= frames_per_col;
+            ia.scale = scale;
+            ia.eps = eps;
+            ia.acc = carried ? p->d_carry : nullptr;
+            ia.out_lin = out_lin;
+            ia.out_db = out_db;
+            sti_interleave_kernel<<<dim3(N2 / 128, nc), 256, 0, st>>>(ia);
+            g_launches++;
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    return PSG_OK;
+}
+
 extern "C" int psg_sti_run(psg_plan* p, const void* iq_dev, int64_t sample_stride, int64_t sub_stride, int nsub,
                            const int64_t* col_offset_dev, int ncol, int frames_per_col, int64_t hop, float in_scale,
                            float eps, float* out_lin_dev, float* out_db_dev, void* cuda_stream) {
@@ -399,65 +613,39 @@ extern "C" int psg_sti_run(psg_plan* p, const void* iq_dev, int64_t sample_strid
     a.out_lin = out_lin_dev;
     a.out_db = out_db_dev;
     a.partial = nullptr;
+    a.gpc = 1;
+    a.chunk = frames_per_col;
+    a.nsplit = 1;
 
     const bool tma_ok = sample_stride == 1 && (reinterpret_cast<uintptr_t>(iq_dev) & 15) == 0;
     const Variant* v = nullptr;
     if (!g_force_generic.load()) {
-        v = find_variant(p->logn, tma_ok ? PSG_LOADER_TMA : PSG_LOADER_LDG);
-        if (!v && tma_ok) v = find_variant(p->logn, PSG_LOADER_LDG);
+        // measured (profiles/r01_sweep_variants_4GB.txt): the direct LDG loader wins for nfft <= 2048
+        // (several frames per CTA hide its latency), the TMA ring wins from 4096 up
+        const bool prefer_tma = tma_ok && p->logn >= 12;
+        v = find_variant(p->logn, prefer_tma ? PSG_LOADER_TMA : PSG_LOADER_LDG, tma_ok);
+        if (!v && tma_ok) v = find_variant(p->logn, PSG_LOADER_TMA, tma_ok);
+        if (!v) v = find_variant(p->logn, PSG_LOADER_LDG, tma_ok);
+        bool force_split = false;
+        {
+            std::lock_guard<std::mutex> lk(g_variant_mu);
+            force_split = g_variant_override == "split";
+        }
+        if (p->logn >= 13 && p->logn <= 16 && (force_split || !v)) return run_split(p, a, ncs, frames_per_col, st);
     }
 
     if (v) {
-        const int vi = (int)(v - g_variants);
-        if (!p->attr_done[vi]) {
-            CUDA_TRY(cudaFuncSetAttribute(v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->smem));
-            int occ = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v->fn, v->threads, v->smem));
-            if (occ < 1) return fail(PSG_ERR_CUDA, "variant %s does not fit on an SM", v->name);
-            p->occ[vi] = occ;
-            p->attr_done[vi] = 1;
-        }
         // per-pass twiddle tables: one layout per radix set; rebuilt when the variant changes
         if (strcmp(p->variant_name, v->name) != 0 || !p->d_twp) {
-            int r[4], np = variant_radices(v, r);
-            std::vector<float2> t = build_pass_tables(N, r, np);
             if (p->d_twp) { CUDA_TRY(cudaStreamSynchronize(st)); cudaFree(p->d_twp); p->d_twp = nullptr; }
-            CUDA_TRY(cudaMalloc(&p->d_twp, sizeof(float2) * t.size()));
-            CUDA_TRY(cudaMemcpy(p->d_twp, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice));
+            int rc = upload_pass_tables(v, &p->d_twp);
+            if (rc) return rc;
             snprintf(p->variant_name, sizeof(p->variant_name), "%s", v->name);
         }
         a.twp = p->d_twp;
-        // geometry: gpc lanes per column inside a CTA, nsplit CTAs per column
-        const int F = v->F;
-        const int gpc = std::min(F, floor_pow2(frames_per_col));
-        const int cpc = F / gpc;
-        const int colblocks = (ncs + cpc - 1) / cpc;
-        const int iters = (frames_per_col + gpc - 1) / gpc;  // per column if one CTA did it all
-        const long long slots = (long long)p->sms * p->occ[vi];
-        const long long target = slots * 24;
-        int nsplit = (int)std::min<long long>((target + colblocks - 1) / colblocks, 1 << 20);
-        const int smin = (iters + 255) / 256, smax = std::max(1, iters / 16);
-        nsplit = std::max(smin, std::min(nsplit, smax));
-        nsplit = std::max(nsplit, 1);
-        int chunk = ((iters + nsplit - 1) / nsplit) * gpc;
-        nsplit = (frames_per_col + chunk - 1) / chunk;
-        a.gpc = gpc;
-        a.chunk = chunk;
-        a.nsplit = nsplit;
-        if (nsplit > 1) {
-            const size_t need = (size_t)ncs * nsplit * N;
-            size_t have_b = p->partial_elems * sizeof(float);
-            int rc = ensure_buffer((void**)&p->d_partial, &have_b, need * sizeof(float));
-            p->partial_elems = have_b / sizeof(float);
-            if (rc) return rc;
-            a.partial = p->d_partial;
-        }
-        const long long grid = (long long)colblocks * nsplit;
-        if (grid > 2147483647ll) return fail(PSG_ERR_ARG, "psg_sti_run: grid too large");
-        void* args[] = {(void*)&a};
-        CUDA_TRY(cudaLaunchKernel(v->fn, dim3((unsigned)grid), dim3(v->threads), args, v->smem, st));
-        g_launches++;
-    } else {
+        return launch_fused(p, v, a, ncs, frames_per_col, 16, st);
+    }
+    {
         // generic radix-2 path
         snprintf(p->variant_name, sizeof(p->variant_name), "generic_radix2");
         const bool in_smem = N <= 16384;
@@ -525,10 +713,26 @@ extern "C" int psg_median_time(psg_plan* p, const float* img_dev, int nsub, int 
     if (!img_dev || (!med_lin_dev && !med_db_dev)) return fail(PSG_ERR_ARG, "psg_median_time: NULL pointer");
     if (nsub < 1 || ncol < 1 || nfft < 1) return fail(PSG_ERR_ARG, "psg_median_time: bad shape");
     CUDA_TRY(cudaSetDevice(p->device));
-    const size_t total = (size_t)nsub * nfft;
-    const int blocks = (int)((total + 127) / 128);
-    median_time_kernel<<<blocks, 128, 0, (cudaStream_t)cuda_stream>>>(img_dev, nsub, ncol, nfft, eps, med_lin_dev,
-                                                                      med_db_dev);
+    // bins per CTA: the widest tile of [ncol][bpc] keys that fits in shared memory and still gives
+    // every SM a CTA; when even 8 bins do not fit (ncol > ~6900) the columns are re-read from L2.
+    const size_t smem_max = 222 * 1024;
+    const size_t hdr = 3 * 256 * sizeof(unsigned);
+    int bpc = 8;
+    for (int cand = 32; cand >= 8; cand /= 2) {
+        const long long ctas = (long long)nsub * ((nfft + cand - 1) / cand);
+        if (hdr + (size_t)ncol * cand * 4 <= smem_max && (ctas >= p->sms || cand == 8)) { bpc = cand; break; }
+    }
+    const bool tiled = hdr + (size_t)ncol * bpc * 4 <= smem_max;
+    const size_t smem = hdr + (tiled ? (size_t)ncol * bpc * 4 : 0);
+    const void* fn = nullptr;
+    if (tiled) fn = bpc == 32 ? (const void*)median_time_kernel<32, true> : bpc == 16 ? (const void*)median_time_kernel<16, true>
+                                                                                      : (const void*)median_time_kernel<8, true>;
+    else fn = (const void*)median_time_kernel<8, false>;
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    const long long blocks = (long long)nsub * ((nfft + bpc - 1) / bpc);
+    void* args[] = {(void*)&img_dev, (void*)&nsub, (void*)&ncol, (void*)&nfft, (void*)&eps, (void*)&med_lin_dev,
+                    (void*)&med_db_dev};
+    CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(256), args, smem, (cudaStream_t)cuda_stream));
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return PSG_OK;

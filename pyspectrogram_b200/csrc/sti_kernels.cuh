@@ -505,9 +505,9 @@ __global__ void __launch_bounds__(256) sti_generic_kernel(const StiArgs a, int l
 }
 
 // ---- median over the time axis (np.median(sxx, axis=1), drfProc.py:401 / :451) ------------------
-// img [nsub][ncol][nfft]; one thread per (sub, bin): exact k-th order statistic by a 32-step
-// bisection on the IEEE bit pattern (monotone for the non-negative powers this path produces;
-// negative values are mapped to an order-preserving key as well), reads coalesced across bins.
+// img [nsub][ncol][nfft]; exact k-th order statistic per (sub, bin) by a 32-step bisection on the
+// IEEE bit pattern (monotone for the non-negative powers this path produces; negative values are
+// mapped to an order-preserving key as well).
 PSG_DEV unsigned f2key(float f) {
     const unsigned u = __float_as_uint(f);
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -516,34 +516,177 @@ PSG_DEV float key2f(unsigned k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-__global__ void __launch_bounds__(128) median_time_kernel(const float* __restrict__ img, int nsub, int ncol,
+// One CTA owns BPC adjacent bins of one sub-channel and all ncol columns of them; its 256 threads
+// are BPC bins x SL = 256/BPC column slices.  The [ncol][BPC] tile is read from global memory once
+// (rows of BPC floats, coalesced), converted to order-preserving keys and kept in shared memory
+// (TILED; ncol*BPC*4 bytes) -- or, when the tile does not fit, re-read from L2 on every step.
+// Each bisection step: every thread counts its slice, slice counts meet in shared memory, every
+// thread of a bin adds them up in the same order, so all SL threads of a bin walk the same path.
+template <int BPC, bool TILED>
+__global__ void __launch_bounds__(256) median_time_kernel(const float* __restrict__ img, int nsub, int ncol,
                                                           int nfft, float eps, float* med_lin, float* med_db) {
-    const size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (gid >= (size_t)nsub * nfft) return;
-    const int sub = (int)(gid / nfft), bin = (int)(gid - (size_t)sub * nfft);
-    const float* p = img + (size_t)sub * ncol * nfft + bin;
+    constexpr int SL = 256 / BPC;
+    extern __shared__ __align__(16) unsigned med_smem[];
+    unsigned* cnts = med_smem;                 // [2][SL][BPC] slice counts, ping-pong
+    unsigned* mins = med_smem + 2 * 256;       // [SL][BPC]
+    unsigned* tile = med_smem + 3 * 256;       // [ncol][BPC] keys (TILED)
+    const int tid = threadIdx.x;
+    const int b = tid % BPC, s = tid / BPC;
+    const int blocks_per_sub = (nfft + BPC - 1) / BPC;
+    const int sub = blockIdx.x / blocks_per_sub;
+    const int bin0 = (blockIdx.x - sub * blocks_per_sub) * BPC;
+    const int bin = bin0 + b;
+    const bool live = bin < nfft;
+    const float* p = img + (size_t)sub * ncol * nfft + (live ? bin : nfft - 1);
+    if constexpr (TILED) {
+        for (int c = s; c < ncol; c += SL) tile[c * BPC + b] = f2key(__ldg(p + (size_t)c * nfft));
+        __syncthreads();
+    }
+    auto key_at = [&](int c) -> unsigned {
+        if constexpr (TILED) return tile[c * BPC + b];
+        else return f2key(__ldg(p + (size_t)c * nfft));
+    };
     const int klo = (ncol - 1) >> 1;  // 0-based rank of the lower middle
     // largest key K with count(key < K) <= klo  ==> K is the klo-th smallest key
     unsigned key = 0;
     for (int bit = 31; bit >= 0; --bit) {
         const unsigned cand = key | (1u << bit);
-        int cnt = 0;
-        for (int c = 0; c < ncol; ++c) cnt += (f2key(__ldg(p + (size_t)c * nfft)) < cand) ? 1 : 0;
-        if (cnt <= klo) key = cand;
+        unsigned cnt = 0;
+        for (int c = s; c < ncol; c += SL) cnt += (key_at(c) < cand) ? 1u : 0u;
+        unsigned* cb = cnts + (bit & 1) * 256;
+        cb[s * BPC + b] = cnt;
+        __syncthreads();
+        unsigned tot = 0;
+#pragma unroll
+        for (int q = 0; q < SL; ++q) tot += cb[q * BPC + b];
+        if (tot <= (unsigned)klo) key = cand;
     }
     float m = key2f(key);
     if ((ncol & 1) == 0) {
         // upper middle: the same value if it is repeated, else the smallest value above it
-        int cnt_le = 0;
-        unsigned nxt = 0xffffffffu;
-        for (int c = 0; c < ncol; ++c) {
-            const unsigned kk = f2key(__ldg(p + (size_t)c * nfft));
-            cnt_le += (kk <= key) ? 1 : 0;
+        unsigned cnt_le = 0, nxt = 0xffffffffu;
+        for (int c = s; c < ncol; c += SL) {
+            const unsigned kk = key_at(c);
+            cnt_le += (kk <= key) ? 1u : 0u;
             if (kk > key && kk < nxt) nxt = kk;
         }
-        const float hi = (cnt_le >= klo + 2) ? m : key2f(nxt);
+        // buffer 1 was last read in step bit=1, and every thread is past the barrier of step bit=0
+        cnts[256 + s * BPC + b] = cnt_le;
+        mins[s * BPC + b] = nxt;
+        __syncthreads();
+        unsigned tot = 0, mn = 0xffffffffu;
+#pragma unroll
+        for (int q = 0; q < SL; ++q) {
+            tot += cnts[256 + q * BPC + b];
+            mn = min(mn, mins[q * BPC + b]);
+        }
+        const float hi = (tot >= (unsigned)klo + 2u) ? m : key2f(mn);
         m = (m + hi) * 0.5f;  // numpy: mean of the two middle values in float32
     }
-    if (med_lin) med_lin[gid] = m;
-    if (med_db) med_db[gid] = power_to_db(m, eps);
+    if (live && s == 0) {
+        const size_t o = (size_t)sub * nfft + bin;
+        if (med_lin) med_lin[o] = m;
+        if (med_db) med_db[o] = power_to_db(m, eps);
+    }
+}
+
+// ---- large nfft (N = R0 * 4096, R0 = 2..16): two phases through an L2-resident scratch -----------
+// A frame of N >= 16384 points does not fit the shared memory of one SM together with its
+// pipeline (65536 points are 512 KB).  The first radix-R0 pass therefore runs as its own streaming
+// kernel: thread n' loads x[n0*N2 + n'] (n0 < R0, N2 = N/R0 = 4096; coalesced across n'), applies
+// the window, does the R0-point DFT in registers, multiplies output k0 by W_N^{n'*k0} and stores
+// y[frame][k0][n'] to a scratch buffer sized to stay in the 126 MB L2.  The R0 sub-sequences
+// y[frame][k0][:] are independent 4096-point transforms whose outputs are the bins k0 + R0*k', so
+// phase B is the tuned 4096-point fused kernel run on the scratch with k0 in the role of the
+// sub-channel, and phase C interleaves the R0 partial spectra into the fftshifted column.
+struct SplitArgs {
+    const float2* iq;
+    long long sample_stride, sub_stride, hop_elems;
+    const long long* col_off;
+    int ncol;         // columns per sub-channel (global)
+    int cs_lo;        // first (sub*ncol + col) of this chunk
+    int ncs_chunk;    // column-subchannel pairs in this chunk
+    int k_lo, nfr_chunk;  // frame range [k_lo, k_lo + nfr_chunk) of every column in the chunk
+    int col_frames;       // scratch frames reserved per column (>= nfr_chunk)
+    const float* win;     // [N] w/sum(w)
+    const float2* twa;    // [(R0-1)][N2] W_N^{n'*k0}, k0 = 1..R0-1
+    float2* scratch;      // [ncs_chunk][col_frames][R0][N2]
+};
+
+PSG_DEV void stg_keep(float2* p, float2 v) {
+    asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+
+template <int R0, int FPB>
+__global__ void __launch_bounds__(256) sti_split_pass_kernel(const SplitArgs a) {
+    constexpr int N2 = 4096;
+    const int np = blockIdx.x * 256 + threadIdx.x;  // n'
+    const int nframes = a.ncs_chunk * a.nfr_chunk;
+    const int f0 = blockIdx.y * FPB;
+    float w[R0];
+    cf tw[R0 - 1];
+#pragma unroll
+    for (int n = 0; n < R0; ++n) w[n] = __ldg(a.win + n * N2 + np);
+#pragma unroll
+    for (int k = 1; k < R0; ++k) tw[k - 1] = __ldg(a.twa + (k - 1) * N2 + np);
+#pragma unroll 1
+    for (int f = f0; f < min(f0 + FPB, nframes); ++f) {
+        const int csl = f / a.nfr_chunk, kk = f - csl * a.nfr_chunk;
+        const int cs = a.cs_lo + csl;
+        const int col = cs % a.ncol, sub = cs / a.ncol;
+        const float2* src = a.iq + a.col_off[col] + (long long)sub * a.sub_stride + (long long)(a.k_lo + kk) * a.hop_elems;
+        cf x[R0];
+#pragma unroll
+        for (int n = 0; n < R0; ++n) x[n] = ldg_stream(src + (long long)(n * N2 + np) * a.sample_stride);
+#pragma unroll
+        for (int n = 0; n < R0; ++n) x[n] = cscale(x[n], w[n]);
+        dftR<R0>(x);
+        float2* dst = a.scratch + ((size_t)csl * a.col_frames + kk) * (R0 * N2) + np;
+        stg_keep(dst, x[0]);
+#pragma unroll
+        for (int k = 1; k < R0; ++k) stg_keep(dst + (size_t)k * N2, cmul(x[k], tw[k - 1]));
+    }
+}
+
+// Phase C: tmp[k0][c][(k' + N2/2) & (N2-1)] (the fftshifted sub-spectra phase B wrote, raw sums)
+// -> column c, output index (k0 + R0*k' + N/2) mod N.  One CTA moves KT consecutive k' of one column
+// through shared memory so that both sides are coalesced.  Columns whose frames span several
+// chunks accumulate in `acc` (first: assign, later: add) and are scaled / converted on the last.
+struct InterleaveArgs {
+    const float* tmp;
+    int r0, ncs_chunk, cs_lo;
+    int first, last;
+    float scale, eps;
+    float* acc;      // [ncs_chunk][N] raw sums carried between frame blocks (null when single block)
+    float* out_lin;  // [ncs_total][N] or null
+    float* out_db;
+};
+
+__global__ void __launch_bounds__(256) sti_interleave_kernel(const InterleaveArgs a) {
+    constexpr int N2 = 4096, KT = 128;
+    __shared__ float tile[16][KT + 1];
+    const int r0 = a.r0;
+    const int N = r0 * N2;
+    const int c = blockIdx.y;
+    const int kp0 = blockIdx.x * KT;
+    for (int e = threadIdx.x; e < r0 * KT; e += 256) {
+        const int k0 = e / KT, j = e - k0 * KT;
+        tile[k0][j] = a.tmp[((size_t)k0 * a.ncs_chunk + c) * N2 + (((kp0 + j) + N2 / 2) & (N2 - 1))];
+    }
+    __syncthreads();
+    const size_t ocol = (size_t)(a.cs_lo + c) * N;
+    for (int e = threadIdx.x; e < r0 * KT; e += 256) {
+        const int j = e / r0, k0 = e - j * r0;
+        const int k = k0 + r0 * (kp0 + j);
+        const int idx = (k + N / 2) & (N - 1);
+        float v = tile[k0][j];
+        if (!a.first) v += a.acc[(size_t)c * N + idx];
+        if (!a.last) {
+            a.acc[(size_t)c * N + idx] = v;
+        } else {
+            const float p = v * a.scale;
+            if (a.out_lin) a.out_lin[ocol + idx] = p;
+            if (a.out_db) a.out_db[ocol + idx] = power_to_db(p, a.eps);
+        }
+    }
 }

@@ -198,6 +198,11 @@ def set_variant(name=None):
     _lib.check(_lib.load().psg_set_variant(name.encode() if name else None))
 
 
+def set_split_scratch(nbytes: int):
+    """Scratch bytes per chunk of the large-nfft split path (default 64 MiB, sized for the L2)."""
+    _lib.check(_lib.load().psg_set_split_scratch(int(nbytes)))
+
+
 def set_force_generic(on: bool):
     _lib.check(_lib.load().psg_set_force_generic(1 if on else 0))
 

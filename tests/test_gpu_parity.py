@@ -179,6 +179,37 @@ def test_default_path_all_sizes_and_modes(torch, nfft, mode):
     assert_psd_close(lin.cpu().numpy()[0].T, ref.T, noise_like=False, what=f"nfft={nfft} mode {mode} {plan.variant}")
 
 
+@pytest.mark.parametrize("nfft,nfr,ncol,scratch_mb", [
+    (16384, 3, 7, 1),     # 8 scratch frames: 2 columns per chunk, 4 chunks (ragged tail)
+    (16384, 21, 2, 1),    # a column's frames exceed the scratch: frame blocks 8+8+5 carried and summed
+    (65536, 5, 3, 2),     # 4 scratch frames < 5 frames: carried, one column per chunk
+    (8192, 6, 5, 64),     # the split path cross-checks the fused 8192 kernel's size
+    (32768, 2, 4, 64)])
+def test_split_path_chunking(torch, nfft, nfr, ncol, scratch_mb):
+    """Large-nfft two-phase path (first pass -> L2 scratch -> 4096-point fused kernel -> interleave)
+    with the scratch shrunk so that every chunking branch runs; oracle = float64 numpy."""
+    from pyspectrogram_b200 import engine
+    rng = np.random.default_rng(nfft // 1024 + nfr)
+    n = nfft * nfr * ncol + 2 * nfft + 5
+    x = _recording(rng, n)
+    starts = (np.arange(ncol) * nfft * nfr + np.arange(ncol) % 3).astype(np.int64)
+    plan = engine.StiPlan(nfft)
+    try:
+        engine.set_split_scratch(scratch_mb << 20)
+        engine.set_variant("split")
+        lin, db = plan.run(torch.from_numpy(x).cuda(), torch.from_numpy(starts).cuda(), nfr, nfft,
+                           want_lin=True, want_db=True)
+        torch.cuda.synchronize()
+        assert plan.variant.startswith(f"split{nfft // 4096}x4096")
+    finally:
+        engine.set_variant(None)
+        engine.set_split_scratch(64 << 20)
+    ref = _oracle_columns(x, starts, nfft, nfr, nfft)
+    assert_psd_close(lin.cpu().numpy()[0].T, ref.T, noise_like=False, what=f"split {nfft}")
+    assert_db_close(db.cpu().numpy()[0].T, 10 * np.log10(ref.T.astype(np.float32) + np.float32(1e-15)),
+                    ref_lin=ref.T, what=f"split {nfft} dB")
+
+
 def test_generic_kernel_cross_checks_tuned(torch):
     from pyspectrogram_b200 import engine
     rng = np.random.default_rng(5)
@@ -218,15 +249,19 @@ def test_split_columns_and_strided_subchannels(torch):
 
 
 def test_median_is_exact_order_statistic(torch):
+    """np.median(sxx, axis=1) bit for bit: odd/even column counts, repeated values, every tile
+    width of the kernel (32/16/8 bins per CTA), bins that do not fill the last CTA, and the
+    untiled fallback for more columns than fit in shared memory."""
     from pyspectrogram_b200 import engine
     rng = np.random.default_rng(3)
     plan = engine.StiPlan(256)
-    for ncol in (1, 2, 3, 100, 101, 1000):
-        img = rng.random((2, ncol, 256), dtype=np.float32) ** 4
-        img[0, : ncol // 2, 7] = img[0, 0, 7]  # repeated values
+    for nsub, ncol, nfft in ((2, 1, 256), (2, 2, 256), (2, 3, 256), (2, 100, 256), (2, 101, 256), (2, 1000, 256),
+                             (1, 1000, 8192), (1, 3600, 512), (3, 7001, 40), (1, 6, 5)):
+        img = rng.random((nsub, ncol, nfft), dtype=np.float32) ** 4
+        img[0, : ncol // 2, 3] = img[0, 0, 3]  # repeated values
         lin, db = plan.median(torch.from_numpy(img).cuda(), want_lin=True, want_db=True)
         ref = np.median(img, axis=1)
-        assert np.array_equal(lin.cpu().numpy(), ref), ncol
+        assert np.array_equal(lin.cpu().numpy(), ref), (nsub, ncol, nfft)
         assert np.abs(db.cpu().numpy() - 10 * np.log10(ref + np.float32(1e-15))).max() <= 1e-4
 
 

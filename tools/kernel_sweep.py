@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--ntime", type=int, default=1000)
     ap.add_argument("--only", default="")
     ap.add_argument("--odd", action="store_true", help="odd (8-byte aligned) frame starts")
+    ap.add_argument("--big", action="store_true", help="only the large-nfft split path (8192..65536)")
+    ap.add_argument("--scratch-mb", type=int, default=0, help="split path scratch size")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.json"))
     args = ap.parse_args()
     import torch
@@ -38,7 +40,12 @@ def main():
     iq = torch.empty(n + 8, dtype=torch.complex64, device=dev)
     torch.view_as_real(iq).normal_(0.0, 1e-2)
     rows = []
-    for name, logn in engine.variants() + [("generic", 12)]:
+    if args.scratch_mb:
+        engine.set_split_scratch(args.scratch_mb << 20)
+    todo = engine.variants() + [("generic", 12)]
+    if args.big:
+        todo = [("split", 13), ("split", 14), ("split", 15), ("split", 16)]
+    for name, logn in todo:
         if args.only and args.only not in name:
             continue
         nfft = 1 << logn
