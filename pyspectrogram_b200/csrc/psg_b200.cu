@@ -76,15 +76,35 @@ static const Variant g_variants[] = {
     //            LOGN E  R0  R1  R2 R3  F  LD ST XB MINB
     make_variant<8, 16, 16, 16, 1, 1, 16, M, 3, 2, 2>("tma8_16x16_f16_s3x2"),
     make_variant<8, 16, 16, 16, 1, 1, 16, L, 1, 2, 2>("ldg8_16x16_f16"),
+    make_variant<8, 16, 16, 16, 1, 1, 8, L, 1, 2, 4>("ldg8_16x16_f8"),
+    make_variant<8, 16, 16, 16, 1, 1, 4, L, 1, 2, 8>("ldg8_16x16_f4"),
+    make_variant<8, 16, 16, 16, 1, 1, 2, L, 1, 2, 16>("ldg8_16x16_f2"),
     make_variant<9, 16, 2, 16, 16, 1, 8, M, 3, 2, 2>("tma9_2x16x16_f8_s3x2"),
     make_variant<9, 16, 16, 16, 2, 1, 8, M, 3, 2, 2>("tma9_16x16x2_f8_s3x2"),
     make_variant<9, 16, 2, 16, 16, 1, 8, L, 1, 2, 2>("ldg9_2x16x16_f8"),
+    make_variant<9, 8, 8, 8, 8, 1, 4, L, 1, 2, 4>("ldg9_8x8x8_f4"),
+    make_variant<9, 8, 8, 8, 8, 1, 8, L, 1, 2, 2>("ldg9_8x8x8_f8"),
+    make_variant<9, 8, 8, 8, 8, 1, 2, L, 1, 2, 8>("ldg9_8x8x8_f2"),
+    make_variant<9, 8, 8, 8, 8, 1, 1, L, 1, 2, 16>("ldg9_8x8x8_f1"),
+    make_variant<9, 16, 2, 16, 16, 1, 4, L, 1, 2, 4>("ldg9_2x16x16_f4"),
+    make_variant<9, 16, 2, 16, 16, 1, 2, L, 1, 2, 8>("ldg9_2x16x16_f2"),
+    make_variant<9, 8, 8, 8, 8, 1, 4, M, 3, 2, 4>("tma9_8x8x8_f4_s3x2"),
     make_variant<10, 16, 4, 16, 16, 1, 4, M, 3, 2, 2>("tma10_4x16x16_f4_s3x2"),
     make_variant<10, 16, 16, 16, 4, 1, 4, M, 3, 2, 2>("tma10_16x16x4_f4_s3x2"),
     make_variant<10, 16, 4, 16, 16, 1, 4, L, 1, 2, 2>("ldg10_4x16x16_f4"),
+    make_variant<10, 16, 4, 16, 16, 1, 2, L, 1, 2, 4>("ldg10_4x16x16_f2"),
+    make_variant<10, 16, 4, 16, 16, 1, 1, L, 1, 2, 8>("ldg10_4x16x16_f1"),
+    make_variant<10, 16, 4, 16, 16, 1, 1, M, 3, 2, 8>("tma10_4x16x16_f1_s3x2"),
+    make_variant<10, 16, 4, 16, 16, 1, 1, M, 2, 1, 8>("tma10_4x16x16_f1_s2x1"),
+    make_variant<10, 16, 4, 16, 16, 1, 8, L, 1, 2, 1>("ldg10_4x16x16_f8"),
     make_variant<11, 16, 8, 16, 16, 1, 2, M, 3, 2, 2>("tma11_8x16x16_f2_s3x2"),
     make_variant<11, 16, 16, 16, 8, 1, 2, M, 3, 2, 2>("tma11_16x16x8_f2_s3x2"),
     make_variant<11, 16, 8, 16, 16, 1, 2, L, 1, 2, 2>("ldg11_8x16x16_f2"),
+    make_variant<11, 16, 8, 16, 16, 1, 1, L, 1, 2, 4>("ldg11_8x16x16_f1"),
+    make_variant<11, 16, 8, 16, 16, 1, 1, L, 1, 1, 4>("ldg11_8x16x16_f1_x1"),
+    make_variant<11, 16, 8, 16, 16, 1, 1, M, 2, 1, 4>("tma11_8x16x16_f1_s2x1"),
+    make_variant<11, 16, 8, 16, 16, 1, 1, M, 3, 2, 4>("tma11_8x16x16_f1_s3x2"),
+    make_variant<11, 16, 8, 16, 16, 1, 4, L, 1, 2, 1>("ldg11_8x16x16_f4"),
     make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 1, 2>("tma12_16x16x16_f1_s2x1"),
     make_variant<12, 16, 16, 16, 16, 1, 1, M, 1, 2, 2>("tma12_16x16x16_f1_s1x2"),
     make_variant<12, 16, 16, 16, 16, 1, 1, M, 3, 2, 1>("tma12_16x16x16_f1_s3x2"),
@@ -99,19 +119,30 @@ static const Variant g_variants[] = {
 #undef M
 static const int g_nvariants = (int)(sizeof(g_variants) / sizeof(g_variants[0]));
 
-static const Variant* find_variant(int logn, int loader, bool tma_allowed) {
+static const Variant* variant_by_name(const char* name) {
+    for (int i = 0; i < g_nvariants; ++i)
+        if (strcmp(name, g_variants[i].name) == 0) return &g_variants[i];
+    return nullptr;
+}
+
+// Default variant per FFT length, from the measured sweeps (profiles/r01_sweep_*.txt, 4 GB of IQ,
+// full-coverage Mode A): small CTAs (one frame group) win from 512 up, the TMA ring with two
+// stages and one exchange buffer wins from 1024 up, the direct LDG loader below that.
+static const char* const g_default_tma[] = {"ldg8_16x16_f8", "ldg9_8x8x8_f1", "tma10_4x16x16_f1_s2x1",
+                                            "tma11_8x16x16_f1_s2x1", "tma12_16x16x16_f1_s2x1", "tma13_8x8x8x16_f1_s2x1"};
+static const char* const g_default_ldg[] = {"ldg8_16x16_f8", "ldg9_8x8x8_f1", "ldg10_4x16x16_f1",
+                                            "ldg11_8x16x16_f1", "ldg12_16x16x16_f1", "ldg13_2x16x16x16_f1"};
+
+static const Variant* pick_variant(int logn, bool tma_ok) {
     {
         std::lock_guard<std::mutex> lk(g_variant_mu);
         if (!g_variant_override.empty()) {
-            for (int i = 0; i < g_nvariants; ++i)
-                if (g_variant_override == g_variants[i].name && g_variants[i].logn == logn &&
-                    (g_variants[i].loader == PSG_LOADER_LDG || tma_allowed))
-                    return &g_variants[i];
+            const Variant* v = variant_by_name(g_variant_override.c_str());
+            if (v && v->logn == logn && (v->loader == PSG_LOADER_LDG || tma_ok)) return v;
         }
     }
-    for (int i = 0; i < g_nvariants; ++i)
-        if (g_variants[i].logn == logn && g_variants[i].loader == loader) return &g_variants[i];
-    return nullptr;
+    if (logn < 8 || logn > 13) return nullptr;
+    return variant_by_name((tma_ok ? g_default_tma : g_default_ldg)[logn - 8]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -464,7 +495,7 @@ static int upload_pass_tables(const Variant* v, float2** d_out) {
 static int run_split(psg_plan* p, StiArgs a, int ncs, int frames_per_col, cudaStream_t st) {
     constexpr int N2 = 4096;
     const int N = p->nfft, r0 = N / N2;
-    const Variant* v = find_variant(12, PSG_LOADER_TMA, true);
+    const Variant* v = variant_by_name(g_default_tma[12 - 8]);
     if (!v) return fail(PSG_ERR_UNSUPPORTED, "no 4096-point variant for the split path");
     if (!p->d_twa) {
         std::vector<float2> t((size_t)(r0 - 1) * N2);
@@ -620,12 +651,7 @@ extern "C" int psg_sti_run(psg_plan* p, const void* iq_dev, int64_t sample_strid
     const bool tma_ok = sample_stride == 1 && (reinterpret_cast<uintptr_t>(iq_dev) & 15) == 0;
     const Variant* v = nullptr;
     if (!g_force_generic.load()) {
-        // measured (profiles/r01_sweep_variants_4GB.txt): the direct LDG loader wins for nfft <= 2048
-        // (several frames per CTA hide its latency), the TMA ring wins from 4096 up
-        const bool prefer_tma = tma_ok && p->logn >= 12;
-        v = find_variant(p->logn, prefer_tma ? PSG_LOADER_TMA : PSG_LOADER_LDG, tma_ok);
-        if (!v && tma_ok) v = find_variant(p->logn, PSG_LOADER_TMA, tma_ok);
-        if (!v) v = find_variant(p->logn, PSG_LOADER_LDG, tma_ok);
+        v = pick_variant(p->logn, tma_ok);
         bool force_split = false;
         {
             std::lock_guard<std::mutex> lk(g_variant_mu);

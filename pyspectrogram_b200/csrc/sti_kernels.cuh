@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
     constexpr int P = PL::P;
     constexpr int NB0 = E / R0;
     static_assert(P >= 2, "tuned kernels need at least two passes");
+    static_assert(R0 <= E && R1 <= E && R2 <= E && R3 <= E, "a thread must hold a whole butterfly");
     static_assert(STAGES <= 8, "one mbarrier per stage in a 64-byte header");
     constexpr bool L01 = WarpLocal<E, R0, R1, PL::S0>::value;
     constexpr bool L12 = WarpLocal<E, R1, R2, PL::S1>::value;
