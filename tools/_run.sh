@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-(timeout 600 python -m pytest tests -m gpu -x -q -k "every_variant" 2>&1 | tail -5)
-for o in ldg8 ldg9 10_ 11_; do timeout 300 python tools/kernel_sweep.py --gb 4 --reps 5 --only $o 2>&1 | grep nfft; done | tee gpurun_out/sweep_small2.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
+echo rc=$?; tail -c 2500 gpurun_out/bench_n2.json; tail -5 gpurun_out/bench_n2.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 1 > gpurun_out/bench_ref_n2.json 2> gpurun_out/bench_ref_n2.err
+echo rc=$?; tail -c 1500 gpurun_out/bench_ref_n2.json; tail -3 gpurun_out/bench_ref_n2.err
