@@ -141,7 +141,7 @@ int psg_set_force_generic(int on);
  */
 int psg_set_variant(const char* name);
 /* Bytes of the L2-resident scratch the large-nfft split path (nfft >= 16384) works through per
- * chunk (default 64 MiB).  Process-wide; tuning / tests. */
+ * chunk (default 2 GiB cap; only what a call needs is allocated).  Process-wide; tuning / tests. */
 int psg_set_split_scratch(int64_t bytes);
 int psg_variant_count(void);
 const char* psg_variant_name(int index);

@@ -27,7 +27,10 @@ static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_force_generic{0};
 static std::mutex g_variant_mu;
 static std::string g_variant_override;  // "" = automatic
-static std::atomic<long long> g_split_scratch_bytes{64ll << 20};  // L2-resident scratch of the split path
+// Scratch cap of the large-nfft split path.  Measured (profiles/r01_sweep_split_scratch*.txt): L2-sized
+// chunks (16..128 MiB) lose more to the three short dependent launches per chunk than they save in
+// HBM traffic; 1..4 GiB chunks run each phase at its own roofline.
+static std::atomic<long long> g_split_scratch_bytes{2048ll << 20};
 
 static int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -54,7 +57,7 @@ struct Variant {
     const void* fn;
 };
 
-template <int LOGN, int E, int R0, int R1, int R2, int R3, int F, int LOADER, int STAGES, int XBUF, int MINB>
+template <int LOGN, int E, int R0, int R1, int R2, int R3, int F, int LOADER, int STAGES, int XBUF, int MINB, int PFL2 = 0>
 static Variant make_variant(const char* name) {
     using CF = FusedCfg<LOGN, E, R0, R1, R2, R3, F, LOADER, STAGES, XBUF>;
     Variant v;
@@ -65,7 +68,7 @@ static Variant make_variant(const char* name) {
     v.threads = CF::NT;
     v.minb = MINB;
     v.smem = CF::smem_bytes;
-    v.fn = (const void*)sti_fused_kernel<LOGN, E, R0, R1, R2, R3, F, LOADER, STAGES, XBUF, MINB>;
+    v.fn = (const void*)sti_fused_kernel<LOGN, E, R0, R1, R2, R3, F, LOADER, STAGES, XBUF, MINB, PFL2>;
     return v;
 }
 
@@ -94,6 +97,8 @@ static const Variant g_variants[] = {
     make_variant<10, 16, 4, 16, 16, 1, 4, L, 1, 2, 2>("ldg10_4x16x16_f4"),
     make_variant<10, 16, 4, 16, 16, 1, 2, L, 1, 2, 4>("ldg10_4x16x16_f2"),
     make_variant<10, 16, 4, 16, 16, 1, 1, L, 1, 2, 8>("ldg10_4x16x16_f1"),
+    make_variant<10, 16, 4, 16, 16, 1, 1, L, 1, 2, 8, 2>("ldg10_4x16x16_f1_pf2"),
+    make_variant<10, 16, 4, 16, 16, 1, 1, L, 1, 1, 8, 4>("ldg10_4x16x16_f1_x1_pf4"),
     make_variant<10, 16, 4, 16, 16, 1, 1, M, 3, 2, 8>("tma10_4x16x16_f1_s3x2"),
     make_variant<10, 16, 4, 16, 16, 1, 1, M, 2, 1, 8>("tma10_4x16x16_f1_s2x1"),
     make_variant<10, 16, 4, 16, 16, 1, 8, L, 1, 2, 1>("ldg10_4x16x16_f8"),
@@ -111,6 +116,10 @@ static const Variant g_variants[] = {
     make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 2, 1>("tma12_16x16x16_f1_s2x2"),
     make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 2, 2>("ldg12_16x16x16_f1"),
     make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 1, 2>("ldg12_16x16x16_f1_x1"),
+    make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 1, 2, 1>("ldg12_16x16x16_f1_x1_pf1"),
+    make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 1, 2, 2>("ldg12_16x16x16_f1_x1_pf2"),
+    make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 2, 2, 2>("ldg12_16x16x16_f1_x2_pf2"),
+    make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 1, 2, 4>("ldg12_16x16x16_f1_x1_pf4"),
     make_variant<13, 16, 2, 16, 16, 16, 1, M, 2, 1, 1>("tma13_2x16x16x16_f1_s2x1"),
     make_variant<13, 16, 8, 8, 8, 16, 1, M, 2, 1, 1>("tma13_8x8x8x16_f1_s2x1"),
     make_variant<13, 16, 2, 16, 16, 16, 1, L, 1, 1, 1>("ldg13_2x16x16x16_f1"),

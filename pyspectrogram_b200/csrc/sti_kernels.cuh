@@ -225,7 +225,7 @@ struct FusedCfg {
     static constexpr size_t smem_bytes = bar_bytes + stage_bytes + xch_bytes;
 };
 
-template <int LOGN, int E, int R0, int R1, int R2, int R3, int F, int LOADER, int STAGES, int XBUF, int MINB>
+template <int LOGN, int E, int R0, int R1, int R2, int R3, int F, int LOADER, int STAGES, int XBUF, int MINB, int PFL2 = 0>
 __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(const StiArgs a) {
     using CF = FusedCfg<LOGN, E, R0, R1, R2, R3, F, LOADER, STAGES, XBUF>;
     constexpr int N = CF::N, T = CF::T, NT = CF::NT, NPAD = CF::NPAD, SLOT = CF::SLOT;
@@ -348,6 +348,14 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
             }
         } else {
             const float2* src = a.iq + fbase;
+            if constexpr (PFL2 > 0) {
+                // contiguous frames: pull the frame PFL2 iterations ahead into L2 so that the LDGs of
+                // that iteration see L2 latency, not DRAM latency (no registers, no shared memory)
+                if (t == 0 && a.sample_stride == 1 && col_ok && (k0 + (j + PFL2) * gpc + lane) < k1) {
+                    const uintptr_t pa = reinterpret_cast<uintptr_t>(src + (long long)PFL2 * fstep) & ~(uintptr_t)15;
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pa), "r"(N * 8 + 16) : "memory");
+                }
+            }
             if (valid) {
 #pragma unroll
                 for (int i = 0; i < NB0; ++i)

@@ -199,7 +199,7 @@ def set_variant(name=None):
 
 
 def set_split_scratch(nbytes: int):
-    """Scratch bytes per chunk of the large-nfft split path (default 64 MiB, sized for the L2)."""
+    """Scratch bytes per chunk of the large-nfft split path (default cap 2 GiB)."""
     _lib.check(_lib.load().psg_set_split_scratch(int(nbytes)))
 
 

@@ -203,7 +203,7 @@ def test_split_path_chunking(torch, nfft, nfr, ncol, scratch_mb):
         assert plan.variant.startswith(f"split{nfft // 4096}x4096")
     finally:
         engine.set_variant(None)
-        engine.set_split_scratch(64 << 20)
+        engine.set_split_scratch(2048 << 20)
     ref = _oracle_columns(x, starts, nfft, nfr, nfft)
     assert_psd_close(lin.cpu().numpy()[0].T, ref.T, noise_like=False, what=f"split {nfft}")
     assert_db_close(db.cpu().numpy()[0].T, 10 * np.log10(ref.T.astype(np.float32) + np.float32(1e-15)),

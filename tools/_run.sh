@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
-echo rc=$?; tail -c 2500 gpurun_out/bench_n2.json; tail -5 gpurun_out/bench_n2.err
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 1 > gpurun_out/bench_ref_n2.json 2> gpurun_out/bench_ref_n2.err
-echo rc=$?; tail -c 1500 gpurun_out/bench_ref_n2.json; tail -3 gpurun_out/bench_ref_n2.err
+(timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5)
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+timeout 600 python bench.py > gpurun_out/bench3.json 2> gpurun_out/bench3.err; echo rc=$?; cat gpurun_out/bench3.json; tail -3 gpurun_out/bench3.err
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench3_ref.json 2> gpurun_out/bench3_ref.err; echo rc=$?; cat gpurun_out/bench3_ref.json; tail -3 gpurun_out/bench3_ref.err

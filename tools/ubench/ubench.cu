@@ -50,6 +50,13 @@ __global__ void __launch_bounds__(256) ks(float2* out, long long* clk) {
             if (MODE == 1) { float4 v; const unsigned sb = (unsigned)__cvta_generic_to_shared(&sm[(2 * threadIdx.x + i * 512) % (256 * 16)]);
                              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sb)); acc4.x += v.x; acc4.y += v.w; }
             if (MODE == 2) { asm volatile("st.shared.v2.f32 [%0], {%1,%2};" :: "r"(sa), "f"(acc.x), "f"(acc.y)); }
+            if (MODE == 4) { float v; const unsigned sc = (unsigned)__cvta_generic_to_shared(reinterpret_cast<float*>(sm) + (threadIdx.x + i * 256 + (it & 1)) % (256 * 32));
+                             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(sc)); acc.x += v; }
+            if (MODE == 5) { const unsigned sb = (unsigned)__cvta_generic_to_shared(&sm[(2 * threadIdx.x + i * 512) % (256 * 16)]);
+                             asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(sb), "f"(acc.x), "f"(acc.y), "f"(acc.x), "f"(acc.y)); }
+            if (MODE == 6) { float4 v; const unsigned sb = (unsigned)__cvta_generic_to_shared(&sm[(2 * threadIdx.x + i * 512) % (256 * 16)]);
+                             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sb));
+                             asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(sb), "f"(v.y), "f"(v.x), "f"(v.w), "f"(v.z)); }
             if (MODE == 3) { float2 v; asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(sa));
                              asm volatile("st.shared.v2.f32 [%0], {%1,%2};" :: "r"(sa), "f"(v.y), "f"(v.x)); }
         }
@@ -75,7 +82,7 @@ void run(const char* name, F launch, int instr_per_iter_elem, int blocks_per_sm)
 }
 
 int main() {
-    for (int bps : {2, 4}) {
+    for (int bps : {2}) {
         run("FFMA (dep chain +1)", [](float2* o, long long* c, int b) { k<0><<<148 * b, 256>>>(o, 0.5f, c); }, 2, bps);
         run("FFMA scalar", [](float2* o, long long* c, int b) { k<5><<<148 * b, 256>>>(o, 0.5f, c); }, 1, bps);
         run("FFMA2", [](float2* o, long long* c, int b) { k<1><<<148 * b, 256>>>(o, 0.5f, c); }, 1, bps);
@@ -87,6 +94,9 @@ int main() {
         run("LDS.128", [](float2* o, long long* c, int b) { ks<1><<<148 * b, 256>>>(o, c); }, 1, bps);
         run("STS.64", [](float2* o, long long* c, int b) { ks<2><<<148 * b, 256>>>(o, c); }, 1, bps);
         run("LDS.64+STS.64", [](float2* o, long long* c, int b) { ks<3><<<148 * b, 256>>>(o, c); }, 2, bps);
+        run("LDS.32", [](float2* o, long long* c, int b) { ks<4><<<148 * b, 256>>>(o, c); }, 1, bps);
+        run("STS.128", [](float2* o, long long* c, int b) { ks<5><<<148 * b, 256>>>(o, c); }, 1, bps);
+        run("LDS.128+STS.128", [](float2* o, long long* c, int b) { ks<6><<<148 * b, 256>>>(o, c); }, 2, bps);
     }
     return 0;
 }
