@@ -103,6 +103,28 @@ int psg_sti_run(psg_plan* plan, const void* iq_dev,
                 float* out_lin_dev, float* out_db_dev, void* cuda_stream);
 
 /*
+ * Raw integer IQ ingest: the same fused path reading Digital RF's native
+ * complex int16 / int8 samples (interleaved re, im) instead of complex64, so the host-side cast to
+ * complex64 and the divide by the full-scale reference that precede the path in the reference
+ * (DrfInput.read, drfProc.py:124-129; get_ref, drfProc.py:182-201) disappear: pass in_scale = 1/ref.
+ * Strides and offsets stay in complex elements.  psg_sti_run == psg_sti_run_typed(PSG_IQ_C64).
+ */
+enum { PSG_IQ_C64 = 0, PSG_IQ_CI16 = 1, PSG_IQ_CI8 = 2 };
+int psg_sti_run_typed(psg_plan* plan, const void* iq_dev, int iq_type,
+                      int64_t sample_stride, int64_t sub_stride, int nsub,
+                      const int64_t* col_offset_dev, int ncol,
+                      int frames_per_col, int64_t hop,
+                      float in_scale, float eps,
+                      float* out_lin_dev, float* out_db_dev, void* cuda_stream);
+int psg_sti_host_typed(psg_plan* plan, const void* iq_host, int iq_type, int64_t iq_host_elems,
+                       int64_t sample_stride, int64_t sub_stride, int nsub,
+                       const int64_t* col_offset_host, int ncol,
+                       int frames_per_col, int64_t hop,
+                       float in_scale, float eps,
+                       float* out_lin_host, float* out_db_host,
+                       float* med_lin_host, float* med_db_host);
+
+/*
  * Median over the time axis of a finished linear-power image (np.median(sxx, axis=1),
  * drfProc.py:401 / :451): img_dev is [nsub][ncol][nfft]; med_lin_dev / med_db_dev are
  * [nsub][nfft] (either may be NULL).  Even ncol gives the fp32 mean of the two middle values,

@@ -13,6 +13,10 @@ LIB_PATH = os.path.join(HERE, "libpsgb200.so")
 PSG_WINDOW_KAISER = 0
 PSG_WINDOW_BOXCAR = 1
 
+PSG_IQ_C64 = 0
+PSG_IQ_CI16 = 1
+PSG_IQ_CI8 = 2
+
 PSG_OK = 0
 PSG_ERR_ARG = -1
 PSG_ERR_UNSUPPORTED = -2
@@ -47,6 +51,10 @@ _SIGS = {
     "psg_plan_window": (C.c_int, [_P, _P]),
     "psg_sti_run": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int, _P, C.c_int, C.c_int, C.c_int64,
                               C.c_float, C.c_float, _P, _P, _P]),
+    "psg_sti_run_typed": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int64, C.c_int, _P, C.c_int, C.c_int, C.c_int64,
+                                    C.c_float, C.c_float, _P, _P, _P]),
+    "psg_sti_host_typed": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int, _P, C.c_int, C.c_int,
+                                     C.c_int64, C.c_float, C.c_float, _P, _P, _P, _P]),
     "psg_median_time": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P]),
     "psg_sti_host": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, _P, C.c_int, C.c_int,
                                C.c_int64, C.c_float, C.c_float, _P, _P, _P, _P]),

@@ -52,14 +52,15 @@ static int fail(int code, const char* fmt, ...) {
 // ------------------------------------------------------------------------------------------------
 struct Variant {
     const char* name;
-    int logn, F, loader, threads, minb;
+    int logn, F, loader, threads, minb, iqt;
     size_t smem;
     const void* fn;
 };
 
-template <int LOGN, int E, int R0, int R1, int R2, int R3, int F, int LOADER, int STAGES, int XBUF, int MINB, int PFL2 = 0>
+template <int LOGN, int E, int R0, int R1, int R2, int R3, int F, int LOADER, int STAGES, int XBUF, int MINB, int PFL2 = 0,
+          int IQT = IQ_C64>
 static Variant make_variant(const char* name) {
-    using CF = FusedCfg<LOGN, E, R0, R1, R2, R3, F, LOADER, STAGES, XBUF>;
+    using CF = FusedCfg<LOGN, E, R0, R1, R2, R3, F, LOADER, STAGES, XBUF, IQT>;
     Variant v;
     v.name = name;
     v.logn = LOGN;
@@ -67,8 +68,9 @@ static Variant make_variant(const char* name) {
     v.loader = LOADER;
     v.threads = CF::NT;
     v.minb = MINB;
+    v.iqt = IQT;
     v.smem = CF::smem_bytes;
-    v.fn = (const void*)sti_fused_kernel<LOGN, E, R0, R1, R2, R3, F, LOADER, STAGES, XBUF, MINB, PFL2>;
+    v.fn = (const void*)sti_fused_kernel<LOGN, E, R0, R1, R2, R3, F, LOADER, STAGES, XBUF, MINB, PFL2, IQT>;
     return v;
 }
 
@@ -123,6 +125,27 @@ static const Variant g_variants[] = {
     make_variant<13, 16, 2, 16, 16, 16, 1, M, 2, 1, 1>("tma13_2x16x16x16_f1_s2x1"),
     make_variant<13, 16, 8, 8, 8, 16, 1, M, 2, 1, 1>("tma13_8x8x8x16_f1_s2x1"),
     make_variant<13, 16, 2, 16, 16, 16, 1, L, 1, 1, 1>("ldg13_2x16x16x16_f1"),
+    // raw integer IQ ingest (complex int16 / int8): the default geometry of every size, both loaders
+    make_variant<8, 16, 16, 16, 1, 1, 8, L, 1, 2, 4, 0, IQ_CI16>("ldg8_16x16_f8_i16"),
+    make_variant<9, 8, 8, 8, 8, 1, 1, L, 1, 2, 16, 0, IQ_CI16>("ldg9_8x8x8_f1_i16"),
+    make_variant<10, 16, 4, 16, 16, 1, 1, M, 2, 1, 8, 0, IQ_CI16>("tma10_4x16x16_f1_s2x1_i16"),
+    make_variant<10, 16, 4, 16, 16, 1, 1, L, 1, 2, 8, 0, IQ_CI16>("ldg10_4x16x16_f1_i16"),
+    make_variant<11, 16, 8, 16, 16, 1, 1, M, 2, 1, 4, 0, IQ_CI16>("tma11_8x16x16_f1_s2x1_i16"),
+    make_variant<11, 16, 8, 16, 16, 1, 1, L, 1, 2, 4, 0, IQ_CI16>("ldg11_8x16x16_f1_i16"),
+    make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 1, 2, 0, IQ_CI16>("tma12_16x16x16_f1_s2x1_i16"),
+    make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 2, 2, 0, IQ_CI16>("ldg12_16x16x16_f1_i16"),
+    make_variant<13, 16, 8, 8, 8, 16, 1, M, 2, 1, 1, 0, IQ_CI16>("tma13_8x8x8x16_f1_s2x1_i16"),
+    make_variant<13, 16, 2, 16, 16, 16, 1, L, 1, 1, 1, 0, IQ_CI16>("ldg13_2x16x16x16_f1_i16"),
+    make_variant<8, 16, 16, 16, 1, 1, 8, L, 1, 2, 4, 0, IQ_CI8>("ldg8_16x16_f8_i8"),
+    make_variant<9, 8, 8, 8, 8, 1, 1, L, 1, 2, 16, 0, IQ_CI8>("ldg9_8x8x8_f1_i8"),
+    make_variant<10, 16, 4, 16, 16, 1, 1, M, 2, 1, 8, 0, IQ_CI8>("tma10_4x16x16_f1_s2x1_i8"),
+    make_variant<10, 16, 4, 16, 16, 1, 1, L, 1, 2, 8, 0, IQ_CI8>("ldg10_4x16x16_f1_i8"),
+    make_variant<11, 16, 8, 16, 16, 1, 1, M, 2, 1, 4, 0, IQ_CI8>("tma11_8x16x16_f1_s2x1_i8"),
+    make_variant<11, 16, 8, 16, 16, 1, 1, L, 1, 2, 4, 0, IQ_CI8>("ldg11_8x16x16_f1_i8"),
+    make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 1, 2, 0, IQ_CI8>("tma12_16x16x16_f1_s2x1_i8"),
+    make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 2, 2, 0, IQ_CI8>("ldg12_16x16x16_f1_i8"),
+    make_variant<13, 16, 8, 8, 8, 16, 1, M, 2, 1, 1, 0, IQ_CI8>("tma13_8x8x8x16_f1_s2x1_i8"),
+    make_variant<13, 16, 2, 16, 16, 16, 1, L, 1, 1, 1, 0, IQ_CI8>("ldg13_2x16x16x16_f1_i8"),
 };
 #undef L
 #undef M
@@ -142,16 +165,19 @@ static const char* const g_default_tma[] = {"ldg8_16x16_f8", "ldg9_8x8x8_f1", "t
 static const char* const g_default_ldg[] = {"ldg8_16x16_f8", "ldg9_8x8x8_f1", "ldg10_4x16x16_f1",
                                             "ldg11_8x16x16_f1", "ldg12_16x16x16_f1", "ldg13_2x16x16x16_f1"};
 
-static const Variant* pick_variant(int logn, bool tma_ok) {
+static const Variant* pick_variant(int logn, bool tma_ok, int iqt) {
     {
         std::lock_guard<std::mutex> lk(g_variant_mu);
         if (!g_variant_override.empty()) {
             const Variant* v = variant_by_name(g_variant_override.c_str());
-            if (v && v->logn == logn && (v->loader == PSG_LOADER_LDG || tma_ok)) return v;
+            if (v && v->logn == logn && v->iqt == iqt && (v->loader == PSG_LOADER_LDG || tma_ok)) return v;
         }
     }
     if (logn < 8 || logn > 13) return nullptr;
-    return variant_by_name((tma_ok ? g_default_tma : g_default_ldg)[logn - 8]);
+    std::string name = (tma_ok ? g_default_tma : g_default_ldg)[logn - 8];
+    if (iqt == IQ_CI16) name += "_i16";
+    if (iqt == IQ_CI8) name += "_i8";
+    return variant_by_name(name.c_str());
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -556,6 +582,7 @@ static int run_split(psg_plan* p, StiArgs a, int ncs, int frames_per_col, cudaSt
             // phase A
             SplitArgs sa;
             sa.iq = a.iq;
+            sa.iq_type = a.iq_type;
             sa.sample_stride = a.sample_stride;
             sa.sub_stride = a.sub_stride;
             sa.hop_elems = a.hop_elems;
@@ -582,6 +609,7 @@ static int run_split(psg_plan* p, StiArgs a, int ncs, int frames_per_col, cudaSt
             // phase B: r0 * nc virtual columns of nf frames each
             StiArgs b;
             b.iq = p->d_scratch;
+            b.iq_type = IQ_C64;
             b.sample_stride = 1;
             b.sub_stride = N2;
             b.hop_elems = N;
@@ -619,17 +647,29 @@ static int run_split(psg_plan* p, StiArgs a, int ncs, int frames_per_col, cudaSt
     return PSG_OK;
 }
 
+static int iq_bytes(int iq_type) { return iq_type == PSG_IQ_C64 ? 8 : iq_type == PSG_IQ_CI16 ? 4 : iq_type == PSG_IQ_CI8 ? 2 : 0; }
+
 extern "C" int psg_sti_run(psg_plan* p, const void* iq_dev, int64_t sample_stride, int64_t sub_stride, int nsub,
                            const int64_t* col_offset_dev, int ncol, int frames_per_col, int64_t hop, float in_scale,
                            float eps, float* out_lin_dev, float* out_db_dev, void* cuda_stream) {
+    return psg_sti_run_typed(p, iq_dev, PSG_IQ_C64, sample_stride, sub_stride, nsub, col_offset_dev, ncol, frames_per_col,
+                             hop, in_scale, eps, out_lin_dev, out_db_dev, cuda_stream);
+}
+
+extern "C" int psg_sti_run_typed(psg_plan* p, const void* iq_dev, int iq_type, int64_t sample_stride, int64_t sub_stride,
+                                 int nsub, const int64_t* col_offset_dev, int ncol, int frames_per_col, int64_t hop,
+                                 float in_scale, float eps, float* out_lin_dev, float* out_db_dev, void* cuda_stream) {
     if (!p) return fail(PSG_ERR_ARG, "psg_sti_run: plan is NULL");
+    const int iqb = iq_bytes(iq_type);
+    if (!iqb) return fail(PSG_ERR_ARG, "psg_sti_run: unknown iq_type %d", iq_type);
     if (!iq_dev || !col_offset_dev) return fail(PSG_ERR_ARG, "psg_sti_run: NULL input pointer");
     if (!out_lin_dev && !out_db_dev) return fail(PSG_ERR_ARG, "psg_sti_run: both outputs are NULL");
     if (nsub < 1 || ncol < 1 || frames_per_col < 1)
         return fail(PSG_ERR_ARG, "psg_sti_run: nsub=%d ncol=%d frames_per_col=%d must be >= 1", nsub, ncol, frames_per_col);
     if (sample_stride < 1) return fail(PSG_ERR_ARG, "psg_sti_run: sample_stride=%lld must be >= 1", (long long)sample_stride);
     if (frames_per_col > 1 && hop < 1) return fail(PSG_ERR_ARG, "psg_sti_run: hop=%lld must be >= 1", (long long)hop);
-    if ((reinterpret_cast<uintptr_t>(iq_dev) & 7) != 0) return fail(PSG_ERR_ARG, "psg_sti_run: iq_dev must be 8-byte aligned");
+    if ((reinterpret_cast<uintptr_t>(iq_dev) & (uintptr_t)(iqb - 1)) != 0)
+        return fail(PSG_ERR_ARG, "psg_sti_run: iq_dev must be %d-byte aligned", iqb);
     if ((long long)ncol * nsub > (1ll << 30)) return fail(PSG_ERR_ARG, "psg_sti_run: too many columns");
     CUDA_TRY(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
@@ -637,7 +677,8 @@ extern "C" int psg_sti_run(psg_plan* p, const void* iq_dev, int64_t sample_strid
     const int ncs = ncol * nsub;
 
     StiArgs a;
-    a.iq = (const float2*)iq_dev;
+    a.iq = iq_dev;
+    a.iq_type = iq_type;
     a.sample_stride = sample_stride;
     a.sub_stride = sub_stride;
     a.hop_elems = hop * sample_stride;
@@ -660,7 +701,7 @@ extern "C" int psg_sti_run(psg_plan* p, const void* iq_dev, int64_t sample_strid
     const bool tma_ok = sample_stride == 1 && (reinterpret_cast<uintptr_t>(iq_dev) & 15) == 0;
     const Variant* v = nullptr;
     if (!g_force_generic.load()) {
-        v = pick_variant(p->logn, tma_ok);
+        v = pick_variant(p->logn, tma_ok, iq_type);
         bool force_split = false;
         {
             std::lock_guard<std::mutex> lk(g_variant_mu);
@@ -777,7 +818,18 @@ extern "C" int psg_sti_host(psg_plan* p, const void* iq_host, int64_t iq_host_el
                             int64_t sub_stride, int nsub, const int64_t* col_offset_host, int ncol,
                             int frames_per_col, int64_t hop, float in_scale, float eps, float* out_lin_host,
                             float* out_db_host, float* med_lin_host, float* med_db_host) {
+    return psg_sti_host_typed(p, iq_host, PSG_IQ_C64, iq_host_elems, sample_stride, sub_stride, nsub, col_offset_host,
+                              ncol, frames_per_col, hop, in_scale, eps, out_lin_host, out_db_host, med_lin_host,
+                              med_db_host);
+}
+
+extern "C" int psg_sti_host_typed(psg_plan* p, const void* iq_host, int iq_type, int64_t iq_host_elems,
+                                  int64_t sample_stride, int64_t sub_stride, int nsub, const int64_t* col_offset_host,
+                                  int ncol, int frames_per_col, int64_t hop, float in_scale, float eps,
+                                  float* out_lin_host, float* out_db_host, float* med_lin_host, float* med_db_host) {
     if (!p) return fail(PSG_ERR_ARG, "psg_sti_host: plan is NULL");
+    const int iqb = iq_bytes(iq_type);
+    if (!iqb) return fail(PSG_ERR_ARG, "psg_sti_host: unknown iq_type %d", iq_type);
     if (!iq_host || !col_offset_host) return fail(PSG_ERR_ARG, "psg_sti_host: NULL input pointer");
     if (!out_lin_host && !out_db_host && !med_lin_host && !med_db_host)
         return fail(PSG_ERR_ARG, "psg_sti_host: no output requested");
@@ -799,9 +851,9 @@ extern "C" int psg_sti_host(psg_plan* p, const void* iq_host, int64_t iq_host_el
     cudaStream_t st = p->stream;
     // keep the device copy 16-byte aligned relative to the host element parity so that aligned
     // host frames stay aligned on the device
-    const long long lo_al = lo & ~1ll;
+    const long long lo_al = lo & ~(long long)(16 / iqb - 1);
     const size_t span = (size_t)(hi + col_extent - lo_al);
-    int rc = ensure_buffer(&p->d_in, &p->in_bytes, (span + 2) * 8);
+    int rc = ensure_buffer(&p->d_in, &p->in_bytes, span * iqb + 32);
     if (rc) return rc;
     {
         size_t have = p->off_elems * 8;
@@ -823,9 +875,10 @@ extern "C" int psg_sti_host(psg_plan* p, const void* iq_host, int64_t iq_host_el
         if (rc) return rc;
     }
     CUDA_TRY(cudaMemcpyAsync(p->d_off, rel.data(), (size_t)ncol * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(p->d_in, (const char*)iq_host + (size_t)lo_al * 8, span * 8, cudaMemcpyHostToDevice, st));
-    rc = psg_sti_run(p, p->d_in, sample_stride, sub_stride, nsub, (const int64_t*)p->d_off, ncol, frames_per_col, hop,
-                     in_scale, eps, need_lin ? p->d_out[0] : nullptr, out_db_host ? p->d_out[1] : nullptr, st);
+    CUDA_TRY(cudaMemcpyAsync(p->d_in, (const char*)iq_host + (size_t)lo_al * iqb, span * iqb, cudaMemcpyHostToDevice, st));
+    rc = psg_sti_run_typed(p, p->d_in, iq_type, sample_stride, sub_stride, nsub, (const int64_t*)p->d_off, ncol,
+                           frames_per_col, hop, in_scale, eps, need_lin ? p->d_out[0] : nullptr,
+                           out_db_host ? p->d_out[1] : nullptr, st);
     if (rc) return rc;
     if (med_lin_host || med_db_host) {
         rc = psg_median_time(p, p->d_out[0], nsub, ncol, N, eps, med_lin_host ? p->d_out[2] : nullptr,

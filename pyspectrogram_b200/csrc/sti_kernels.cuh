@@ -44,7 +44,8 @@
 #include "cplx.cuh"
 
 struct StiArgs {
-    const float2* iq;
+    const void* iq;   // complex samples: fp32 pairs (c64), int16 pairs (ci16) or int8 pairs (ci8)
+    int iq_type;      // PSG_IQ_* (runtime switch for the generic / split kernels; tuned kernels are templated)
     long long sample_stride;  // elements between consecutive samples
     long long sub_stride;     // elements between sub-channels
     long long hop_elems;      // hop * sample_stride
@@ -70,6 +71,44 @@ PSG_DEV float2 ldg_stream(const float2* p) {
     float2 v;
     asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
     return v;
+}
+
+// Raw integer IQ (Digital RF's native complex int16 / int8): element size
+// and decoding.  The full-scale factor 1/ref (drfProc.py:129, get_ref :182-201) is not applied per
+// sample: it is folded into the power scale in_scale^2 of the epilogue.
+enum { IQ_C64 = 0, IQ_CI16 = 1, IQ_CI8 = 2 };
+template <int IQT> struct IqBytes { static constexpr int value = (IQT == IQ_C64) ? 8 : (IQT == IQ_CI16) ? 4 : 2; };
+PSG_DEV float2 decode_ci16(uint32_t r) {
+    return make_float2((float)(short)(r & 0xffffu), (float)(short)(r >> 16));
+}
+PSG_DEV float2 decode_ci8(uint32_t r) {
+    return make_float2((float)(signed char)(r & 0xffu), (float)(signed char)((r >> 8) & 0xffu));
+}
+template <int IQT>
+PSG_DEV float2 ldg_iq(const void* base, long long elem) {
+    if constexpr (IQT == IQ_C64) {
+        return ldg_stream(reinterpret_cast<const float2*>(base) + elem);
+    } else if constexpr (IQT == IQ_CI16) {
+        uint32_t r;
+        asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(r) : "l"(reinterpret_cast<const uint32_t*>(base) + elem));
+        return decode_ci16(r);
+    } else {
+        unsigned short r;
+        asm volatile("ld.global.nc.L1::no_allocate.b16 %0, [%1];" : "=h"(r) : "l"(reinterpret_cast<const unsigned short*>(base) + elem));
+        return decode_ci8(r);
+    }
+}
+PSG_DEV float2 ldg_iq_rt(int iqt, const void* base, long long elem) {
+    if (iqt == IQ_CI16) return ldg_iq<IQ_CI16>(base, elem);
+    if (iqt == IQ_CI8) return ldg_iq<IQ_CI8>(base, elem);
+    return ldg_iq<IQ_C64>(base, elem);
+}
+// element idx of a shared-memory stage holding raw samples
+template <int IQT>
+PSG_DEV float2 lds_iq(const unsigned char* stage, int idx) {
+    if constexpr (IQT == IQ_C64) return reinterpret_cast<const float2*>(stage)[idx];
+    else if constexpr (IQT == IQ_CI16) return decode_ci16(reinterpret_cast<const uint32_t*>(stage)[idx]);
+    else return decode_ci8(reinterpret_cast<const unsigned short*>(stage)[idx]);
 }
 
 PSG_DEV float power_to_db(float p, float eps) { return 10.0f * log10f(p + eps); }
@@ -212,22 +251,24 @@ PSG_DEV void exchange_sync() {
     else __syncthreads();
 }
 
-template <int LOGN, int E, int R0, int R1, int R2, int R3, int F, int LOADER, int STAGES, int XBUF>
+template <int LOGN, int E, int R0, int R1, int R2, int R3, int F, int LOADER, int STAGES, int XBUF, int IQT = IQ_C64>
 struct FusedCfg {
     static constexpr int N = 1 << LOGN, T = N / E, NT = F * T;
     using PLN = Plan<N, R0, R1, R2, R3>;
     static constexpr int NPAD = psg_pad(N) + 2;  // even: every group's buffer stays 16-byte aligned
-    static constexpr int SLOT = N + 2;  // one frame + one element of alignment slack either side
+    static constexpr int SLOT = N * IqBytes<IQT>::value + 16;  // bytes: one frame + 16 of alignment slack
     static constexpr int TWSM = (PLN::ROW1 ? PLN::TW1_LEN : 0) + (PLN::ROW2 ? PLN::TW2_LEN : 0);  // complex
     static constexpr size_t bar_bytes = 64 + (size_t)TWSM * 8;
-    static constexpr size_t stage_bytes = (LOADER == PSG_LOADER_TMA) ? (size_t)STAGES * F * SLOT * 8 : 0;
+    static constexpr size_t stage_bytes = (LOADER == PSG_LOADER_TMA) ? (size_t)STAGES * F * SLOT : 0;
     static constexpr size_t xch_bytes = (size_t)F * XBUF * NPAD * 8;
     static constexpr size_t smem_bytes = bar_bytes + stage_bytes + xch_bytes;
 };
 
-template <int LOGN, int E, int R0, int R1, int R2, int R3, int F, int LOADER, int STAGES, int XBUF, int MINB, int PFL2 = 0>
+template <int LOGN, int E, int R0, int R1, int R2, int R3, int F, int LOADER, int STAGES, int XBUF, int MINB, int PFL2 = 0,
+          int IQT = IQ_C64>
 __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(const StiArgs a) {
-    using CF = FusedCfg<LOGN, E, R0, R1, R2, R3, F, LOADER, STAGES, XBUF>;
+    using CF = FusedCfg<LOGN, E, R0, R1, R2, R3, F, LOADER, STAGES, XBUF, IQT>;
+    constexpr int IQB = IqBytes<IQT>::value;
     constexpr int N = CF::N, T = CF::T, NT = CF::NT, NPAD = CF::NPAD, SLOT = CF::SLOT;
     using PL = Plan<N, R0, R1, R2, R3>;
     constexpr int P = PL::P;
@@ -244,7 +285,7 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
     float2* twsm = reinterpret_cast<float2*>(smem_raw + 64);  // row-layout twiddle tables
-    float2* stage = reinterpret_cast<float2*>(smem_raw + CF::bar_bytes);
+    unsigned char* stage = smem_raw + CF::bar_bytes;
     float2* xch = reinterpret_cast<float2*>(smem_raw + CF::bar_bytes + CF::stage_bytes);
 
     const int tid = threadIdx.x;
@@ -280,8 +321,8 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
         if constexpr (LOADER == PSG_LOADER_TMA) {
             uint64_t* bar = bars + (pj % STAGES);
             if (col_ok && (k0 + pj * gpc + lane) < k1) {
-                const uintptr_t src = reinterpret_cast<uintptr_t>(a.iq + pbase);
-                const uint32_t bytes = N * 8 + ((src & 8) ? 16 : 0);
+                const uintptr_t src = reinterpret_cast<uintptr_t>(a.iq) + (uintptr_t)(pbase * IQB);
+                const uint32_t bytes = N * IQB + ((src & 15) ? 16 : 0);
                 mbar_expect_tx(bar, bytes);
                 bulk_g2s(stage + ((size_t)(pj % STAGES) * F + g) * SLOT, reinterpret_cast<const void*>(src & ~(uintptr_t)15),
                          bytes, bar);
@@ -335,25 +376,26 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
             if constexpr (ALL_LOCAL) __syncwarp();
             if (STAGES > 1 && t == 0 && pj < niter) produce();
             mbar_wait(bars + (j % STAGES), (j / STAGES) & 1);
-            const float2* sb = stage + ((size_t)(j % STAGES) * F + g) * SLOT +
-                               ((reinterpret_cast<uintptr_t>(a.iq + fbase) >> 3) & 1);
+            const unsigned char* sb = stage + ((size_t)(j % STAGES) * F + g) * SLOT;
+            // the copy started at the 16-byte boundary below the frame: skip the leading elements
+            const int skew = (int)(((reinterpret_cast<uintptr_t>(a.iq) + (uintptr_t)(fbase * IQB)) & 15) / IQB);
             if (valid) {
 #pragma unroll
                 for (int i = 0; i < NB0; ++i)
 #pragma unroll
-                    for (int n = 0; n < R0; ++n) x[i * R0 + n] = sb[t + i * T + n * PL::S0];
+                    for (int n = 0; n < R0; ++n) x[i * R0 + n] = lds_iq<IQT>(sb, skew + t + i * T + n * PL::S0);
             } else {
 #pragma unroll
                 for (int i = 0; i < E; ++i) x[i] = make_float2(0.f, 0.f);
             }
         } else {
-            const float2* src = a.iq + fbase;
             if constexpr (PFL2 > 0) {
                 // contiguous frames: pull the frame PFL2 iterations ahead into L2 so that the LDGs of
                 // that iteration see L2 latency, not DRAM latency (no registers, no shared memory)
                 if (t == 0 && a.sample_stride == 1 && col_ok && (k0 + (j + PFL2) * gpc + lane) < k1) {
-                    const uintptr_t pa = reinterpret_cast<uintptr_t>(src + (long long)PFL2 * fstep) & ~(uintptr_t)15;
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pa), "r"(N * 8 + 16) : "memory");
+                    const uintptr_t pa = (reinterpret_cast<uintptr_t>(a.iq) + (uintptr_t)((fbase + (long long)PFL2 * fstep) * IQB)) &
+                                         ~(uintptr_t)15;
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pa), "r"(N * IQB + 16) : "memory");
                 }
             }
             if (valid) {
@@ -361,7 +403,7 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
                 for (int i = 0; i < NB0; ++i)
 #pragma unroll
                     for (int n = 0; n < R0; ++n)
-                        x[i * R0 + n] = ldg_stream(src + (long long)(t + i * T + n * PL::S0) * a.sample_stride);
+                        x[i * R0 + n] = ldg_iq<IQT>(a.iq, fbase + (long long)(t + i * T + n * PL::S0) * a.sample_stride);
             } else {
 #pragma unroll
                 for (int i = 0; i < E; ++i) x[i] = make_float2(0.f, 0.f);
@@ -473,13 +515,13 @@ __global__ void __launch_bounds__(256) sti_generic_kernel(const StiArgs a, int l
         const int sub = cs / a.ncol;
         const int k0 = split * a.chunk;
         const int k1 = min(a.nfr, k0 + a.chunk);
-        const float2* src = a.iq + a.col_off[col] + (long long)sub * a.sub_stride + (long long)k0 * a.hop_elems;
+        long long src = a.col_off[col] + (long long)sub * a.sub_stride + (long long)k0 * a.hop_elems;
         __syncthreads();
         for (int i = t; i < N; i += nt) accs[i] = 0.f;
         for (int k = k0; k < k1; ++k, src += a.hop_elems) {
             __syncthreads();
             for (int i = t; i < N; i += nt)
-                buf[i] = cscale(ldg_stream(src + (long long)i * a.sample_stride), a.win[i]);
+                buf[i] = cscale(ldg_iq_rt(a.iq_type, a.iq, src + (long long)i * a.sample_stride), a.win[i]);
             for (int s = N >> 1; s >= 1; s >>= 1) {
                 __syncthreads();
                 const int step = (N >> 1) / s;  // twiddle stride: W_{2s}^j = W_N^{j*N/(2s)}
@@ -609,7 +651,8 @@ __global__ void __launch_bounds__(256) median_time_kernel(const float* __restric
 // phase B is the tuned 4096-point fused kernel run on the scratch with k0 in the role of the
 // sub-channel, and phase C interleaves the R0 partial spectra into the fftshifted column.
 struct SplitArgs {
-    const float2* iq;
+    const void* iq;
+    int iq_type;
     long long sample_stride, sub_stride, hop_elems;
     const long long* col_off;
     int ncol;         // columns per sub-channel (global)
@@ -643,10 +686,10 @@ __global__ void __launch_bounds__(256) sti_split_pass_kernel(const SplitArgs a) 
         const int csl = f / a.nfr_chunk, kk = f - csl * a.nfr_chunk;
         const int cs = a.cs_lo + csl;
         const int col = cs % a.ncol, sub = cs / a.ncol;
-        const float2* src = a.iq + a.col_off[col] + (long long)sub * a.sub_stride + (long long)(a.k_lo + kk) * a.hop_elems;
+        const long long src = a.col_off[col] + (long long)sub * a.sub_stride + (long long)(a.k_lo + kk) * a.hop_elems;
         cf x[R0];
 #pragma unroll
-        for (int n = 0; n < R0; ++n) x[n] = ldg_stream(src + (long long)(n * N2 + np) * a.sample_stride);
+        for (int n = 0; n < R0; ++n) x[n] = ldg_iq_rt(a.iq_type, a.iq, src + (long long)(n * N2 + np) * a.sample_stride);
 #pragma unroll
         for (int n = 0; n < R0; ++n) x[n] = cscale(x[n], w[n]);
         dftR<R0>(x);

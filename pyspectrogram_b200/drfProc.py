@@ -52,13 +52,36 @@ def _freq_axis(nfft, sr):
     return np.fft.fftshift(np.fft.fftfreq(nfft, 1 / sr))
 
 
-def _sti(d1, sr, nfft, integrate, device, want):
+def _is_raw_iq(d1):
+    """Raw integer IQ: Digital RF's structured ('r', 'i') int16 / int8 dtype, or a plain int16 /
+    int8 array whose last axis is (re, im)."""
+    return isinstance(d1, np.ndarray) and (d1.dtype.fields is not None or d1.dtype in (np.int16, np.int8))
+
+
+def _sti(d1, sr, nfft, integrate, device, want, ref=1.0):
     nfft = int(nfft)
-    arr, out_dtype = _as_c64(d1)
-    if arr.ndim not in (2, 3):
+    if _is_raw_iq(d1):
+        # extension (SURVEY.md section 8(f) N1): the samples go to the GPU as stored; 1/ref is applied
+        # to the power in the kernel epilogue instead of x/ref on the host (drfProc.py:129)
+        arr = np.ascontiguousarray(d1)
+        out_dtype = np.float32
+        shape = arr.shape if arr.dtype.fields is not None else arr.shape[:-1]
+        if arr.dtype.fields is None and arr.shape[-1] != 2:
+            raise ValueError("raw integer IQ must have a last axis of length 2 (re, im)")
+        in_scale = 1.0 / float(ref)
+    else:
+        arr, out_dtype = _as_c64(d1)
+        shape = arr.shape
+        in_scale = 1.0 / float(ref)
+    return _sti_core(arr, shape, out_dtype, in_scale, sr, nfft, integrate, device, want)
+
+
+def _sti_core(arr, shape, out_dtype, in_scale, sr, nfft, integrate, device, want):
+    ndim = len(shape)
+    if ndim not in (2, 3):
         raise ValueError("d1 must be (nfft*nint, ntime) or (nfft*nint, ntime, nsub)")
-    rows, ntime = arr.shape[0], arr.shape[1]
-    nsub = arr.shape[2] if arr.ndim == 3 else 1
+    rows, ntime = shape[0], shape[1]
+    nsub = shape[2] if ndim == 3 else 1
     if rows < nfft:
         # the reference passes a length-nfft window to a shorter segment: scipy raises ValueError
         raise ValueError(f"window is longer than input signal ({rows} rows < nfft={nfft})")
@@ -67,37 +90,41 @@ def _sti(d1, sr, nfft, integrate, device, want):
     frames = rows // nfft if integrate else 1
     plan = engine.get_plan(nfft, device)
     res = plan.host(arr.reshape(-1), np.arange(ntime, dtype=np.int64) * nsub, frames, nfft,
-                    sample_stride=ntime * nsub, sub_stride=1, nsub=nsub, eps=_EPS, want=want)
+                    sample_stride=ntime * nsub, sub_stride=1, nsub=nsub, in_scale=in_scale, eps=_EPS, want=want)
     out = {}
     for key, val in res.items():
         if val.ndim == 3:  # [nsub][ntime][nfft] -> (nfft, ntime[, nsub]) as the viewer indexes it
             val = val.transpose(2, 1, 0)
-            val = val if arr.ndim == 3 else val[:, :, 0]
+            val = val if ndim == 3 else val[:, :, 0]
         else:  # [nsub][nfft] -> (nfft[, nsub])
-            val = val.T if arr.ndim == 3 else val[0]
+            val = val.T if ndim == 3 else val[0]
         out[key] = val if out_dtype == np.float32 else val.astype(out_dtype)
     return _freq_axis(nfft, sr), out
 
 
-def sti_proc_data(d1, sr, nfft, *, integrate=False, device=0):
+def sti_proc_data(d1, sr, nfft, *, integrate=False, device=0, ref=1.0):
     """STI of ``d1`` shaped ``(nfft*nint, ntime[, nsub])`` -> ``(f, sxx, sxx_med)``.
 
     ``sxx`` is ``(nfft, ntime[, nsub])`` linear power (float32 for complex64 input), fftshifted;
     ``sxx_med`` is its median over time (drfProc.py:364-403).  With the default
     ``integrate=False`` only the first ``nfft`` rows of each time bin are used, exactly like the
     reference; ``integrate=True`` averages ``floor(rows/nfft)`` back-to-back frames (Mode A).
+
+    ``d1`` may also be raw integer IQ (Digital RF's structured int16 / int8 dtype, or an integer array
+    with a last axis ``(re, im)``) together with ``ref`` = the full-scale level of ``get_ref``: the
+    result equals ``sti_proc_data(d1_as_complex / ref, ...)`` without the host-side cast and divide.
     """
-    f, out = _sti(d1, sr, nfft, integrate, device, ("lin", "med"))
+    f, out = _sti(d1, sr, nfft, integrate, device, ("lin", "med"), ref)
     return f, out["lin"], out["med"]
 
 
-def sti_proc_data_db(d1, sr, nfft, *, integrate=False, device=0, eps=_EPS):
+def sti_proc_data_db(d1, sr, nfft, *, integrate=False, device=0, eps=_EPS, ref=1.0):
     """``sti_proc_data`` plus the worker loop's dB step (drfProc.py:308-310) fused on the GPU.
 
     Returns ``(f, sxx_dbfs, sxx_med_dbfs)``.
     """
     assert eps == _EPS
-    f, out = _sti(d1, sr, nfft, integrate, device, ("db", "med_db"))
+    f, out = _sti(d1, sr, nfft, integrate, device, ("db", "med_db"), ref)
     return f, out["db"], out["med_db"]
 
 
@@ -203,6 +230,24 @@ class DrfInput:
         self.last_read[ichan] = (st_sample, n_sample)
         return x / ref
 
+    def read_raw(self, st_sample, n_sample, chan_entry):
+        """``read`` without the cast to complex64 and without ``/ ref`` (drfProc.py:124-129): the
+        samples as stored (``DigitalRFReader.read_vector_raw``).  Extension for the raw-ingest path."""
+        ichan, isub = self._split(chan_entry)
+        x = self.drf_Obj.read_vector_raw(st_sample, n_sample, ichan) if isub is None else \
+            self.drf_Obj.read_vector_raw(st_sample, n_sample, ichan, isub)
+        self.bnds[ichan] = self.drf_Obj.get_bounds(ichan)
+        self.last_read[ichan] = (st_sample, n_sample)
+        return x
+
+    def read_sti_raw(self, st_sample, chan_entry, en_sample, nfft, nint, ntime):
+        """``read_sti`` on raw samples: ``(n_st, dout_raw, ref)``; same framing (drfProc.py:158-166)."""
+        ichan, _ = self._split(chan_entry)
+        n_sample = nint * nfft
+        n_st = engine.frame_starts(st_sample, en_sample, nfft, nint, ntime)
+        dlist = [self.read_raw(ist, n_sample, chan_entry)[:, np.newaxis] for ist in n_st]
+        return n_st, np.concatenate(dlist, axis=1), self.ref_dict[ichan]
+
     def read_sti(self, st_sample, chan_entry, en_sample, nfft, nint, ntime):
         """``(n_st, dout)`` with ``dout`` shaped ``(nfft*nint, ntime[, nsub])`` (drfProc.py:132-167)."""
         n_sample = nint * nfft
@@ -304,7 +349,7 @@ class DrfProcessor(QRunnable):
     """
 
     def __init__(self, datasource, drfdir, tabID, fftbins, n_int, ntime, *args, integrate=False, device=0,
-                 reader=None, **kwargs):
+                 reader=None, raw_ingest=False, **kwargs):
         super(DrfProcessor, self).__init__()
         self.drfIn = DrfInput(drfdir, reader=reader)
         self.drf_path = Path(drfdir).expanduser()
@@ -314,6 +359,7 @@ class DrfProcessor(QRunnable):
         self.ntime = ntime
         self.integrate = integrate
         self.device = device
+        self.raw_ingest = raw_ingest  # ship the stored integer samples to the GPU, fold 1/ref into the kernel
         self.bnds = self.drfIn.time_bnds
         self.chan_listing = list(self.drfIn.chan_2sub.keys())
         self.sub_chan_list = list(self.drfIn.chan_entries.keys())
@@ -345,10 +391,16 @@ class DrfProcessor(QRunnable):
             st_time, end_time = self.bnds
         s_samp = _time_to_sample(st_time, sr)
         e_samp = _time_to_sample(end_time, sr)
-        n_st, d1 = self.drfIn.read_sti(s_samp, ichan, e_samp, self.fftbins, self.n_int, self.ntime)
+        ref = 1.0
+        if self.raw_ingest and hasattr(self.drfIn.drf_Obj, "read_vector_raw") and self.drfIn.ref_dict[ichan] != 1.0:
+            n_st, d1, ref = self.drfIn.read_sti_raw(s_samp, ichan, e_samp, self.fftbins, self.n_int, self.ntime)
+            if d1.ndim == 2 and d1.dtype.fields is not None:
+                d1 = d1[:, :, np.newaxis]  # the viewer wants (nfft, ntime, nsub), drfview.py:1289
+        else:
+            n_st, d1 = self.drfIn.read_sti(s_samp, ichan, e_samp, self.fftbins, self.n_int, self.ntime)
         time_ar = np.array([_sample_to_datetime(istime, int(sr)) for istime in n_st])
         f, sxx_dbfs, sxx_med_dbfs = sti_proc_data_db(d1, sr, self.fftbins, integrate=self.integrate,
-                                                     device=self.device)
+                                                     device=self.device, ref=ref)
         self.freqs_all = f
         self.signals.iterated.emit(i, self.tabID, time_ar, self.freqs_all, sxx_dbfs, sxx_med_dbfs)
         return time_ar, f, sxx_dbfs, sxx_med_dbfs

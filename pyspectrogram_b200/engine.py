@@ -85,7 +85,10 @@ class StiPlan:
             in_scale=1.0, eps=DB_EPS, want_lin=True, want_db=False, out_lin=None, out_db=None):
         """Fused frame->window->FFT->|X|^2->mean->fftshift->(dB) on device-resident IQ.
 
-        ``iq``: CUDA tensor, complex64 (or float32 viewed as interleaved re/im).
+        ``iq``: CUDA tensor, complex64 (or float32 viewed as interleaved re/im), or raw integer IQ as
+        int16 / int8 (re, im) pairs -- Digital RF's native sample formats; pass ``in_scale=1/ref``
+        (``get_ref``, drfProc.py:182-201) instead of dividing on the host (drfProc.py:129).
+        Strides and offsets are always in complex elements.
         ``col_offsets``: CUDA int64 tensor ``[ncol]`` of element offsets into ``iq``.
         Returns ``(lin, db)`` tensors ``[nsub][ncol][nfft]`` (``None`` for the one not requested).
         Work is enqueued on torch's current stream; nothing synchronises.
@@ -93,8 +96,10 @@ class StiPlan:
         torch = _torch()
         if not iq.is_cuda or not col_offsets.is_cuda:
             raise ValueError("iq and col_offsets must be CUDA tensors (use StiPlan.host for host arrays)")
-        if iq.dtype not in (torch.complex64, torch.float32):
-            raise TypeError(f"iq must be complex64 (or its float32 view), got {iq.dtype}")
+        iq_type = {torch.complex64: _lib.PSG_IQ_C64, torch.float32: _lib.PSG_IQ_C64, torch.int16: _lib.PSG_IQ_CI16,
+                   torch.int8: _lib.PSG_IQ_CI8}.get(iq.dtype)
+        if iq_type is None:
+            raise TypeError(f"iq must be complex64 (or its float32 view), or raw int16 / int8 (re, im) pairs; got {iq.dtype}")
         if col_offsets.dtype != torch.int64 or not col_offsets.is_contiguous():
             raise TypeError("col_offsets must be a contiguous int64 tensor")
         if iq.device.index != self.device or col_offsets.device.index != self.device:
@@ -112,8 +117,8 @@ class StiPlan:
                 raise ValueError("output tensors must be contiguous float32 [nsub][ncol][nfft]")
         stream = torch.cuda.current_stream(dev).cuda_stream
         with self._lock:
-            _lib.check(self._lib.psg_sti_run(
-                self._h, C.c_void_p(iq.data_ptr()), int(sample_stride), int(sub_stride), int(nsub),
+            _lib.check(self._lib.psg_sti_run_typed(
+                self._h, C.c_void_p(iq.data_ptr()), iq_type, int(sample_stride), int(sub_stride), int(nsub),
                 C.c_void_p(col_offsets.data_ptr()), ncol, int(frames_per_col), hop, float(in_scale), float(eps),
                 C.c_void_p(out_lin.data_ptr() if out_lin is not None else None),
                 C.c_void_p(out_db.data_ptr() if out_db is not None else None), C.c_void_p(stream)))
@@ -138,13 +143,13 @@ class StiPlan:
     # ---- host path -------------------------------------------------------------------------
     def host(self, iq: np.ndarray, col_offsets, frames_per_col=1, hop=None, *, sample_stride=1, sub_stride=0,
              nsub=1, in_scale=1.0, eps=DB_EPS, want=("lin", "med")):
-        """Host complex64 array in, host float32 arrays out (H2D, kernels, D2H inside the call).
+        """Host complex64 (or raw int16 / int8 pair) array in, host float32 arrays out (H2D, kernels,
+        D2H inside the call).
 
         ``want``: any of ``"lin" "db" "med" "med_db"``.  Returns a dict of numpy arrays:
         images ``[nsub][ncol][nfft]``, medians ``[nsub][nfft]``.
         """
-        if not isinstance(iq, np.ndarray) or iq.dtype != np.complex64 or not iq.flags.c_contiguous:
-            raise TypeError("iq must be a C-contiguous numpy complex64 array")
+        iq, iq_type, nelem = _host_iq(iq)
         offs = np.ascontiguousarray(col_offsets, dtype=np.int64)
         ncol = int(offs.size)
         hop = self.nfft if hop is None else int(hop)
@@ -158,11 +163,31 @@ class StiPlan:
             else:
                 ptr[key] = C.c_void_p(None)
         with self._lock:
-            _lib.check(self._lib.psg_sti_host(
-                self._h, iq.ctypes.data_as(C.c_void_p), int(iq.size), int(sample_stride), int(sub_stride),
+            _lib.check(self._lib.psg_sti_host_typed(
+                self._h, iq.ctypes.data_as(C.c_void_p), iq_type, nelem, int(sample_stride), int(sub_stride),
                 int(nsub), offs.ctypes.data_as(C.c_void_p), ncol, int(frames_per_col), hop, float(in_scale),
                 float(eps), ptr["lin"], ptr["db"], ptr["med"], ptr["med_db"]))
         return out
+
+
+def _host_iq(iq):
+    """``(array, PSG_IQ_*, number of complex elements)`` for a host IQ array: complex64, or raw
+    integer IQ as an int16 / int8 array whose last axis is (re, im), or Digital RF's structured
+    dtype with two integer fields ('r', 'i')."""
+    if not isinstance(iq, np.ndarray) or not iq.flags.c_contiguous:
+        raise TypeError("iq must be a C-contiguous numpy array")
+    if iq.dtype == np.complex64:
+        return iq, _lib.PSG_IQ_C64, int(iq.size)
+    if iq.dtype.fields is not None and len(iq.dtype.fields) == 2:
+        base = {np.dtype(np.int16): _lib.PSG_IQ_CI16, np.dtype(np.int8): _lib.PSG_IQ_CI8}
+        kinds = {v[0] for v in iq.dtype.fields.values()}
+        if len(kinds) == 1 and next(iter(kinds)) in base and iq.dtype.itemsize == 2 * next(iter(kinds)).itemsize:
+            return iq, base[next(iter(kinds))], int(iq.size)
+    if iq.dtype in (np.int16, np.int8):
+        if iq.size % 2:
+            raise ValueError("raw integer IQ needs (re, im) pairs")
+        return iq, (_lib.PSG_IQ_CI16 if iq.dtype == np.int16 else _lib.PSG_IQ_CI8), int(iq.size // 2)
+    raise TypeError(f"iq dtype {iq.dtype} is not supported (complex64, int16 pairs, int8 pairs)")
 
 
 _plans = {}

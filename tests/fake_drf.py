@@ -37,3 +37,20 @@ class FakeReader:
         if sub is not None and d.ndim == 2:
             out = out[:, sub]
         return out.astype(np.complex64)
+
+    def read_vector_raw(self, start, n, chan, sub=None):
+        """Samples as stored: Digital RF keeps complex integers as a structured ('r', 'i') dtype."""
+        d = self.channels[chan]
+        lo = int(start) - self.first
+        if lo < 0 or lo + n > d.shape[0]:
+            raise IOError("read outside the recording")
+        self.reads.append((int(start), int(n)))
+        out = d[lo:lo + int(n)]
+        if sub is not None and d.ndim == 2:
+            out = out[:, sub]
+        if not self.int16:
+            return out.astype(np.complex64)
+        raw = np.empty(out.shape, dtype=np.dtype([("r", np.int16), ("i", np.int16)]))
+        raw["r"] = np.round(out.real).astype(np.int16)
+        raw["i"] = np.round(out.imag).astype(np.int16)
+        return raw

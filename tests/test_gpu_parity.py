@@ -146,10 +146,17 @@ def test_every_variant_matches_float64_oracle(torch, variant):
     starts[1] |= 1  # an odd (8-byte aligned only) start
     starts[-1] = n - nfr * nfft  # a column that ends at the last sample
     plan = engine.StiPlan(nfft)
-    dx, ds = torch.from_numpy(x).cuda(), torch.from_numpy(starts).cuda()
+    in_scale = 1.0
+    feed = x
+    if variant.endswith(("_i16", "_i8")):  # raw integer ingest variants: quantise the recording
+        amp, dt = (20000.0, np.int16) if variant.endswith("_i16") else (100.0, np.int8)
+        feed = np.stack([np.round(x.real * amp * 8), np.round(x.imag * amp * 8)], axis=1).astype(dt)
+        in_scale = 1.0 / (amp * 8)
+        x = ((feed[:, 0].astype(np.float32) + 1j * feed[:, 1].astype(np.float32)) * np.float32(in_scale)).astype(np.complex64)
+    dx, ds = torch.from_numpy(feed).cuda(), torch.from_numpy(starts).cuda()
     try:
         engine.set_variant(variant)
-        lin, db = plan.run(dx, ds, nfr, nfft, want_lin=True, want_db=True)
+        lin, db = plan.run(dx, ds, nfr, nfft, in_scale=in_scale, want_lin=True, want_db=True)
         torch.cuda.synchronize()
         assert plan.variant == variant
     finally:
@@ -208,6 +215,113 @@ def test_split_path_chunking(torch, nfft, nfr, ncol, scratch_mb):
     assert_psd_close(lin.cpu().numpy()[0].T, ref.T, noise_like=False, what=f"split {nfft}")
     assert_db_close(db.cpu().numpy()[0].T, 10 * np.log10(ref.T.astype(np.float32) + np.float32(1e-15)),
                     ref_lin=ref.T, what=f"split {nfft} dB")
+
+
+@pytest.mark.parametrize("nfft", [256, 512, 1024, 2048, 4096, 8192, 16384, 65536])
+def test_repeated_runs_are_bit_identical(torch, nfft):
+    """Race canary (compute-sanitizer is not available on the GPU pool): the kernels have no
+    atomics and sum in a fixed order, so 12 back-to-back runs on two streams must agree bit for
+    bit; a missing barrier in an exchange shows up as run-to-run differences."""
+    from pyspectrogram_b200 import engine
+    rng = np.random.default_rng(nfft)
+    nfr = 37 if nfft <= 4096 else 9
+    ncol = 301 if nfft <= 4096 else 24
+    n = nfft * nfr * ncol + 64
+    x = torch.from_numpy(_recording(rng, n)).cuda()
+    starts = torch.from_numpy((np.arange(ncol) * nfft * nfr + np.arange(ncol) % 2).astype(np.int64)).cuda()
+    plan = engine.StiPlan(nfft)
+    ref = None
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    for i in range(12):
+        with torch.cuda.stream(streams[i % 2]):
+            lin, db = plan.run(x, starts, nfr, nfft, want_lin=True, want_db=True)
+        torch.cuda.synchronize()
+        if ref is None:
+            ref = (lin.clone(), db.clone())
+        else:
+            assert torch.equal(lin, ref[0]) and torch.equal(db, ref[1]), (nfft, i, plan.variant)
+
+
+# ---------------------------------------------------------------------------------------------
+# raw integer IQ ingest (SURVEY.md section 8(f) N1)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nfft", [64, 256, 512, 1024, 2048, 4096, 8192, 16384])
+@pytest.mark.parametrize("kind", ["int16", "int8"])
+def test_raw_integer_iq_matches_reference_on_normalised_samples(torch, nfft, kind):
+    """The reference casts the stored integers to complex64 and divides by get_ref's full scale
+    (drfProc.py:124-129, :182-201) before the path; the GPU reads the integers and folds 1/ref into
+    the epilogue.  Oracle: float64 PSD of x/ref.  Contiguous (TMA) and interleaved (LDG) layouts."""
+    from pyspectrogram_b200 import engine
+    from pyspectrogram_b200.drfProc import get_ref
+    rng = np.random.default_rng(nfft + len(kind))
+    dt, amp, props = (np.int16, 3000, dict(H5Tget_class=0, H5Tget_precision=16, H5Tget_size=2)) if kind == "int16" else \
+                     (np.int8, 40, dict(H5Tget_class=0, H5Tget_precision=8, H5Tget_size=1))
+    ref = get_ref(props)
+    nfr, ncol = 3, 6
+    n = nfft * nfr * ncol + nfft + 13
+    tone = np.exp(2j * np.pi * 0.123 * np.arange(n)) * amp * 3
+    xc = (rng.standard_normal(n) + 1j * rng.standard_normal(n)) * amp + tone
+    raw = np.stack([np.clip(np.round(xc.real), -32000, 32000), np.clip(np.round(xc.imag), -32000, 32000)], axis=1)
+    if kind == "int8":
+        raw = np.clip(raw, -127, 127)
+    raw = raw.astype(dt)
+    x = ((raw[:, 0].astype(np.float32) + 1j * raw[:, 1].astype(np.float32)) / np.float32(ref)).astype(np.complex64)
+    starts = (np.arange(ncol) * nfft * nfr + np.array([0, 1, 2, 3, 5, 7])).astype(np.int64)
+    plan = engine.StiPlan(nfft)
+    expect = _oracle_columns(x, starts, nfft, nfr, nfft)
+    lin, db = plan.run(torch.from_numpy(raw).cuda(), torch.from_numpy(starts).cuda(), nfr, nfft,
+                       in_scale=1.0 / ref, want_lin=True, want_db=True)
+    assert_psd_close(lin.cpu().numpy()[0].T, expect.T, noise_like=False, what=f"{kind} contiguous {plan.variant}")
+    assert_db_close(db.cpu().numpy()[0].T, 10 * np.log10(expect.T.astype(np.float32) + np.float32(1e-15)),
+                    ref_lin=expect.T, what=f"{kind} dB")
+    if nfft >= 256 and nfft <= 8192:
+        assert plan.variant.endswith("_i16" if kind == "int16" else "_i8"), plan.variant
+    # two interleaved sub-channels [sample][sub][re,im]: strided loader
+    raw2 = np.stack([raw, raw[::-1]], axis=1).copy()
+    lin2, _ = plan.run(torch.from_numpy(raw2).cuda(), torch.from_numpy(starts * 2).cuda(), nfr, nfft,
+                       sample_stride=2, sub_stride=1, nsub=2, in_scale=1.0 / ref)
+    assert_psd_close(lin2.cpu().numpy()[0].T, expect.T, noise_like=False, what=f"{kind} strided {plan.variant}")
+    # host entry point with the structured dtype Digital RF uses
+    if kind == "int16":
+        st = np.empty(n, dtype=np.dtype([("r", np.int16), ("i", np.int16)]))
+        st["r"], st["i"] = raw[:, 0], raw[:, 1]
+        res = plan.host(st, starts, nfr, nfft, in_scale=1.0 / ref, want=("lin",))
+        assert_psd_close(res["lin"][0].T, expect.T, noise_like=False, what="int16 structured host")
+
+
+def test_drop_in_accepts_raw_iq_and_processor_raw_ingest(dp):
+    """sti_proc_data(raw, ..., ref=...) == sti_proc_data(raw_as_complex/ref, ...), and a DrfProcessor
+    with raw_ingest=True emits the same dB arrays as the cast-and-divide path."""
+    from tests.fake_drf import FakeReader
+    rng = np.random.default_rng(4)
+    nfft, nint, ntime, nsub = 512, 2, 12, 2
+    raw = np.empty((nfft * nint, ntime, nsub), dtype=np.dtype([("r", np.int16), ("i", np.int16)]))
+    raw["r"] = rng.integers(-9000, 9000, raw.shape)
+    raw["i"] = rng.integers(-9000, 9000, raw.shape)
+    ref = 2 ** 15.5
+    xc = ((raw["r"].astype(np.float32) + 1j * raw["i"].astype(np.float32)) / np.float32(ref)).astype(np.complex64)
+    f0, s0, m0 = dp.sti_proc_data(xc, 1.0e6, nfft)
+    f1, s1, m1 = dp.sti_proc_data(raw, 1.0e6, nfft, ref=ref)
+    assert np.array_equal(f0, f1) and s1.shape == s0.shape and s1.dtype == np.float32
+    assert_psd_close(s1, s0, what="raw drop-in")
+    assert_psd_close(m1, m0, what="raw drop-in median")
+    # plain integer array with a trailing (re, im) axis
+    plain = np.stack([raw["r"], raw["i"]], axis=-1)
+    f2, s2, m2 = dp.sti_proc_data(plain, 1.0e6, nfft, ref=ref, integrate=True)
+    f3, s3, m3 = dp.sti_proc_data(xc, 1.0e6, nfft, integrate=True)
+    assert_psd_close(s2, s3, what="raw drop-in mode A")
+
+    n = 1 << 17
+    data = np.round((rng.standard_normal((n, nsub)) + 1j * rng.standard_normal((n, nsub))) * 3000).astype(np.complex64)
+    out = []
+    for raw_ingest in (False, True):
+        reader = FakeReader({"ch0": data}, sample_rate=1000000, first_sample=1_700_000_000 * 1000000, int16=True)
+        proc = dp.DrfProcessor("file", "/nonexistent", 1, 1024.0, 2.0, 16.0, reader=reader, raw_ingest=raw_ingest)
+        out.append(proc.iterate_once(0))
+    (t0, fa, sa, ma), (t1, fb, sb, mb) = out
+    assert np.array_equal(fa, fb) and sa.shape == sb.shape == (1024, 16, nsub)
+    assert np.abs(sa - sb).max() <= 1e-3 and np.abs(ma - mb).max() <= 1e-3
 
 
 def test_generic_kernel_cross_checks_tuned(torch):

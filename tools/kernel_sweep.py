@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--odd", action="store_true", help="odd (8-byte aligned) frame starts")
     ap.add_argument("--big", action="store_true", help="only the large-nfft split path (8192..65536)")
+    ap.add_argument("--raw", default="", choices=["", "int16", "int8"], help="raw integer IQ ingest variants")
     ap.add_argument("--scratch-mb", type=int, default=0, help="split path scratch size")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.json"))
     args = ap.parse_args()
@@ -36,9 +37,15 @@ def main():
     except Exception:
         peak = 6650.0
     dev = torch.device("cuda")
-    n = int(args.gb * 1e9 / 8)
-    iq = torch.empty(n + 8, dtype=torch.complex64, device=dev)
-    torch.view_as_real(iq).normal_(0.0, 1e-2)
+    ebytes = {"": 8, "int16": 4, "int8": 2}[args.raw]
+    n = int(args.gb * 1e9 / ebytes)
+    if args.raw:
+        dt = torch.int16 if args.raw == "int16" else torch.int8
+        iq = torch.randint(-100, 100, (n + 8, 2), dtype=dt, device=dev)
+    else:
+        iq = torch.empty(n + 8, dtype=torch.complex64, device=dev)
+        torch.view_as_real(iq).normal_(0.0, 1e-2)
+    suffix = {"": "", "int16": "_i16", "int8": "_i8"}[args.raw]
     rows = []
     if args.scratch_mb:
         engine.set_split_scratch(args.scratch_mb << 20)
@@ -47,6 +54,10 @@ def main():
         todo = [("split", 13), ("split", 14), ("split", 15), ("split", 16)]
     for name, logn in todo:
         if args.only and args.only not in name:
+            continue
+        if name not in ("split", "generic") and name.endswith(("_i16", "_i8")) != bool(suffix):
+            continue
+        if suffix and name not in ("split", "generic") and not name.endswith(suffix):
             continue
         nfft = 1 << logn
         nint = n // args.ntime // nfft
@@ -77,7 +88,7 @@ def main():
             engine.set_variant(None)
             engine.set_force_generic(False)
         ms = float(np.median(ts))
-        nbytes = 8 * nfft * nint * args.ntime + 4 * nfft * args.ntime
+        nbytes = ebytes * nfft * nint * args.ntime + 4 * nfft * args.ntime
         row = {"variant": used, "nfft": nfft, "nint": nint, "ms": ms, "best_ms": float(min(ts)),
                "gsamples_s": nfft * nint * args.ntime / ms / 1e6, "gbs": nbytes / ms / 1e6,
                "frac": nbytes / ms / 1e6 / peak}
