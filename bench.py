@@ -216,6 +216,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-raw", action="store_true", help="skip the extra raw-int16 ingest e2e measurement")
     ap.add_argument("--variant", default=None, help="force a kernel variant (tuning)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -334,6 +335,8 @@ def main():
             else:
                 e2e = {"value": None, "unit": "Msamples/s", "error": "pinned host allocation failed on a rank"}
         line["e2e"] = e2e
+        if world == 1 and not args.no_raw:
+            line["e2e_raw_int16"] = e2e_raw_int16(torch, plan, iq, starts_np, nint, args)
     if rank == 0 and world == 1 and not args.no_cpu:
         ref = CpuReference(1, 32)
         ref.step()
@@ -384,6 +387,37 @@ def e2e_measure(torch, plan, iq_dev, starts_np, nint, args, dist=None):
             "d2h_bytes_per_step": int(d2h), "steps": len(times),
             "path": "psg_sti_host (pinned host complex64 recording + int64 start table -> dB image + dB median), "
                     "one channel per rank, all ranks at once"}
+
+
+def e2e_raw_int16(torch, plan, iq_dev, starts_np, nint, args):
+    """Extra (not the contract's ``e2e``): the same recording stored as Digital RF stores it --
+    complex int16 -- pushed through the typed host entry point with 1/ref folded into the kernel
+    (SURVEY.md section 8(f) N1).  Half the PCIe bytes of the complex64 path for the same samples."""
+    ref = 2.0 ** 15.5  # get_ref for int16 (drfProc.py:199-201)
+    nsamp = iq_dev.numel()
+    try:
+        host = torch.empty((nsamp, 2), dtype=torch.int16, pin_memory=True)
+    except Exception as exc:
+        return {"value": None, "unit": "Msamples/s", "error": f"pinned host allocation failed: {exc}"}
+    view = torch.view_as_real(iq_dev)
+    chunk = 1 << 26
+    for lo in range(0, nsamp, chunk):
+        hi = min(nsamp, lo + chunk)
+        host[lo:hi].copy_((view[lo:hi] * ref).round_().clamp_(-32767, 32767).to(torch.int16))
+    torch.cuda.synchronize()
+    h = host.numpy()
+    times = []
+    for i in range(1 + max(1, args.e2e_steps)):
+        t0 = time.perf_counter()
+        res = plan.host(h, starts_np, nint, NFFT, in_scale=1.0 / ref, want=("db", "med_db"))
+        dt = time.perf_counter() - t0
+        if i:
+            times.append(dt)
+    dt = float(np.mean(times))
+    return {"value": nint * NFFT * NTIME / dt / 1e6, "unit": "Msamples/s", "ms_per_step": dt * 1e3,
+            "h2d_bytes_per_step": int(4 * (starts_np[-1] + nint * NFFT - starts_np[0]) + 8 * NTIME),
+            "d2h_bytes_per_step": int(res["db"].nbytes + res["med_db"].nbytes), "steps": len(times),
+            "path": "psg_sti_host_typed(PSG_IQ_CI16): pinned host complex-int16 recording -> dB image + dB median"}
 
 
 if __name__ == "__main__":
