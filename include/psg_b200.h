@@ -46,7 +46,7 @@ typedef struct psg_plan psg_plan; /* opaque */
 typedef enum psg_status {
     PSG_OK = 0,
     PSG_ERR_ARG = -1,         /* bad argument (message says which) */
-    PSG_ERR_UNSUPPORTED = -2, /* nfft / layout not implemented on the GPU path */
+    PSG_ERR_UNSUPPORTED = -2, /* nfft outside [PSG_MIN_NFFT, PSG_MAX_NFFT] / layout not implemented */
     PSG_ERR_CUDA = -3,        /* CUDA runtime error (message carries cudaGetErrorString) */
     PSG_ERR_NODEVICE = -4,    /* no CUDA device, or device is not sm_100 */
     PSG_ERR_NOMEM = -5
@@ -68,7 +68,8 @@ int psg_device_count(void);
  * Kaiser window (drfProc.py:386 / :435 `sig.get_window(("kaiser", 1.7), nfft)`; scipy
  * windows/_windows.py:1318-1320, :2551), computed in float64 on the host, the spectrum scaling
  * 1/sum(w)^2 (scipy _spectral_py.py:2277) folded in, and the float64-accurate twiddle table.
- * nfft must be a power of two in [PSG_MIN_NFFT, PSG_MAX_NFFT].
+ * nfft: any integer in [PSG_MIN_NFFT, PSG_MAX_NFFT] (the viewer allows any length, drfview.py:474-479).
+ * Powers of two run the tuned kernels; other lengths run Bluestein's algorithm on the GPU.
  */
 #define PSG_MIN_NFFT 2
 #define PSG_MAX_NFFT 1048576

@@ -189,6 +189,7 @@ struct psg_plan {
     float2* d_tw = nullptr;
     float2* d_twp = nullptr;
     std::vector<float> h_win;
+    std::vector<double> h_win_d;  // w/sum(w) in float64 (Bluestein folds it into a complex table)
     // large-nfft split path (nfft = r0 * 4096): first-pass twiddles, the 4096-point sub-transform's
     // tables, the L2-sized scratch of first-pass outputs, the sub-spectra and carried sums
     float2* d_twa = nullptr;
@@ -200,6 +201,11 @@ struct psg_plan {
     size_t tmp_bytes = 0;
     float* d_carry = nullptr;
     size_t carry_bytes = 0;
+    // arbitrary nfft (Bluestein): convolution length 2^logm, tables
+    int logm = 0;
+    float2* d_aw = nullptr;
+    float2* d_bbr = nullptr;
+    float2* d_twm = nullptr;
     long long* d_colb = nullptr;
     size_t colb_bytes = 0;
     std::vector<long long> h_colb;
@@ -293,9 +299,9 @@ extern "C" int psg_variant_logn(int i) { return (i >= 0 && i < g_nvariants) ? g_
 
 // Host-side window table w[n]/sum(w) (fp64 math, fp32 result) without touching a device: what the
 // plan uploads.  Exposed so CPU-only tests can pin the table against scipy's.
-extern "C" int psg_window_table(int nfft, int window_kind, double beta, float* host_out, double* sum_out) {
-    if (nfft < 1 || !host_out) return fail(PSG_ERR_ARG, "psg_window_table: bad arguments");
-    std::vector<double> w(nfft);
+static int window_table_d(int nfft, int window_kind, double beta, std::vector<double>& w, double* sum_out) {
+    if (nfft < 1) return fail(PSG_ERR_ARG, "psg_window_table: bad arguments");
+    w.resize(nfft);
     if (window_kind == PSG_WINDOW_KAISER) {
         const double a = 0.5 * nfft, i0b = bessel_i0(beta);
         for (int n = 0; n < nfft; ++n) {
@@ -315,8 +321,79 @@ extern "C" int psg_window_table(int nfft, int window_kind, double beta, float* h
         c = (t - s) - y;
         s = t;
     }
-    for (int n = 0; n < nfft; ++n) host_out[n] = (float)(w[n] / s);
+    for (int n = 0; n < nfft; ++n) w[n] /= s;
     if (sum_out) *sum_out = s;
+    return PSG_OK;
+}
+
+extern "C" int psg_window_table(int nfft, int window_kind, double beta, float* host_out, double* sum_out) {
+    if (!host_out) return fail(PSG_ERR_ARG, "psg_window_table: bad arguments");
+    std::vector<double> w;
+    int rc = window_table_d(nfft, window_kind, beta, w, sum_out);
+    if (rc) return rc;
+    for (int n = 0; n < nfft; ++n) host_out[n] = (float)w[n];
+    return PSG_OK;
+}
+
+// in-place radix-2 FFT in float64 on the host (plan tables only)
+static void host_fft(std::vector<double>& re, std::vector<double>& im) {
+    const size_t n = re.size();
+    for (size_t i = 1, j = 0; i < n; ++i) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) { std::swap(re[i], re[j]); std::swap(im[i], im[j]); }
+    }
+    for (size_t len = 2; len <= n; len <<= 1) {
+        const double ang = -2.0 * M_PI / (double)len;
+        for (size_t i = 0; i < n; i += len)
+            for (size_t k = 0; k < len / 2; ++k) {
+                const double wr = cos(ang * (double)k), wi = sin(ang * (double)k);
+                const size_t a = i + k, b = a + len / 2;
+                const double xr = re[b] * wr - im[b] * wi, xi = re[b] * wi + im[b] * wr;
+                re[b] = re[a] - xr; im[b] = im[a] - xi;
+                re[a] += xr; im[a] += xi;
+            }
+    }
+}
+
+// Bluestein tables for a non power-of-two nfft (see sti_kernels.cuh): aw, bit-reversed B/M, W_M
+static int build_bluestein(psg_plan* p) {
+    const int N = p->nfft;
+    int logm = 1;
+    while ((1ll << logm) < 2ll * N - 1) ++logm;
+    const size_t M = (size_t)1 << logm;
+    p->logm = logm;
+    std::vector<double> cr(N), ci(N);
+    for (int n = 0; n < N; ++n) {
+        const long long q = ((long long)n * n) % (2ll * N);  // exact phase reduction
+        const double ang = M_PI * (double)q / (double)N;
+        cr[n] = cos(ang);
+        ci[n] = sin(ang);
+    }
+    std::vector<float2> aw(N), bbr(M), twm(M / 2);
+    for (int n = 0; n < N; ++n) aw[n] = make_float2((float)(p->h_win_d[n] * cr[n]), (float)(-p->h_win_d[n] * ci[n]));
+    std::vector<double> br(M, 0.0), bi(M, 0.0);
+    for (int n = 0; n < N; ++n) {
+        br[n] = cr[n]; bi[n] = ci[n];
+        if (n) { br[M - n] = cr[n]; bi[M - n] = ci[n]; }
+    }
+    host_fft(br, bi);
+    for (size_t i = 0; i < M; ++i) {
+        size_t r = 0;
+        for (int b = 0; b < logm; ++b) r |= ((i >> b) & 1) << (logm - 1 - b);
+        bbr[i] = make_float2((float)(br[r] / (double)M), (float)(bi[r] / (double)M));
+    }
+    for (size_t m = 0; m < M / 2; ++m) {
+        const double ang = -2.0 * M_PI * (double)m / (double)M;
+        twm[m] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+    CUDA_TRY(cudaMalloc(&p->d_aw, sizeof(float2) * N));
+    CUDA_TRY(cudaMalloc(&p->d_bbr, sizeof(float2) * M));
+    CUDA_TRY(cudaMalloc(&p->d_twm, sizeof(float2) * (M / 2)));
+    CUDA_TRY(cudaMemcpy(p->d_aw, aw.data(), sizeof(float2) * N, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(p->d_bbr, bbr.data(), sizeof(float2) * M, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(p->d_twm, twm.data(), sizeof(float2) * (M / 2), cudaMemcpyHostToDevice));
     return PSG_OK;
 }
 
@@ -325,10 +402,7 @@ extern "C" int psg_plan_create(psg_plan** out, int nfft, int window_kind, double
     *out = nullptr;
     if (nfft < PSG_MIN_NFFT || nfft > PSG_MAX_NFFT)
         return fail(PSG_ERR_UNSUPPORTED, "nfft=%d outside [%d, %d]", nfft, PSG_MIN_NFFT, PSG_MAX_NFFT);
-    const int logn = ilog2_exact(nfft);
-    if (logn < 0)
-        return fail(PSG_ERR_UNSUPPORTED, "nfft=%d is not a power of two (only power-of-two FFT lengths run on the GPU path)",
-                    nfft);
+    const int logn = ilog2_exact(nfft);  // -1: not a power of two -> Bluestein
     int sms = 0;
     int rc = check_device(device, &sms);
     if (rc) return rc;
@@ -342,8 +416,9 @@ extern "C" int psg_plan_create(psg_plan** out, int nfft, int window_kind, double
     p->h_win.resize(nfft);
     p->attr_done.assign(g_nvariants, 0);
     p->occ.assign(g_nvariants, 0);
-    rc = psg_window_table(nfft, window_kind, beta, p->h_win.data(), nullptr);
+    rc = window_table_d(nfft, window_kind, beta, p->h_win_d, nullptr);
     if (rc) { delete p; return rc; }
+    for (int n = 0; n < nfft; ++n) p->h_win[n] = (float)p->h_win_d[n];
 
     // full twiddle table (generic kernels) and the per-pass tables of every tuned variant layout
     std::vector<float2> tw(nfft);
@@ -363,6 +438,10 @@ extern "C" int psg_plan_create(psg_plan** out, int nfft, int window_kind, double
     PLAN_TRY(cudaMemcpy(p->d_tw, tw.data(), sizeof(float2) * nfft, cudaMemcpyHostToDevice));
     PLAN_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
 #undef PLAN_TRY
+    if (logn < 0) {
+        rc = build_bluestein(p);
+        if (rc) { psg_plan_destroy(p); return rc; }
+    }
     p->variant_name[0] = 0;
     *out = p;
     return PSG_OK;
@@ -381,6 +460,9 @@ extern "C" int psg_plan_destroy(psg_plan* p) {
     cudaFree(p->d_tmp);
     cudaFree(p->d_carry);
     cudaFree(p->d_colb);
+    cudaFree(p->d_aw);
+    cudaFree(p->d_bbr);
+    cudaFree(p->d_twm);
     cudaFree(p->d_partial);
     cudaFree(p->d_gwork);
     cudaFree(p->d_gacc);
@@ -647,6 +729,73 @@ static int run_split(psg_plan* p, StiArgs a, int ncs, int frames_per_col, cudaSt
     return PSG_OK;
 }
 
+// non power-of-two nfft: Bluestein kernel, work buffer in shared memory up to M = 16384
+static int run_bluestein(psg_plan* p, StiArgs a, int ncs, int frames_per_col, cudaStream_t st) {
+    const int N = p->nfft;
+    const size_t M = (size_t)1 << p->logm;
+    snprintf(p->variant_name, sizeof(p->variant_name), "bluestein_m%zu", M);
+    const size_t smem_need = M * 8 + (size_t)N * 4;
+    const bool in_smem = smem_need <= 200 * 1024;
+    const int iters = frames_per_col;
+    int nsplit = std::max(1, (iters + 255) / 256);
+    const long long target = (long long)p->sms * (in_smem ? 2 : 2);
+    if ((long long)ncs * nsplit < target) nsplit = (int)std::min<long long>(std::max(1, iters / 4), (target + ncs - 1) / ncs);
+    nsplit = std::max(nsplit, 1);
+    const int chunk = (iters + nsplit - 1) / nsplit;
+    nsplit = (iters + chunk - 1) / chunk;
+    a.gpc = 1;
+    a.chunk = chunk;
+    a.nsplit = nsplit;
+    if (nsplit > 1) {
+        const size_t need = (size_t)ncs * nsplit * N;
+        size_t have_b = p->partial_elems * sizeof(float);
+        int rc = ensure_buffer((void**)&p->d_partial, &have_b, need * sizeof(float));
+        p->partial_elems = have_b / sizeof(float);
+        if (rc) return rc;
+        a.partial = p->d_partial;
+    }
+    const long long items = (long long)ncs * nsplit;
+    long long grid = std::min<long long>(items, (long long)p->sms * 4);
+    float2* gwork = nullptr;
+    float* gacc = nullptr;
+    size_t smem = 0;
+    if (in_smem) {
+        smem = smem_need;
+        CUDA_TRY(cudaFuncSetAttribute((const void*)sti_bluestein_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      200 * 1024));
+    } else {
+        grid = std::min<long long>(items, (long long)p->sms * 2);
+        const size_t slab = M + (size_t)(N + 1) / 2;  // float2 units: work buffer + accumulators
+        if (p->gwork_slabs < (size_t)grid * slab) {
+            if (p->d_gwork) { CUDA_TRY(cudaStreamSynchronize(st)); cudaFree(p->d_gwork); cudaFree(p->d_gacc); }
+            p->d_gwork = nullptr; p->d_gacc = nullptr; p->gwork_slabs = 0;
+            cudaError_t e1 = cudaMalloc(&p->d_gwork, sizeof(float2) * (size_t)grid * M);
+            cudaError_t e2 = cudaMalloc(&p->d_gacc, sizeof(float) * (size_t)grid * N);
+            if (e1 != cudaSuccess || e2 != cudaSuccess) return fail(PSG_ERR_NOMEM, "scratch for nfft=%d failed", N);
+            p->gwork_slabs = (size_t)grid * slab;
+        }
+        gwork = p->d_gwork;
+        gacc = p->d_gacc;
+    }
+    BluesteinArgs b;
+    b.aw = p->d_aw;
+    b.bbr = p->d_bbr;
+    b.twm = p->d_twm;
+    b.n = N;
+    b.logm = p->logm;
+    void* args[] = {(void*)&a, (void*)&b, (void*)&gwork, (void*)&gacc};
+    CUDA_TRY(cudaLaunchKernel((const void*)sti_bluestein_kernel, dim3((unsigned)grid), dim3(256), args, smem, st));
+    g_launches++;
+    if (nsplit > 1) {
+        const size_t total = (size_t)ncs * N;
+        const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)p->sms * 16);
+        sti_finalize_kernel<<<blocks, 256, 0, st>>>(a.partial, nsplit, N, (size_t)ncs, a.scale, a.eps, a.out_lin, a.out_db);
+        g_launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return PSG_OK;
+}
+
 static int iq_bytes(int iq_type) { return iq_type == PSG_IQ_C64 ? 8 : iq_type == PSG_IQ_CI16 ? 4 : iq_type == PSG_IQ_CI8 ? 2 : 0; }
 
 extern "C" int psg_sti_run(psg_plan* p, const void* iq_dev, int64_t sample_stride, int64_t sub_stride, int nsub,
@@ -698,6 +847,7 @@ extern "C" int psg_sti_run_typed(psg_plan* p, const void* iq_dev, int iq_type, i
     a.chunk = frames_per_col;
     a.nsplit = 1;
 
+    if (p->logn < 0) return run_bluestein(p, a, ncs, frames_per_col, st);
     const bool tma_ok = sample_stride == 1 && (reinterpret_cast<uintptr_t>(iq_dev) & 15) == 0;
     const Variant* v = nullptr;
     if (!g_force_generic.load()) {

@@ -742,3 +742,90 @@ __global__ void __launch_bounds__(256) sti_interleave_kernel(const InterleaveArg
         }
     }
 }
+
+// ---- arbitrary (non power-of-two) nfft: Bluestein's chirp-z algorithm ----------------------------
+// The viewer allows any integer FFT length 32..2^20 (drfview.py:474-479) and scipy's FFT takes them
+// all.  With c[n] = exp(+j*pi*n^2/N):  X[k] = conj(c[k]) * sum_n (x[n] w[n] conj(c[n])) c[k-n], so
+// |X[k]|^2 = |(a (*) c)[k]|^2 with a[n] = x[n] w[n] conj(c[n]) -- the unit-modulus post-chirp drops
+// out of the power.  The circular convolution of length M = 2^m >= 2N-1 runs as
+// IFFT_M(FFT_M(a) .* B), B = FFT_M(wrapped chirp)/M precomputed in float64 on the host.  Forward
+// transform: radix-2 DIF (natural in, bit-reversed out); B is stored bit-reversed; inverse: radix-2
+// DIT (bit-reversed in, natural out), so no reordering pass is needed.  Simple shared-memory
+// radix-2 code: functional coverage of the reference's full nfft range, not a tuned path.
+struct BluesteinArgs {
+    const float2* aw;   // [N]  w[n]/sum(w) * conj(c[n])
+    const float2* bbr;  // [M]  FFT_M(b)[bitrev(i)] / M
+    const float2* twm;  // [M/2] exp(-2*pi*j*m/M)
+    int n, logm;
+};
+
+__global__ void __launch_bounds__(256) sti_bluestein_kernel(const StiArgs a, const BluesteinArgs b, float2* gwork,
+                                                            float* gacc) {
+    const int N = b.n, M = 1 << b.logm;
+    extern __shared__ __align__(16) float2 smem[];
+    float2* buf = gwork ? gwork + (size_t)blockIdx.x * M : smem;
+    float* accs = gacc ? gacc + (size_t)blockIdx.x * N : reinterpret_cast<float*>(smem + M);
+    const int t = threadIdx.x, nt = blockDim.x;
+    const int ncs = a.ncol * a.nsub;
+    for (int item = blockIdx.x; item < ncs * a.nsplit; item += gridDim.x) {
+        const int split = item % a.nsplit;
+        const int cs = item / a.nsplit;
+        const int col = cs % a.ncol, sub = cs / a.ncol;
+        const int k0 = split * a.chunk;
+        const int k1 = min(a.nfr, k0 + a.chunk);
+        long long src = a.col_off[col] + (long long)sub * a.sub_stride + (long long)k0 * a.hop_elems;
+        __syncthreads();
+        for (int i = t; i < N; i += nt) accs[i] = 0.f;
+        for (int k = k0; k < k1; ++k, src += a.hop_elems) {
+            __syncthreads();
+            for (int i = t; i < M; i += nt)
+                buf[i] = (i < N) ? cmul(ldg_iq_rt(a.iq_type, a.iq, src + (long long)i * a.sample_stride), __ldg(b.aw + i))
+                                 : make_float2(0.f, 0.f);
+            for (int s = M >> 1; s >= 1; s >>= 1) {  // forward, DIF
+                __syncthreads();
+                const int step = (M >> 1) / s;
+                for (int i = t; i < (M >> 1); i += nt) {
+                    const int j = i & (s - 1);
+                    const int base = ((i / s) * 2 * s) + j;
+                    const cf u = buf[base], v = buf[base + s];
+                    buf[base] = cadd(u, v);
+                    const cf d = csub(u, v);
+                    buf[base + s] = (s > 1) ? cmul(d, __ldg(b.twm + (size_t)j * step)) : d;
+                }
+            }
+            __syncthreads();
+            for (int i = t; i < M; i += nt) buf[i] = cmul(buf[i], __ldg(b.bbr + i));
+            for (int s = 1; s <= (M >> 1); s <<= 1) {  // inverse, DIT, conjugate twiddles
+                __syncthreads();
+                const int step = (M >> 1) / s;
+                for (int i = t; i < (M >> 1); i += nt) {
+                    const int j = i & (s - 1);
+                    const int base = ((i / s) * 2 * s) + j;
+                    const cf u = buf[base];
+                    cf v = buf[base + s];
+                    if (s > 1) v = cmulc(v, __ldg(b.twm + (size_t)j * step));
+                    buf[base] = cadd(u, v);
+                    buf[base + s] = csub(u, v);
+                }
+            }
+            __syncthreads();
+            for (int i = t; i < N; i += nt) {
+                const cf v = buf[i];
+                accs[i] = fmaf(v.x, v.x, fmaf(v.y, v.y, accs[i]));
+            }
+        }
+        __syncthreads();
+        const int half = N / 2;  // np.fft.fftshift: out[(k + N//2) mod N] = in[k]
+        for (int i = t; i < N; i += nt) {
+            int idx = i + half;
+            if (idx >= N) idx -= N;
+            if (a.nsplit > 1) {
+                a.partial[((size_t)cs * a.nsplit + split) * N + idx] = accs[i];
+            } else {
+                const float p = accs[i] * a.scale;
+                if (a.out_lin) a.out_lin[(size_t)cs * N + idx] = p;
+                if (a.out_db) a.out_db[(size_t)cs * N + idx] = power_to_db(p, a.eps);
+            }
+        }
+    }
+}

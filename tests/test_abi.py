@@ -95,9 +95,9 @@ def test_no_device_fails_loudly_and_there_is_no_fallback():
 def test_argument_errors_map_to_python_exceptions():
     lib = _lib.load()
     h = C.c_void_p()
-    assert lib.psg_plan_create(C.byref(h), 96, 0, 1.7, 0) == _lib.PSG_ERR_UNSUPPORTED  # not a power of two
-    assert b"power of two" in lib.psg_last_error()
-    assert lib.psg_plan_create(C.byref(h), 1 << 21, 0, 1.7, 0) == _lib.PSG_ERR_UNSUPPORTED
+    assert lib.psg_plan_create(C.byref(h), 1 << 21, 0, 1.7, 0) == _lib.PSG_ERR_UNSUPPORTED  # above PSG_MAX_NFFT
+    assert b"outside" in lib.psg_last_error()
+    assert lib.psg_plan_create(C.byref(h), 1, 0, 1.7, 0) == _lib.PSG_ERR_UNSUPPORTED
     assert lib.psg_plan_create(None, 1024, 0, 1.7, 0) == _lib.PSG_ERR_ARG
     assert lib.psg_sti_run(None, None, 1, 0, 1, None, 1, 1, 1, 1.0, 1e-15, None, None, None) == _lib.PSG_ERR_ARG
     assert lib.psg_plan_destroy(None) == 0

@@ -76,10 +76,34 @@ def test_zero_input_hits_db_floor(dp):
     assert sdb.dtype == np.float32
 
 
-def test_non_power_of_two_fails_loudly(dp):
+def test_non_power_of_two_matches_reference_golden(dp):
+    """The viewer allows any FFT length (drfview.py:474-479); non powers of two run Bluestein."""
     g = load("sti_r_96x5_nonpow2")
-    with pytest.raises(NotImplementedError):
-        dp.sti_proc_data(g["d1"], float(g["sr"]), 96)
+    f, sxx, med = dp.sti_proc_data(g["d1"], float(g["sr"]), 96)
+    assert np.array_equal(f, g["f"]) and sxx.shape == g["sxx"].shape and sxx.dtype == g["sxx"].dtype
+    assert_psd_close(sxx, g["sxx"], noise_like=False, what="nfft=96")
+    assert_psd_close(med, g["med"], noise_like=False, what="nfft=96 median")
+
+
+@pytest.mark.parametrize("nfft", [3, 5, 7, 33, 100, 1000, 1023, 1025, 4095, 5000, 8191, 12000, 20000, 100000])
+@pytest.mark.parametrize("mode", ["R", "A"])
+def test_arbitrary_nfft_against_float64_oracle(torch, nfft, mode):
+    """Odd, even, prime and large non power-of-two lengths (work buffer in shared memory up to
+    M = 16384, in global scratch above), fftshift for odd N, oracle = float64 numpy."""
+    from pyspectrogram_b200 import engine
+    rng = np.random.default_rng(nfft)
+    nfr = 1 if mode == "R" else 3
+    ncol = 4 if nfft <= 20000 else 2
+    n = nfft * nfr * ncol + nfft + 3
+    x = _recording(rng, n)
+    starts = (np.arange(ncol) * nfft * nfr + np.arange(ncol) % 2).astype(np.int64)
+    plan = engine.StiPlan(nfft)
+    lin, db = plan.run(torch.from_numpy(x).cuda(), torch.from_numpy(starts).cuda(), nfr, nfft, want_lin=True, want_db=True)
+    assert plan.variant.startswith("bluestein")
+    ref = _oracle_columns(x, starts, nfft, nfr, nfft)
+    assert_psd_close(lin.cpu().numpy()[0].T, ref.T, noise_like=False, what=f"nfft={nfft} {plan.variant}")
+    assert_db_close(db.cpu().numpy()[0].T, 10 * np.log10(ref.T.astype(np.float32) + np.float32(1e-15)),
+                    ref_lin=ref.T, what=f"nfft={nfft} dB")
 
 
 def test_short_input_raises_value_error(dp):
