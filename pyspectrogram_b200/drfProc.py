@@ -349,7 +349,7 @@ class DrfProcessor(QRunnable):
     """
 
     def __init__(self, datasource, drfdir, tabID, fftbins, n_int, ntime, *args, integrate=False, device=0,
-                 reader=None, raw_ingest=False, **kwargs):
+                 reader=None, raw_ingest=False, resident=False, resident_max_bytes=32 << 30, **kwargs):
         super(DrfProcessor, self).__init__()
         self.drfIn = DrfInput(drfdir, reader=reader)
         self.drf_path = Path(drfdir).expanduser()
@@ -360,6 +360,11 @@ class DrfProcessor(QRunnable):
         self.integrate = integrate
         self.device = device
         self.raw_ingest = raw_ingest  # ship the stored integer samples to the GPU, fold 1/ref into the kernel
+        # keep the recording window on the GPU between iterations and address frames in place
+        # (SURVEY.md section 8(f) N2); falls back to the reference's per-bin reads when the window is sparse
+        self.resident = resident
+        self.resident_max_bytes = int(resident_max_bytes)
+        self._cache = {}
         self.bnds = self.drfIn.time_bnds
         self.chan_listing = list(self.drfIn.chan_2sub.keys())
         self.sub_chan_list = list(self.drfIn.chan_entries.keys())
@@ -391,6 +396,10 @@ class DrfProcessor(QRunnable):
             st_time, end_time = self.bnds
         s_samp = _time_to_sample(st_time, sr)
         e_samp = _time_to_sample(end_time, sr)
+        if self.resident:
+            out = self._iterate_resident(i, ichan, sr, s_samp, e_samp)
+            if out is not None:
+                return out
         ref = 1.0
         if self.raw_ingest and hasattr(self.drfIn.drf_Obj, "read_vector_raw") and self.drfIn.ref_dict[ichan] != 1.0:
             n_st, d1, ref = self.drfIn.read_sti_raw(s_samp, ichan, e_samp, self.fftbins, self.n_int, self.ntime)
@@ -403,6 +412,46 @@ class DrfProcessor(QRunnable):
                                                      device=self.device, ref=ref)
         self.freqs_all = f
         self.signals.iterated.emit(i, self.tabID, time_ar, self.freqs_all, sxx_dbfs, sxx_med_dbfs)
+        return time_ar, f, sxx_dbfs, sxx_med_dbfs
+
+    def _iterate_resident(self, i, ichan, sr, s_samp, e_samp):
+        """Loop body on a device-resident recording window: one contiguous read of what is not yet on
+        the GPU, frames addressed through the start table (no gather, no re-upload).  Returns None
+        when the window is too sparse or too large to keep resident (the caller then reads per bin)."""
+        nfft, nint, ntime = int(self.fftbins), int(self.n_int), int(self.ntime)
+        frames = nint if self.integrate else 1
+        n_st = engine.frame_starts(s_samp, e_samp, nfft, nint, ntime)
+        lo, hi = int(n_st.min()), int(n_st.max()) + frames * nfft
+        nsub = len(self.drfIn.chan_2sub[ichan])
+        raw = self.raw_ingest and hasattr(self.drfIn.drf_Obj, "read_vector_raw") and self.drfIn.ref_dict[ichan] != 1.0
+        ebytes = (4 if raw else 8) * nsub
+        used = ntime * frames * nfft
+        if (hi - lo) * ebytes > self.resident_max_bytes or (hi - lo) > 8 * used:
+            return None
+        cache = self._cache.get(ichan)
+        if cache is None:
+            cache = self._cache[ichan] = engine.RecordingCache(self.device)
+        ref = self.drfIn.ref_dict[ichan]
+        if raw:
+            read = lambda st, n: self.drfIn.read_raw(st, n, ichan)
+            in_scale = 1.0 / ref
+        else:
+            read = lambda st, n: self.drfIn.read(st, n, ichan)  # already divided by ref (drfProc.py:129)
+            in_scale = 1.0
+        buf, base = cache.ensure(read, lo, hi)
+        torch = engine._torch()
+        plan = engine.get_plan(nfft, self.device)
+        offs = torch.from_numpy(((n_st - base) * nsub).astype(np.int64)).to(buf.device)
+        _, db = plan.run(buf, offs, frames, nfft, sample_stride=nsub, sub_stride=1, nsub=nsub, in_scale=in_scale,
+                         eps=_EPS, want_lin=True, want_db=True)
+        lin = _
+        _, mdb = plan.median(lin, eps=_EPS, want_lin=False, want_db=True)
+        sxx_dbfs = db.permute(2, 1, 0).cpu().numpy()      # (nfft, ntime, nsub) as the viewer indexes it
+        sxx_med_dbfs = mdb.t().cpu().numpy()               # (nfft, nsub)
+        time_ar = np.array([_sample_to_datetime(istime, int(sr)) for istime in n_st])
+        f = _freq_axis(nfft, sr)
+        self.freqs_all = f
+        self.signals.iterated.emit(i, self.tabID, time_ar, f, sxx_dbfs, sxx_med_dbfs)
         return time_ar, f, sxx_dbfs, sxx_med_dbfs
 
     @pyqtSlot()

@@ -190,6 +190,66 @@ def _host_iq(iq):
     raise TypeError(f"iq dtype {iq.dtype} is not supported (complex64, int16 pairs, int8 pairs)")
 
 
+class RecordingCache:
+    """Device-resident window of one channel's recording.
+
+    The reference re-reads ``ntime`` slices from disk and rebuilds the ``(nfft*nint, ntime, nsub)``
+    array on every pass of the worker loop (drfProc.py:160-166, :275-321).  This cache keeps the
+    samples ``[lo, hi)`` of a channel on the GPU as ``[sample][nsub]`` (complex64 or raw integer
+    pairs); ``ensure`` reads only what is missing -- nothing when the same window is asked again, just
+    the new tail when a streaming window slides forward -- and the STI kernel addresses frames in
+    place through the start table (``col_offsets = (n_st - lo) * nsub``).
+    """
+
+    def __init__(self, device: int = 0, slack: float = 0.25):
+        self.device = int(device)
+        self.slack = float(slack)
+        self.lo = self.hi = 0
+        self.buf = None       # torch tensor [capacity, nsub(, 2)]
+        self.samples_read = 0  # samples fetched from the reader so far (tests / stats)
+
+    def _upload(self, arr):
+        torch = _torch()
+        arr = np.ascontiguousarray(arr)
+        if arr.dtype.fields is not None:  # Digital RF's ('r','i') integer pairs
+            base = next(iter(arr.dtype.fields.values()))[0]
+            arr = arr.view(base).reshape(arr.shape + (2,))
+        if arr.dtype == np.complex64:
+            arr = arr.reshape(arr.shape[0], -1)
+        elif arr.dtype in (np.int16, np.int8):
+            arr = arr.reshape(arr.shape[0], -1, 2)
+        else:
+            arr = arr.astype(np.complex64).reshape(arr.shape[0], -1)
+        return torch.from_numpy(arr).to(f"cuda:{self.device}", non_blocking=False)
+
+    def ensure(self, read, lo: int, hi: int):
+        """Make ``[lo, hi)`` resident; ``read(start, n)`` returns ``n`` samples from ``start`` as an
+        ``(n,)`` / ``(n, nsub)`` array.  Returns the tensor and the absolute index of its row 0."""
+        torch = _torch()
+        lo, hi = int(lo), int(hi)
+        if self.buf is not None and self.lo <= lo and hi <= self.hi:
+            return self.buf, self.lo
+        if self.buf is not None and self.lo <= lo < self.hi <= hi:
+            # sliding window: keep [lo, self.hi), fetch only [self.hi, hi)
+            new = self._upload(read(self.hi, hi - self.hi))
+            self.samples_read += hi - self.hi
+            keep = self.buf[lo - self.lo: self.hi - self.lo]
+            cap = int((hi - lo) * (1.0 + self.slack))
+            out = torch.empty((cap,) + tuple(keep.shape[1:]), dtype=keep.dtype, device=keep.device)
+            out[: keep.shape[0]] = keep
+            out[keep.shape[0]: keep.shape[0] + new.shape[0]] = new
+            self.buf, self.lo, self.hi = out, lo, hi
+            return self.buf, self.lo
+        self.buf = self._upload(read(lo, hi - lo))
+        self.samples_read += hi - lo
+        self.lo, self.hi = lo, hi
+        return self.buf, self.lo
+
+    def drop(self):
+        self.buf = None
+        self.lo = self.hi = 0
+
+
 _plans = {}
 _plans_lock = threading.Lock()
 

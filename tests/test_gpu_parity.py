@@ -449,6 +449,63 @@ def test_drfprocessor_iteration_with_fake_reader(dp):
     assert_db_close(mdb, ref_port.to_dbfs(mr), ref_lin=mr, what="processor median dB")
 
 
+@pytest.mark.parametrize("nsub", [1, 2])
+@pytest.mark.parametrize("raw_ingest", [False, True])
+def test_resident_recording_cache_matches_per_bin_reads(dp, nsub, raw_ingest):
+    """the worker loop on a device-resident window gives the same dB arrays
+    as the reference's read_sti gather, reads every sample once, and reads nothing when the same
+    window is processed again."""
+    from tests.fake_drf import FakeReader
+    rng = np.random.default_rng(31 + nsub)
+    n = 1 << 17
+    shape = (n, nsub) if nsub > 1 else (n,)
+    data = np.round((rng.standard_normal(shape) + 1j * rng.standard_normal(shape)) * 3000).astype(np.complex64)
+    for integrate in (False, True):
+        outs = []
+        for resident in (False, True):
+            reader = FakeReader({"ch0": data}, sample_rate=1000000, first_sample=1_700_000_000 * 1000000, int16=True)
+            proc = dp.DrfProcessor("file", "/nonexistent", 1, 512.0, 4.0, 50.0, reader=reader, integrate=integrate,
+                                   raw_ingest=raw_ingest, resident=resident)
+            outs.append(proc.iterate_once(0))
+            if resident:
+                cache = proc._cache["ch0"]
+                assert cache.samples_read == cache.hi - cache.lo <= n
+                nreads = len(reader.reads)
+                again = proc.iterate_once(1)
+                assert len(reader.reads) == nreads and cache.samples_read == cache.hi - cache.lo
+                assert np.array_equal(again[2], outs[-1][2]) and np.array_equal(again[3], outs[-1][3])
+        (t0, f0, s0, m0), (t1, f1, s1, m1) = outs
+        assert np.array_equal(f0, f1) and np.array_equal(t0, t1)
+        assert s1.shape == (512, 50, nsub) and m1.shape == (512, nsub)
+        s0 = s0.reshape(s1.shape)
+        m0 = m0.reshape(m1.shape)
+        assert np.abs(s0 - s1).max() <= 1e-3 and np.abs(m0 - m1).max() <= 1e-3, (integrate, nsub, raw_ingest)
+
+
+def test_resident_cache_sliding_window_reads_only_the_new_tail(torch):
+    from pyspectrogram_b200 import engine
+    rng = np.random.default_rng(2)
+    rec = (rng.standard_normal(50000) + 1j * rng.standard_normal(50000)).astype(np.complex64)
+    calls = []
+
+    def read(st, n):
+        calls.append((st, n))
+        return rec[st:st + n]
+
+    cache = engine.RecordingCache(0)
+    buf, base = cache.ensure(read, 1000, 21000)
+    assert base == 1000 and calls == [(1000, 20000)]
+    assert np.array_equal(buf[:20000, 0].cpu().numpy(), rec[1000:21000])
+    buf, base = cache.ensure(read, 5000, 20000)  # inside the window: nothing read
+    assert base == 1000 and len(calls) == 1
+    buf, base = cache.ensure(read, 9000, 30000)  # slid forward: only [21000, 30000) is read
+    assert base == 9000 and calls[-1] == (21000, 9000) and cache.samples_read == 29000
+    assert np.array_equal(buf[:21000, 0].cpu().numpy(), rec[9000:30000])
+    buf, base = cache.ensure(read, 40000, 45000)  # disjoint: re-read
+    assert base == 40000 and calls[-1] == (40000, 5000)
+    assert np.array_equal(buf[:5000, 0].cpu().numpy(), rec[40000:45000])
+
+
 def test_large_workload_properties(torch):
     """Size-independent properties at a bench-like size (1 GiB of IQ, nfft=4096, nint=128):
     Parseval (sum of the PSD column == mean windowed frame energy * N / sum(w)^2), a unit tone

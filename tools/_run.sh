@@ -1,1 +1,1 @@
-(timeout 1200 python -m pytest tests -m gpu -x -q -k "non_power or arbitrary" 2>&1 | tail -15)
+(timeout 1200 python -m pytest tests -m gpu -x -q -k "resident" 2>&1 | tail -25)
