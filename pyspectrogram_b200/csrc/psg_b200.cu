@@ -122,7 +122,14 @@ static const Variant g_variants[] = {
     make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 1, 2, 2>("ldg12_16x16x16_f1_x1_pf2"),
     make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 2, 2, 2>("ldg12_16x16x16_f1_x2_pf2"),
     make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 1, 2, 4>("ldg12_16x16x16_f1_x1_pf4"),
+    make_variant<12, 8, 8, 8, 8, 8, 1, M, 2, 1, 2>("tma12_8x8x8x8_f1_s2x1"),
+    make_variant<12, 8, 8, 8, 8, 8, 1, M, 3, 2, 2>("tma12_8x8x8x8_f1_s3x2"),
+    make_variant<12, 16, 16, 4, 8, 8, 1, M, 2, 1, 2>("tma12_16x4x8x8_f1_s2x1"),
     make_variant<13, 16, 2, 16, 16, 16, 1, M, 2, 1, 1>("tma13_2x16x16x16_f1_s2x1"),
+    make_variant<13, 16, 16, 8, 8, 8, 1, M, 2, 1, 1>("tma13_16x8x8x8_f1_s2x1"),
+    make_variant<13, 16, 8, 16, 8, 8, 1, M, 2, 1, 1>("tma13_8x16x8x8_f1_s2x1"),
+    make_variant<13, 16, 16, 16, 4, 8, 1, M, 2, 1, 1>("tma13_16x16x4x8_f1_s2x1"),
+    make_variant<13, 16, 8, 8, 8, 16, 1, M, 1, 1, 1>("tma13_8x8x8x16_f1_s1x1"),
     make_variant<13, 16, 8, 8, 8, 16, 1, M, 2, 1, 1>("tma13_8x8x8x16_f1_s2x1"),
     make_variant<13, 16, 2, 16, 16, 16, 1, L, 1, 1, 1>("ldg13_2x16x16x16_f1"),
     // raw integer IQ ingest (complex int16 / int8): the default geometry of every size, both loaders
@@ -134,7 +141,7 @@ static const Variant g_variants[] = {
     make_variant<11, 16, 8, 16, 16, 1, 1, L, 1, 2, 4, 0, IQ_CI16>("ldg11_8x16x16_f1_i16"),
     make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 1, 2, 0, IQ_CI16>("tma12_16x16x16_f1_s2x1_i16"),
     make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 2, 2, 0, IQ_CI16>("ldg12_16x16x16_f1_i16"),
-    make_variant<13, 16, 8, 8, 8, 16, 1, M, 2, 1, 1, 0, IQ_CI16>("tma13_8x8x8x16_f1_s2x1_i16"),
+    make_variant<13, 16, 16, 8, 8, 8, 1, M, 2, 1, 1, 0, IQ_CI16>("tma13_16x8x8x8_f1_s2x1_i16"),
     make_variant<13, 16, 2, 16, 16, 16, 1, L, 1, 1, 1, 0, IQ_CI16>("ldg13_2x16x16x16_f1_i16"),
     make_variant<8, 16, 16, 16, 1, 1, 8, L, 1, 2, 4, 0, IQ_CI8>("ldg8_16x16_f8_i8"),
     make_variant<9, 8, 8, 8, 8, 1, 1, L, 1, 2, 16, 0, IQ_CI8>("ldg9_8x8x8_f1_i8"),
@@ -144,7 +151,7 @@ static const Variant g_variants[] = {
     make_variant<11, 16, 8, 16, 16, 1, 1, L, 1, 2, 4, 0, IQ_CI8>("ldg11_8x16x16_f1_i8"),
     make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 1, 2, 0, IQ_CI8>("tma12_16x16x16_f1_s2x1_i8"),
     make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 2, 2, 0, IQ_CI8>("ldg12_16x16x16_f1_i8"),
-    make_variant<13, 16, 8, 8, 8, 16, 1, M, 2, 1, 1, 0, IQ_CI8>("tma13_8x8x8x16_f1_s2x1_i8"),
+    make_variant<13, 16, 16, 8, 8, 8, 1, M, 2, 1, 1, 0, IQ_CI8>("tma13_16x8x8x8_f1_s2x1_i8"),
     make_variant<13, 16, 2, 16, 16, 16, 1, L, 1, 1, 1, 0, IQ_CI8>("ldg13_2x16x16x16_f1_i8"),
 };
 #undef L
@@ -161,7 +168,7 @@ static const Variant* variant_by_name(const char* name) {
 // full-coverage Mode A): small CTAs (one frame group) win from 512 up, the TMA ring with two
 // stages and one exchange buffer wins from 1024 up, the direct LDG loader below that.
 static const char* const g_default_tma[] = {"ldg8_16x16_f8", "ldg9_8x8x8_f1", "tma10_4x16x16_f1_s2x1",
-                                            "tma11_8x16x16_f1_s2x1", "tma12_16x16x16_f1_s2x1", "tma13_8x8x8x16_f1_s2x1"};
+                                            "tma11_8x16x16_f1_s2x1", "tma12_16x16x16_f1_s2x1", "tma13_16x8x8x8_f1_s2x1"};
 static const char* const g_default_ldg[] = {"ldg8_16x16_f8", "ldg9_8x8x8_f1", "ldg10_4x16x16_f1",
                                             "ldg11_8x16x16_f1", "ldg12_16x16x16_f1", "ldg13_2x16x16x16_f1"};
 

@@ -506,6 +506,38 @@ def test_resident_cache_sliding_window_reads_only_the_new_tail(torch):
     assert np.array_equal(buf[:5000, 0].cpu().numpy(), rec[40000:45000])
 
 
+def test_seven_worker_threads_share_the_library(dp):
+    """The viewer runs up to 7 workers at once (drfview.py:177-178): concurrent calls from Python
+    threads -- same nfft (one shared, locked plan) and different nfft (separate plans) -- give the
+    single-threaded results."""
+    import threading
+    rng = np.random.default_rng(17)
+    cases = []
+    for k, nfft in enumerate([256, 1024, 1024, 4096, 4096, 1000, 16384]):
+        d1 = ((rng.standard_normal((nfft * 2, 12, 2)) + 1j * rng.standard_normal((nfft * 2, 12, 2))) * 1e-2).astype(np.complex64)
+        cases.append((nfft, d1, k % 2 == 1))
+    expect = [dp.sti_proc_data_db(d1, 1.0e6, nfft, integrate=integ) for nfft, d1, integ in cases]
+    got = [None] * len(cases)
+    errs = []
+
+    def work(i):
+        try:
+            nfft, d1, integ = cases[i]
+            for _ in range(5):
+                got[i] = dp.sti_proc_data_db(d1, 1.0e6, nfft, integrate=integ)
+        except Exception as exc:  # pragma: no cover
+            errs.append((i, exc))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(cases))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs, errs
+    for (f0, s0, m0), (f1, s1, m1) in zip(expect, got):
+        assert np.array_equal(f0, f1) and np.array_equal(s0, s1) and np.array_equal(m0, m1)
+
+
 def test_large_workload_properties(torch):
     """Size-independent properties at a bench-like size (1 GiB of IQ, nfft=4096, nint=128):
     Parseval (sum of the PSD column == mean windowed frame energy * N / sum(w)^2), a unit tone

@@ -1,1 +1,1 @@
-(timeout 1200 python -m pytest tests -m gpu -x -q -k "resident" 2>&1 | tail -25)
+(timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -8)
