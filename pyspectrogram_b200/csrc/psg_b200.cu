@@ -52,15 +52,15 @@ static int fail(int code, const char* fmt, ...) {
 // ------------------------------------------------------------------------------------------------
 struct Variant {
     const char* name;
-    int logn, F, loader, threads, minb, iqt;
+    int logn, F, loader, threads, minb, iqt, twp;
     size_t smem;
     const void* fn;
 };
 
 template <int LOGN, int E, int R0, int R1, int R2, int R3, int F, int LOADER, int STAGES, int XBUF, int MINB, int PFL2 = 0,
-          int IQT = IQ_C64>
+          int IQT = IQ_C64, int TWP = 0>
 static Variant make_variant(const char* name) {
-    using CF = FusedCfg<LOGN, E, R0, R1, R2, R3, F, LOADER, STAGES, XBUF, IQT>;
+    using CF = FusedCfg<LOGN, E, R0, R1, R2, R3, F, LOADER, STAGES, XBUF, IQT, TWP>;
     Variant v;
     v.name = name;
     v.logn = LOGN;
@@ -69,8 +69,9 @@ static Variant make_variant(const char* name) {
     v.threads = CF::NT;
     v.minb = MINB;
     v.iqt = IQT;
+    v.twp = TWP;
     v.smem = CF::smem_bytes;
-    v.fn = (const void*)sti_fused_kernel<LOGN, E, R0, R1, R2, R3, F, LOADER, STAGES, XBUF, MINB, PFL2, IQT>;
+    v.fn = (const void*)sti_fused_kernel<LOGN, E, R0, R1, R2, R3, F, LOADER, STAGES, XBUF, MINB, PFL2, IQT, TWP>;
     return v;
 }
 
@@ -122,6 +123,21 @@ static const Variant g_variants[] = {
     make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 1, 2, 2>("ldg12_16x16x16_f1_x1_pf2"),
     make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 2, 2, 2>("ldg12_16x16x16_f1_x2_pf2"),
     make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 1, 2, 4>("ldg12_16x16x16_f1_x1_pf4"),
+    make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 1, 2, 0, IQ_C64, 1>("tma12_16x16x16_f1_s2x1_tp"),
+    make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 1, 2, 0, IQ_C64, 2>("tma12_16x16x16_f1_s2x1_tq"),
+    make_variant<11, 16, 8, 16, 16, 1, 1, M, 2, 1, 4, 0, IQ_C64, 2>("tma11_8x16x16_f1_s2x1_tq"),
+    make_variant<10, 16, 4, 16, 16, 1, 1, M, 2, 1, 8, 0, IQ_C64, 2>("tma10_4x16x16_f1_s2x1_tq"),
+    make_variant<13, 16, 16, 8, 8, 8, 1, M, 2, 1, 1, 0, IQ_C64, 2>("tma13_16x8x8x8_f1_s2x1_tq"),
+    make_variant<9, 8, 8, 8, 8, 1, 1, L, 1, 2, 16, 0, IQ_C64, 2>("ldg9_8x8x8_f1_tq"),
+    make_variant<11, 16, 8, 16, 16, 1, 1, M, 2, 1, 4, 0, IQ_C64, 1>("tma11_8x16x16_f1_s2x1_tp"),
+    make_variant<10, 16, 4, 16, 16, 1, 1, M, 2, 1, 8, 0, IQ_C64, 1>("tma10_4x16x16_f1_s2x1_tp"),
+    make_variant<13, 16, 16, 8, 8, 8, 1, M, 2, 1, 1, 0, IQ_C64, 1>("tma13_16x8x8x8_f1_s2x1_tp"),
+    make_variant<9, 8, 8, 8, 8, 1, 1, L, 1, 2, 16, 0, IQ_C64, 1>("ldg9_8x8x8_f1_tp"),
+    make_variant<10, 16, 4, 16, 16, 1, 1, L, 1, 2, 8, 0, IQ_C64, 1>("ldg10_4x16x16_f1_tp"),
+    make_variant<11, 16, 8, 16, 16, 1, 1, L, 1, 2, 4, 0, IQ_C64, 1>("ldg11_8x16x16_f1_tp"),
+    make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 2, 2, 0, IQ_C64, 1>("ldg12_16x16x16_f1_tp"),
+    make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 1, 2, 2, IQ_C64, 1>("ldg12_16x16x16_f1_x1_pf2_tp"),
+    make_variant<13, 16, 2, 16, 16, 16, 1, L, 1, 1, 1, 0, IQ_C64, 1>("ldg13_2x16x16x16_f1_tp"),
     make_variant<12, 8, 8, 8, 8, 8, 1, M, 2, 1, 2>("tma12_8x8x8x8_f1_s2x1"),
     make_variant<12, 8, 8, 8, 8, 8, 1, M, 3, 2, 2>("tma12_8x8x8x8_f1_s3x2"),
     make_variant<12, 16, 16, 4, 8, 8, 1, M, 2, 1, 2>("tma12_16x4x8x8_f1_s2x1"),
@@ -134,25 +150,25 @@ static const Variant g_variants[] = {
     make_variant<13, 16, 2, 16, 16, 16, 1, L, 1, 1, 1>("ldg13_2x16x16x16_f1"),
     // raw integer IQ ingest (complex int16 / int8): the default geometry of every size, both loaders
     make_variant<8, 16, 16, 16, 1, 1, 8, L, 1, 2, 4, 0, IQ_CI16>("ldg8_16x16_f8_i16"),
-    make_variant<9, 8, 8, 8, 8, 1, 1, L, 1, 2, 16, 0, IQ_CI16>("ldg9_8x8x8_f1_i16"),
-    make_variant<10, 16, 4, 16, 16, 1, 1, M, 2, 1, 8, 0, IQ_CI16>("tma10_4x16x16_f1_s2x1_i16"),
-    make_variant<10, 16, 4, 16, 16, 1, 1, L, 1, 2, 8, 0, IQ_CI16>("ldg10_4x16x16_f1_i16"),
-    make_variant<11, 16, 8, 16, 16, 1, 1, M, 2, 1, 4, 0, IQ_CI16>("tma11_8x16x16_f1_s2x1_i16"),
-    make_variant<11, 16, 8, 16, 16, 1, 1, L, 1, 2, 4, 0, IQ_CI16>("ldg11_8x16x16_f1_i16"),
-    make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 1, 2, 0, IQ_CI16>("tma12_16x16x16_f1_s2x1_i16"),
-    make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 2, 2, 0, IQ_CI16>("ldg12_16x16x16_f1_i16"),
-    make_variant<13, 16, 16, 8, 8, 8, 1, M, 2, 1, 1, 0, IQ_CI16>("tma13_16x8x8x8_f1_s2x1_i16"),
-    make_variant<13, 16, 2, 16, 16, 16, 1, L, 1, 1, 1, 0, IQ_CI16>("ldg13_2x16x16x16_f1_i16"),
+    make_variant<9, 8, 8, 8, 8, 1, 1, L, 1, 2, 16, 0, IQ_CI16, 1>("ldg9_8x8x8_f1_tp_i16"),
+    make_variant<10, 16, 4, 16, 16, 1, 1, M, 2, 1, 8, 0, IQ_CI16, 2>("tma10_4x16x16_f1_s2x1_tq_i16"),
+    make_variant<10, 16, 4, 16, 16, 1, 1, L, 1, 2, 8, 0, IQ_CI16, 1>("ldg10_4x16x16_f1_tp_i16"),
+    make_variant<11, 16, 8, 16, 16, 1, 1, M, 2, 1, 4, 0, IQ_CI16, 2>("tma11_8x16x16_f1_s2x1_tq_i16"),
+    make_variant<11, 16, 8, 16, 16, 1, 1, L, 1, 2, 4, 0, IQ_CI16, 1>("ldg11_8x16x16_f1_tp_i16"),
+    make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 1, 2, 0, IQ_CI16, 2>("tma12_16x16x16_f1_s2x1_tq_i16"),
+    make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 2, 2, 0, IQ_CI16, 1>("ldg12_16x16x16_f1_tp_i16"),
+    make_variant<13, 16, 16, 8, 8, 8, 1, M, 2, 1, 1, 0, IQ_CI16, 2>("tma13_16x8x8x8_f1_s2x1_tq_i16"),
+    make_variant<13, 16, 2, 16, 16, 16, 1, L, 1, 1, 1, 0, IQ_CI16, 1>("ldg13_2x16x16x16_f1_tp_i16"),
     make_variant<8, 16, 16, 16, 1, 1, 8, L, 1, 2, 4, 0, IQ_CI8>("ldg8_16x16_f8_i8"),
-    make_variant<9, 8, 8, 8, 8, 1, 1, L, 1, 2, 16, 0, IQ_CI8>("ldg9_8x8x8_f1_i8"),
-    make_variant<10, 16, 4, 16, 16, 1, 1, M, 2, 1, 8, 0, IQ_CI8>("tma10_4x16x16_f1_s2x1_i8"),
-    make_variant<10, 16, 4, 16, 16, 1, 1, L, 1, 2, 8, 0, IQ_CI8>("ldg10_4x16x16_f1_i8"),
-    make_variant<11, 16, 8, 16, 16, 1, 1, M, 2, 1, 4, 0, IQ_CI8>("tma11_8x16x16_f1_s2x1_i8"),
-    make_variant<11, 16, 8, 16, 16, 1, 1, L, 1, 2, 4, 0, IQ_CI8>("ldg11_8x16x16_f1_i8"),
-    make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 1, 2, 0, IQ_CI8>("tma12_16x16x16_f1_s2x1_i8"),
-    make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 2, 2, 0, IQ_CI8>("ldg12_16x16x16_f1_i8"),
-    make_variant<13, 16, 16, 8, 8, 8, 1, M, 2, 1, 1, 0, IQ_CI8>("tma13_16x8x8x8_f1_s2x1_i8"),
-    make_variant<13, 16, 2, 16, 16, 16, 1, L, 1, 1, 1, 0, IQ_CI8>("ldg13_2x16x16x16_f1_i8"),
+    make_variant<9, 8, 8, 8, 8, 1, 1, L, 1, 2, 16, 0, IQ_CI8, 1>("ldg9_8x8x8_f1_tp_i8"),
+    make_variant<10, 16, 4, 16, 16, 1, 1, M, 2, 1, 8, 0, IQ_CI8, 2>("tma10_4x16x16_f1_s2x1_tq_i8"),
+    make_variant<10, 16, 4, 16, 16, 1, 1, L, 1, 2, 8, 0, IQ_CI8, 1>("ldg10_4x16x16_f1_tp_i8"),
+    make_variant<11, 16, 8, 16, 16, 1, 1, M, 2, 1, 4, 0, IQ_CI8, 2>("tma11_8x16x16_f1_s2x1_tq_i8"),
+    make_variant<11, 16, 8, 16, 16, 1, 1, L, 1, 2, 4, 0, IQ_CI8, 1>("ldg11_8x16x16_f1_tp_i8"),
+    make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 1, 2, 0, IQ_CI8, 2>("tma12_16x16x16_f1_s2x1_tq_i8"),
+    make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 2, 2, 0, IQ_CI8, 1>("ldg12_16x16x16_f1_tp_i8"),
+    make_variant<13, 16, 16, 8, 8, 8, 1, M, 2, 1, 1, 0, IQ_CI8, 2>("tma13_16x8x8x8_f1_s2x1_tq_i8"),
+    make_variant<13, 16, 2, 16, 16, 16, 1, L, 1, 1, 1, 0, IQ_CI8, 1>("ldg13_2x16x16x16_f1_tp_i8"),
 };
 #undef L
 #undef M
@@ -166,18 +182,20 @@ static const Variant* variant_by_name(const char* name) {
 
 // Default variant per FFT length, from the measured sweeps (profiles/r01_sweep_*.txt, 4 GB of IQ,
 // full-coverage Mode A): small CTAs (one frame group) win from 512 up, the TMA ring with two
-// stages and one exchange buffer wins from 1024 up, the direct LDG loader below that.
-static const char* const g_default_tma[] = {"ldg8_16x16_f8", "ldg9_8x8x8_f1", "tma10_4x16x16_f1_s2x1",
-                                            "tma11_8x16x16_f1_s2x1", "tma12_16x16x16_f1_s2x1", "tma13_16x8x8x8_f1_s2x1"};
-static const char* const g_default_ldg[] = {"ldg8_16x16_f8", "ldg9_8x8x8_f1", "ldg10_4x16x16_f1",
-                                            "ldg11_8x16x16_f1", "ldg12_16x16x16_f1", "ldg13_2x16x16x16_f1"};
+// stages and one exchange buffer wins from 1024 up, the direct LDG loader below that; mid-pass
+// twiddles rebuilt from W^1 (_tq) / W^1,2,4,8 (_tp) instead of loaded win everywhere (the kernels are
+// LSU-bound, not HBM- or FMA-bound).
+static const char* const g_default_tma[] = {"ldg8_16x16_f8", "ldg9_8x8x8_f1_tp", "tma10_4x16x16_f1_s2x1_tq",
+                                            "tma11_8x16x16_f1_s2x1_tq", "tma12_16x16x16_f1_s2x1_tq", "tma13_16x8x8x8_f1_s2x1_tq"};
+static const char* const g_default_ldg[] = {"ldg8_16x16_f8", "ldg9_8x8x8_f1_tp", "ldg10_4x16x16_f1_tp",
+                                            "ldg11_8x16x16_f1_tp", "ldg12_16x16x16_f1_tp", "ldg13_2x16x16x16_f1_tp"};
 
 static const Variant* pick_variant(int logn, bool tma_ok, int iqt) {
     {
         std::lock_guard<std::mutex> lk(g_variant_mu);
         if (!g_variant_override.empty()) {
             const Variant* v = variant_by_name(g_variant_override.c_str());
-            if (v && v->logn == logn && v->iqt == iqt && (v->loader == PSG_LOADER_LDG || tma_ok)) return v;
+            if (v && v->logn == logn && v->iqt == iqt && (v->loader != PSG_LOADER_TMA || tma_ok)) return v;
         }
     }
     if (logn < 8 || logn > 13) return nullptr;
@@ -492,7 +510,7 @@ extern "C" int psg_plan_window(const psg_plan* p, float* host_out) {
 // per-pass twiddle tables for radices (r[0..np)) -- layouts documented in sti_kernels.cuh:
 // pass 0 and mid passes with stride > 32 use the column layout, mid passes with stride <= 32 the
 // row layout (R+2 complex per row, entry k of row n' = W^{n'*k}).
-static std::vector<float2> build_pass_tables(int n, const int* r, int np) {
+static std::vector<float2> build_pass_tables(int n, const int* r, int np, int twp) {
     std::vector<float2> t;
     int s = n;
     for (int p = 0; p + 1 < np; ++p) {
@@ -502,7 +520,18 @@ static std::vector<float2> build_pass_tables(int n, const int* r, int np) {
             const double ang = -2.0 * M_PI * (double)((long long)i * k % m) / (double)m;
             return make_float2((float)cos(ang), (float)sin(ang));
         };
-        if (p >= 1 && s <= 32) {
+        const bool row = p >= 1 && s <= 32;
+        if (p >= 1 && twp) {
+            // power layout: only W^1, W^2, W^4, W^8 (exponents below the radix) are stored
+            const int npw = psg_npow(r[p]);
+            if (row) {
+                for (int i = 0; i < s; ++i)
+                    for (int q = 0; q < 6; ++q) t.push_back(q < npw ? w(i, 1 << q) : make_float2(0.f, 0.f));
+            } else {
+                for (int q = 0; q < npw; ++q)
+                    for (int i = 0; i < s; ++i) t.push_back(w(i, 1 << q));
+            }
+        } else if (row) {
             for (int i = 0; i < s; ++i)
                 for (int k = 0; k < r[p] + 2; ++k) t.push_back(k < r[p] ? w(i, k) : make_float2(0.f, 0.f));
         } else {
@@ -608,7 +637,7 @@ static int launch_fused(psg_plan* p, const Variant* v, StiArgs a, int ncs, int f
 // upload (once per plan) the per-pass twiddle tables of a variant
 static int upload_pass_tables(const Variant* v, float2** d_out) {
     int r[4], np = variant_radices(v, r);
-    std::vector<float2> t = build_pass_tables(1 << v->logn, r, np);
+    std::vector<float2> t = build_pass_tables(1 << v->logn, r, np, v->twp);
     CUDA_TRY(cudaMalloc(d_out, sizeof(float2) * t.size()));
     CUDA_TRY(cudaMemcpy(*d_out, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice));
     return PSG_OK;

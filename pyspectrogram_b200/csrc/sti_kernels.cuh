@@ -144,7 +144,13 @@ PSG_DEV void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint
         : "memory");
 }
 
-template <int N, int R0, int R1, int R2, int R3>
+// number of power-of-two exponents below R: the mid-pass twiddles W^k, k = 1..R-1, of a TWP plan are
+// rebuilt in registers from W^1, W^2, W^4, W^8 (k = hb + k' -> W^hb * W^k', one complex multiply
+// each) instead of being loaded: the loads cost as many LSU wavefronts as a data exchange of the
+// pass, the multiplies run on the less loaded FMA pipe.
+__host__ __device__ constexpr int psg_npow(int r) { return r >= 16 ? 4 : r >= 8 ? 3 : r >= 4 ? 2 : r >= 2 ? 1 : 0; }
+
+template <int N, int R0, int R1, int R2, int R3, int TWP = 0>
 struct Plan {
     static constexpr int P = 1 + (R1 > 1) + (R2 > 1) + (R3 > 1);
     static constexpr int S0 = N / R0, S1 = S0 / R1, S2 = S1 / R2, S3 = S2 / R3;
@@ -154,9 +160,10 @@ struct Plan {
     static constexpr bool ROW1 = (P >= 3) && (S1 <= 32), ROW2 = (P >= 4) && (S2 <= 32);
     static constexpr int TW0 = 0;
     static constexpr int TW1 = TW0 + (R0 - 1) * S0;
-    static constexpr int TW1_LEN = (P >= 3) ? (ROW1 ? S1 * (R1 + 2) : (R1 - 1) * S1) : 0;
+    static constexpr int ROWL1 = TWP ? 6 : R1 + 2, ROWL2 = TWP ? 6 : R2 + 2;  // complex per table row
+    static constexpr int TW1_LEN = (P >= 3) ? (ROW1 ? S1 * ROWL1 : (TWP ? psg_npow(R1) : R1 - 1) * S1) : 0;
     static constexpr int TW2 = TW1 + TW1_LEN;
-    static constexpr int TW2_LEN = (P >= 4) ? (ROW2 ? S2 * (R2 + 2) : (R2 - 1) * S2) : 0;
+    static constexpr int TW2_LEN = (P >= 4) ? (ROW2 ? S2 * ROWL2 : (TWP ? psg_npow(R2) : R2 - 1) * S2) : 0;
     static constexpr int TW_TOTAL = TW2 + TW2_LEN;
     // frequency of (last-pass butterfly b, output j): digit-reverse b, add (N/RL)*j
     PSG_DEV static int low_freq(int b) {
@@ -176,13 +183,41 @@ __host__ __device__ constexpr int pad_off(int d) { return d + 2 * (d >> 4); }
 // twiddles of one mid pass for this thread's butterflies -> registers (issued before the barrier
 // that precedes the pass, so their latency overlaps the wait).  ROW: from the shared-memory row
 // table with LDS.128; else coalesced LDG.64 from the column table in global memory (L1 hits).
-template <int E, int T, int R, int S, bool ROW>
-PSG_DEV void load_pass_tw(const float2* __restrict__ tab, int t, cf* tw) {
+template <int E, int T, int R, int S, bool ROW, int TWP>
+PSG_DEV void load_pass_tw(const float2* __restrict__ tab, int t, cf* tw, const cf* wbase = nullptr) {
     constexpr int NB = E / R;
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
         const int npr = (t + i * T) & (S - 1);
-        if constexpr (ROW) {
+        if constexpr (TWP) {
+            constexpr int NPW = psg_npow(R);
+            cf pw[NPW];
+            if constexpr (TWP == 2) {
+                // W^1, W^2, W^4, W^8 of this butterfly are loop-invariant registers (correctly rounded
+                // table values: squaring W^1 in fp32 would cost ~15 ulp on W^8)
+#pragma unroll
+                for (int q = 0; q < NPW; ++q) pw[q] = wbase[i * NPW + q];
+            } else if constexpr (ROW) {
+                const float4* row = reinterpret_cast<const float4*>(tab + npr * 6);
+                const float4 v0 = row[0];
+                pw[0] = make_float2(v0.x, v0.y);
+                if constexpr (NPW >= 2) pw[1] = make_float2(v0.z, v0.w);
+                if constexpr (NPW >= 3) {
+                    const float4 v1 = row[1];
+                    pw[2] = make_float2(v1.x, v1.y);
+                    if constexpr (NPW >= 4) pw[3] = make_float2(v1.z, v1.w);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < NPW; ++q) pw[q] = __ldg(tab + q * S + npr);
+            }
+#pragma unroll
+            for (int k = 1; k < R; ++k) {
+                const int q = (k >= 8) ? 3 : (k >= 4) ? 2 : (k >= 2) ? 1 : 0;
+                const int hb = 1 << q;
+                tw[i * (R - 1) + k - 1] = (k == hb) ? pw[q] : cmul(tw[i * (R - 1) + (k - hb) - 1], pw[q]);
+            }
+        } else if constexpr (ROW) {
             const float4* row = reinterpret_cast<const float4*>(tab + npr * (R + 2));
             cf tmp[R];
 #pragma unroll
@@ -251,13 +286,14 @@ PSG_DEV void exchange_sync() {
     else __syncthreads();
 }
 
-template <int LOGN, int E, int R0, int R1, int R2, int R3, int F, int LOADER, int STAGES, int XBUF, int IQT = IQ_C64>
+template <int LOGN, int E, int R0, int R1, int R2, int R3, int F, int LOADER, int STAGES, int XBUF, int IQT = IQ_C64,
+          int TWP = 0>
 struct FusedCfg {
     static constexpr int N = 1 << LOGN, T = N / E, NT = F * T;
-    using PLN = Plan<N, R0, R1, R2, R3>;
+    using PLN = Plan<N, R0, R1, R2, R3, TWP>;
     static constexpr int NPAD = psg_pad(N) + 2;  // even: every group's buffer stays 16-byte aligned
     static constexpr int SLOT = N * IqBytes<IQT>::value + 16;  // bytes: one frame + 16 of alignment slack
-    static constexpr int TWSM = (PLN::ROW1 ? PLN::TW1_LEN : 0) + (PLN::ROW2 ? PLN::TW2_LEN : 0);  // complex
+    static constexpr int TWSM = (TWP == 2) ? 0 : (PLN::ROW1 ? PLN::TW1_LEN : 0) + (PLN::ROW2 ? PLN::TW2_LEN : 0);  // complex
     static constexpr size_t bar_bytes = 64 + (size_t)TWSM * 8;
     static constexpr size_t stage_bytes = (LOADER == PSG_LOADER_TMA) ? (size_t)STAGES * F * SLOT : 0;
     static constexpr size_t xch_bytes = (size_t)F * XBUF * NPAD * 8;
@@ -265,12 +301,12 @@ struct FusedCfg {
 };
 
 template <int LOGN, int E, int R0, int R1, int R2, int R3, int F, int LOADER, int STAGES, int XBUF, int MINB, int PFL2 = 0,
-          int IQT = IQ_C64>
+          int IQT = IQ_C64, int TWP = 0>
 __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(const StiArgs a) {
-    using CF = FusedCfg<LOGN, E, R0, R1, R2, R3, F, LOADER, STAGES, XBUF, IQT>;
+    using CF = FusedCfg<LOGN, E, R0, R1, R2, R3, F, LOADER, STAGES, XBUF, IQT, TWP>;
     constexpr int IQB = IqBytes<IQT>::value;
     constexpr int N = CF::N, T = CF::T, NT = CF::NT, NPAD = CF::NPAD, SLOT = CF::SLOT;
-    using PL = Plan<N, R0, R1, R2, R3>;
+    using PL = Plan<N, R0, R1, R2, R3, TWP>;
     constexpr int P = PL::P;
     constexpr int NB0 = E / R0;
     static_assert(P >= 2, "tuned kernels need at least two passes");
@@ -361,6 +397,25 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
 #pragma unroll
         for (int k = 1; k < R0; ++k) tw0[i * (R0 - 1) + k - 1] = __ldg(a.twp + PL::TW0 + (k - 1) * PL::S0 + b);
     }
+    // TWP == 2: the power-of-two twiddles of every mid-pass butterfly of this thread stay in registers
+    constexpr int NPW1 = psg_npow(R1), NPW2 = psg_npow(R2);
+    cf wb1[(TWP == 2 && P >= 3) ? (E / R1) * NPW1 : 1], wb2[(TWP == 2 && P >= 4) ? (E / R2) * NPW2 : 1];
+    if constexpr (TWP == 2 && P >= 3) {
+#pragma unroll
+        for (int i = 0; i < E / R1; ++i) {
+            const int npr = (t + i * T) & (PL::S1 - 1);
+#pragma unroll
+            for (int q = 0; q < NPW1; ++q) wb1[i * NPW1 + q] = __ldg(a.twp + PL::TW1 + (PL::ROW1 ? npr * 6 + q : q * PL::S1 + npr));
+        }
+    }
+    if constexpr (TWP == 2 && P >= 4) {
+#pragma unroll
+        for (int i = 0; i < E / R2; ++i) {
+            const int npr = (t + i * T) & (PL::S2 - 1);
+#pragma unroll
+            for (int q = 0; q < NPW2; ++q) wb2[i * NPW2 + q] = __ldg(a.twp + PL::TW2 + (PL::ROW2 ? npr * 6 + q : q * PL::S2 + npr));
+        }
+    }
     float acc[E];  // |X|^2 sums of this thread's E bins (scalar: registers are the scarce resource)
 #pragma unroll
     for (int i = 0; i < E; ++i) acc[i] = 0.f;
@@ -424,7 +479,7 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
         }
         {
             cf tw1[(P >= 3) ? (E / R1) * (R1 - 1) : 1];
-            if constexpr (P >= 3) load_pass_tw<E, T, R1, PL::S1, PL::ROW1>(PL::ROW1 ? twsm : a.twp + PL::TW1, t, tw1);
+            if constexpr (P >= 3) load_pass_tw<E, T, R1, PL::S1, PL::ROW1, TWP>(PL::ROW1 ? twsm : a.twp + PL::TW1, t, tw1, wb1);
             exchange_sync<L01>();
             if constexpr (LOADER == PSG_LOADER_TMA && STAGES == 1) {
                 static_assert(LOADER != PSG_LOADER_TMA || STAGES > 1 || !L01, "single stage needs a CTA barrier");
@@ -435,7 +490,7 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
         if constexpr (P >= 3) {
             cf tw2[(P >= 4) ? (E / R2) * (R2 - 1) : 1];
             if constexpr (P >= 4)
-                load_pass_tw<E, T, R2, PL::S2, PL::ROW2>(PL::ROW2 ? twsm + (PL::ROW1 ? PL::TW1_LEN : 0) : a.twp + PL::TW2, t, tw2);
+                load_pass_tw<E, T, R2, PL::S2, PL::ROW2, TWP>(PL::ROW2 ? twsm + (PL::ROW1 ? PL::TW1_LEN : 0) : a.twp + PL::TW2, t, tw2, wb2);
             exchange_sync<L12>();
             smem_pass<E, T, R2, PL::S2, P == 3>(buf, tw2, t, acc);
         }
