@@ -218,6 +218,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-raw", action="store_true", help="skip the extra raw-int16 ingest e2e measurement")
     ap.add_argument("--variant", default=None, help="force a kernel variant (tuning)")
+    ap.add_argument("--items-per-slot", type=int, default=0, help="column split target (tuning)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -237,6 +238,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     if args.variant:
         engine.set_variant(args.variant)
+    if args.items_per_slot:
+        from pyspectrogram_b200 import _lib
+        _lib.check(_lib.load().psg_set_items_per_slot(args.items_per_slot))
 
     nsamp = int(FS * args.seconds)
     nint = nsamp // NTIME // NFFT

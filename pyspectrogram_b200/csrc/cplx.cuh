@@ -121,6 +121,63 @@ PSG_DEV void dft16(cf* a) {
     }
 }
 
+// Windowed variants for the first pass: a[n] = x[n] * w[n] folded into the first radix-2 layer.
+// (x0 w0 + x2 w2, x0 w0 - x2 w2) = (fma(x2, w2, m), 2 m - (..)) with m = x0 w0: 3 instructions per
+// pair instead of 4 (two multiplies, add, subtract).
+PSG_DEV void wpair(cf x0, float w0, cf x2, float w2, cf& s, cf& d) {
+    const cf m = mul2(x0, make_float2(w0, w0));
+    s = fma2(x2, make_float2(w2, w2), m);
+    d = fma2(m, make_float2(2.0f, 2.0f), make_float2(-s.x, -s.y));
+}
+
+PSG_DEV void dft4w(cf& a0, cf& a1, cf& a2, cf& a3, float w0, float w1, float w2, float w3) {
+    cf t0, t1, t2, d;
+    wpair(a0, w0, a2, w2, t0, t1);
+    wpair(a1, w1, a3, w3, t2, d);
+    cf t3 = mul_nj(d);
+    a0 = cadd(t0, t2);
+    a2 = csub(t0, t2);
+    a1 = cadd(t1, t3);
+    a3 = csub(t1, t3);
+}
+
+PSG_DEV void dft16w(cf* a, const float* w) {
+    cf u[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        u[i][0] = a[i]; u[i][1] = a[i + 4]; u[i][2] = a[i + 8]; u[i][3] = a[i + 12];
+        dft4w(u[i][0], u[i][1], u[i][2], u[i][3], w[i], w[i + 4], w[i + 8], w[i + 12]);
+    }
+    u[1][1] = cmul(u[1][1], make_float2(PSG_C1_16, -PSG_S1_16));
+    u[1][2] = cmul(u[1][2], make_float2(PSG_SQRT1_2, -PSG_SQRT1_2));
+    u[1][3] = cmul(u[1][3], make_float2(PSG_S1_16, -PSG_C1_16));
+    u[2][1] = cmul(u[2][1], make_float2(PSG_SQRT1_2, -PSG_SQRT1_2));
+    u[2][2] = mul_nj(u[2][2]);
+    u[2][3] = cmul(u[2][3], make_float2(-PSG_SQRT1_2, -PSG_SQRT1_2));
+    u[3][1] = cmul(u[3][1], make_float2(PSG_S1_16, -PSG_C1_16));
+    u[3][2] = cmul(u[3][2], make_float2(-PSG_SQRT1_2, -PSG_SQRT1_2));
+    u[3][3] = cmul(u[3][3], make_float2(-PSG_C1_16, PSG_S1_16));
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        dft4(u[0][c], u[1][c], u[2][c], u[3][c]);
+        a[c] = u[0][c]; a[c + 4] = u[1][c]; a[c + 8] = u[2][c]; a[c + 12] = u[3][c];
+    }
+}
+
+// window multiply + R-point DFT; the fold is implemented for R = 4 and 16 (first passes of the
+// 1024- and 4096-point plans), other radices multiply first
+template <int R>
+PSG_DEV void dftRw(cf* a, const float* w) {
+    if constexpr (R == 16) dft16w(a, w);
+    else if constexpr (R == 4) dft4w(a[0], a[1], a[2], a[3], w[0], w[1], w[2], w[3]);
+    else {
+#pragma unroll
+        for (int n = 0; n < R; ++n) a[n] = mul2(a[n], make_float2(w[n], w[n]));
+        if constexpr (R == 2) dft2(a[0], a[1]);
+        else if constexpr (R == 8) dft8(a);
+    }
+}
+
 template <int R>
 PSG_DEV void dftR(cf* a) {
     if constexpr (R == 2) dft2(a[0], a[1]);

@@ -27,6 +27,7 @@ static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_force_generic{0};
 static std::mutex g_variant_mu;
 static std::string g_variant_override;  // "" = automatic
+static std::atomic<int> g_items_per_slot{24};  // work items per resident CTA slot the column split aims for
 // Scratch cap of the large-nfft split path.  Measured (profiles/r01_sweep_split_scratch*.txt): L2-sized
 // chunks (16..128 MiB) lose more to the three short dependent launches per chunk than they save in
 // HBM traffic; 1..4 GiB chunks run each phase at its own roofline.
@@ -318,6 +319,11 @@ extern "C" int psg_set_split_scratch(int64_t bytes) {
     g_split_scratch_bytes.store(bytes);
     return PSG_OK;
 }
+extern "C" int psg_set_items_per_slot(int n) {
+    if (n < 1 || n > 1024) return fail(PSG_ERR_ARG, "psg_set_items_per_slot: 1..1024");
+    g_items_per_slot.store(n);
+    return PSG_OK;
+}
 extern "C" int psg_variant_count(void) { return g_nvariants; }
 extern "C" const char* psg_variant_name(int i) { return (i >= 0 && i < g_nvariants) ? g_variants[i].name : ""; }
 extern "C" int psg_variant_logn(int i) { return (i >= 0 && i < g_nvariants) ? g_variants[i].logn : -1; }
@@ -599,7 +605,7 @@ static int launch_fused(psg_plan* p, const Variant* v, StiArgs a, int ncs, int f
     const int colblocks = (ncs + cpc - 1) / cpc;
     const int iters = (frames_per_col + gpc - 1) / gpc;  // per column if one CTA did it all
     const long long slots = (long long)p->sms * p->occ[vi];
-    const long long target = slots * 24;
+    const long long target = slots * g_items_per_slot.load();
     int nsplit = (int)std::min<long long>((target + colblocks - 1) / colblocks, 1 << 20);
     const int smin = (iters + 255) / 256, smax = std::max(1, iters / min_iters);
     nsplit = std::max(smin, std::min(nsplit, smax));

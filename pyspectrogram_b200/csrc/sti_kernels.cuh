@@ -464,13 +464,11 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
                 for (int i = 0; i < E; ++i) x[i] = make_float2(0.f, 0.f);
             }
         }
-#pragma unroll
-        for (int i = 0; i < E; ++i) x[i] = cscale(x[i], w[i]);
         // previous frame's last pass must be done reading before this buffer is overwritten
         if constexpr (XBUF == 1) exchange_sync<ALL_LOCAL>();
 #pragma unroll
         for (int i = 0; i < NB0; ++i) {
-            dftR<R0>(&x[i * R0]);
+            dftRw<R0>(&x[i * R0], &w[i * R0]);  // window multiply folded into the first butterfly layer
             float2* p0 = buf + psg_pad(t + i * T);
 #pragma unroll
             for (int kk = 1; kk < R0; ++kk) x[i * R0 + kk] = cmul(x[i * R0 + kk], tw0[i * (R0 - 1) + kk - 1]);
