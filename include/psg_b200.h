@@ -93,7 +93,7 @@ int psg_plan_window(const psg_plan* plan, float* host_out);
  *                   allocation).  Other layouts take the strided LDG loader.
  *   col_offset_dev  int64[ncol] element offsets of every column's first sample (frame index
  *                   table of DrfInput.read_sti, drfProc.py:158-159, times sample_stride)
- *   out_lin_dev / out_db_dev   fp32 [nsub][ncol][nfft], either may be NULL (not both)
+ *   out_lin_dev / out_db_dev   fp32 [nsub][ncol][nfft], 16-byte aligned, either may be NULL (not both)
  *   eps             added before the log (drfProc.py:308: 1e-15)
  */
 int psg_sti_run(psg_plan* plan, const void* iq_dev,

@@ -862,6 +862,8 @@ extern "C" int psg_sti_run_typed(psg_plan* p, const void* iq_dev, int iq_type, i
     if ((reinterpret_cast<uintptr_t>(iq_dev) & (uintptr_t)(iqb - 1)) != 0)
         return fail(PSG_ERR_ARG, "psg_sti_run: iq_dev must be %d-byte aligned", iqb);
     if ((long long)ncol * nsub > (1ll << 30)) return fail(PSG_ERR_ARG, "psg_sti_run: too many columns");
+    if (((reinterpret_cast<uintptr_t>(out_lin_dev) | reinterpret_cast<uintptr_t>(out_db_dev)) & 15) != 0 && p->nfft % 4 == 0)
+        return fail(PSG_ERR_ARG, "psg_sti_run: output images must be 16-byte aligned");
     CUDA_TRY(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const int N = p->nfft;

@@ -111,7 +111,10 @@ PSG_DEV float2 lds_iq(const unsigned char* stage, int idx) {
     else return decode_ci8(reinterpret_cast<const unsigned short*>(stage)[idx]);
 }
 
-PSG_DEV float power_to_db(float p, float eps) { return 10.0f * log10f(p + eps); }
+// 10*log10(p + eps) (drfProc.py:308-310) as 10*log10(2) * lg2.approx(p + eps): one MUFU instead of the
+// ~20-instruction log10f.  lg2.approx is within 2 ulp (2^-22 absolute near 1), i.e. <= 3e-5 dB over the
+// range this path produces (>= -150 dB), against the 1e-3 dB parity bar; p + eps >= 1e-15 is never denormal.
+PSG_DEV float power_to_db(float p, float eps) { return 3.0102999566398120f * __log2f(p + eps); }
 
 __host__ __device__ constexpr int psg_pad(int pos) { return pos + 2 * (pos >> 4); }
 
@@ -498,11 +501,14 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
         }
     }
 
-    // ---- epilogue: digit-reversed register sums -> fftshifted, coalesced stores ----
+    // ---- epilogue: digit-reversed register sums -> fftshifted, coalesced 128-bit stores ----
+    // (one frame per column in Mode R makes this as hot as the transform: keep it lean)
     __syncthreads();
     float* sout = reinterpret_cast<float*>(xch);  // [F][N] floats (fits: F*NPAD*8 bytes available)
     constexpr int RL = PL::RL;
     constexpr int NBL = E / RL;
+    // bins are swizzled in groups of four (bits 2..4 ^= bits 5..7) so that the scattered 32-bit stores
+    // spread over the banks while every aligned group of four bins stays one 128-bit word
 #pragma unroll
     for (int i = 0; i < NBL; ++i) {
         const int b = t + i * T;
@@ -511,25 +517,32 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
         for (int jj = 0; jj < RL; ++jj) {
             const int freq = klow + (N / RL) * jj;
             const int idx = (freq + N / 2) & (N - 1);
-            sout[g * N + (idx ^ ((idx >> 5) & 31))] = acc[i * RL + jj];
+            sout[g * N + (idx ^ (((idx >> 5) & 7) << 2))] = acc[i * RL + jj];
         }
     }
     __syncthreads();
-    // all NT threads cooperate: column slot s, bin idx; lanes summed in fixed order
-    for (int e = tid; e < cpc * N; e += NT) {
-        const int s = e / N, idx = e - s * N;
+    // all NT threads cooperate: column slot s, four bins at idx; lanes summed in fixed order
+    constexpr int NQ = N / 4;
+    const float4* sout4 = reinterpret_cast<const float4*>(sout);
+    for (int e = tid; e < cpc * NQ; e += NT) {
+        const int s = e / NQ, q = e - s * NQ;
         const int c = cs0 + s;
         if (c >= ncs) break;
-        const int sw = idx ^ ((idx >> 5) & 31);
-        float v = 0.f;
-        for (int l = 0; l < gpc; ++l) v += sout[(s * gpc + l) * N + sw];
+        const int sw = q ^ ((q >> 3) & 7);  // the swizzle above, in units of four bins
+        float4 v = sout4[(s * gpc) * NQ + sw];
+        for (int l = 1; l < gpc; ++l) {
+            const float4 u = sout4[(s * gpc + l) * NQ + sw];
+            v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+        }
         if (a.nsplit > 1) {
-            a.partial[((size_t)c * a.nsplit + split) * N + idx] = v;
+            reinterpret_cast<float4*>(a.partial + ((size_t)c * a.nsplit + split) * N)[q] = v;
         } else {
-            const float p = v * a.scale;
-            const size_t o = (size_t)c * N + idx;
-            if (a.out_lin) a.out_lin[o] = p;
-            if (a.out_db) a.out_db[o] = power_to_db(p, a.eps);
+            v.x *= a.scale; v.y *= a.scale; v.z *= a.scale; v.w *= a.scale;
+            const size_t o = (size_t)c * NQ + q;
+            if (a.out_lin) reinterpret_cast<float4*>(a.out_lin)[o] = v;
+            if (a.out_db)
+                reinterpret_cast<float4*>(a.out_db)[o] = make_float4(power_to_db(v.x, a.eps), power_to_db(v.y, a.eps),
+                                                                     power_to_db(v.z, a.eps), power_to_db(v.w, a.eps));
         }
     }
 }
