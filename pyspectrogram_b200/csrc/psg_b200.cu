@@ -81,6 +81,13 @@ static Variant make_variant(const char* name) {
 // name = <loader><logn>_<radices>_f<F>_s<stages>x<xbuf>; first match per (logn, loader) is default
 static const Variant g_variants[] = {
     //            LOGN E  R0  R1  R2 R3  F  LD ST XB MINB
+    make_variant<5, 8, 4, 8, 1, 1, 32, L, 1, 2, 8>("ldg5_4x8_f32"),
+    make_variant<5, 8, 4, 8, 1, 1, 64, L, 1, 2, 4>("ldg5_4x8_f64"),
+    make_variant<6, 8, 8, 8, 1, 1, 32, L, 1, 2, 4>("ldg6_8x8_f32"),
+    make_variant<6, 8, 8, 8, 1, 1, 16, L, 1, 2, 8>("ldg6_8x8_f16"),
+    make_variant<7, 8, 2, 8, 8, 1, 16, L, 1, 2, 4>("ldg7_2x8x8_f16"),
+    make_variant<7, 16, 8, 16, 1, 1, 16, L, 1, 2, 4>("ldg7_8x16_f16"),
+    make_variant<7, 16, 8, 16, 1, 1, 32, L, 1, 2, 2>("ldg7_8x16_f32"),
     make_variant<8, 16, 16, 16, 1, 1, 16, M, 3, 2, 2>("tma8_16x16_f16_s3x2"),
     make_variant<8, 16, 16, 16, 1, 1, 16, L, 1, 2, 2>("ldg8_16x16_f16"),
     make_variant<8, 16, 16, 16, 1, 1, 8, L, 1, 2, 4>("ldg8_16x16_f8"),
@@ -150,6 +157,9 @@ static const Variant g_variants[] = {
     make_variant<13, 16, 8, 8, 8, 16, 1, M, 2, 1, 1>("tma13_8x8x8x16_f1_s2x1"),
     make_variant<13, 16, 2, 16, 16, 16, 1, L, 1, 1, 1>("ldg13_2x16x16x16_f1"),
     // raw integer IQ ingest (complex int16 / int8): the default geometry of every size, both loaders
+    make_variant<5, 8, 4, 8, 1, 1, 32, L, 1, 2, 8, 0, IQ_CI16>("ldg5_4x8_f32_i16"),
+    make_variant<6, 8, 8, 8, 1, 1, 32, L, 1, 2, 4, 0, IQ_CI16>("ldg6_8x8_f32_i16"),
+    make_variant<7, 16, 8, 16, 1, 1, 16, L, 1, 2, 4, 0, IQ_CI16>("ldg7_8x16_f16_i16"),
     make_variant<8, 16, 16, 16, 1, 1, 8, L, 1, 2, 4, 0, IQ_CI16>("ldg8_16x16_f8_i16"),
     make_variant<9, 8, 8, 8, 8, 1, 1, L, 1, 2, 16, 0, IQ_CI16, 1>("ldg9_8x8x8_f1_tp_i16"),
     make_variant<10, 16, 4, 16, 16, 1, 1, M, 2, 1, 8, 0, IQ_CI16, 2>("tma10_4x16x16_f1_s2x1_tq_i16"),
@@ -160,6 +170,9 @@ static const Variant g_variants[] = {
     make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 2, 2, 0, IQ_CI16, 1>("ldg12_16x16x16_f1_tp_i16"),
     make_variant<13, 16, 16, 8, 8, 8, 1, M, 2, 1, 1, 0, IQ_CI16, 2>("tma13_16x8x8x8_f1_s2x1_tq_i16"),
     make_variant<13, 16, 2, 16, 16, 16, 1, L, 1, 1, 1, 0, IQ_CI16, 1>("ldg13_2x16x16x16_f1_tp_i16"),
+    make_variant<5, 8, 4, 8, 1, 1, 32, L, 1, 2, 8, 0, IQ_CI8>("ldg5_4x8_f32_i8"),
+    make_variant<6, 8, 8, 8, 1, 1, 32, L, 1, 2, 4, 0, IQ_CI8>("ldg6_8x8_f32_i8"),
+    make_variant<7, 16, 8, 16, 1, 1, 16, L, 1, 2, 4, 0, IQ_CI8>("ldg7_8x16_f16_i8"),
     make_variant<8, 16, 16, 16, 1, 1, 8, L, 1, 2, 4, 0, IQ_CI8>("ldg8_16x16_f8_i8"),
     make_variant<9, 8, 8, 8, 8, 1, 1, L, 1, 2, 16, 0, IQ_CI8, 1>("ldg9_8x8x8_f1_tp_i8"),
     make_variant<10, 16, 4, 16, 16, 1, 1, M, 2, 1, 8, 0, IQ_CI8, 2>("tma10_4x16x16_f1_s2x1_tq_i8"),
@@ -186,9 +199,9 @@ static const Variant* variant_by_name(const char* name) {
 // stages and one exchange buffer wins from 1024 up, the direct LDG loader below that; mid-pass
 // twiddles rebuilt from W^1 (_tq) / W^1,2,4,8 (_tp) instead of loaded win everywhere (the kernels are
 // LSU-bound, not HBM- or FMA-bound).
-static const char* const g_default_tma[] = {"ldg8_16x16_f8", "ldg9_8x8x8_f1_tp", "tma10_4x16x16_f1_s2x1_tq",
+static const char* const g_default_tma[] = {"ldg5_4x8_f32", "ldg6_8x8_f32", "ldg7_8x16_f16", "ldg8_16x16_f8", "ldg9_8x8x8_f1_tp", "tma10_4x16x16_f1_s2x1_tq",
                                             "tma11_8x16x16_f1_s2x1_tq", "tma12_16x16x16_f1_s2x1_tq", "tma13_16x8x8x8_f1_s2x1_tq"};
-static const char* const g_default_ldg[] = {"ldg8_16x16_f8", "ldg9_8x8x8_f1_tp", "ldg10_4x16x16_f1_tp",
+static const char* const g_default_ldg[] = {"ldg5_4x8_f32", "ldg6_8x8_f32", "ldg7_8x16_f16", "ldg8_16x16_f8", "ldg9_8x8x8_f1_tp", "ldg10_4x16x16_f1_tp",
                                             "ldg11_8x16x16_f1_tp", "ldg12_16x16x16_f1_tp", "ldg13_2x16x16x16_f1_tp"};
 
 static const Variant* pick_variant(int logn, bool tma_ok, int iqt) {
@@ -199,8 +212,8 @@ static const Variant* pick_variant(int logn, bool tma_ok, int iqt) {
             if (v && v->logn == logn && v->iqt == iqt && (v->loader != PSG_LOADER_TMA || tma_ok)) return v;
         }
     }
-    if (logn < 8 || logn > 13) return nullptr;
-    std::string name = (tma_ok ? g_default_tma : g_default_ldg)[logn - 8];
+    if (logn < 5 || logn > 13) return nullptr;
+    std::string name = (tma_ok ? g_default_tma : g_default_ldg)[logn - 5];
     if (iqt == IQ_CI16) name += "_i16";
     if (iqt == IQ_CI8) name += "_i8";
     return variant_by_name(name.c_str());
@@ -654,7 +667,7 @@ static int upload_pass_tables(const Variant* v, float2** d_out) {
 static int run_split(psg_plan* p, StiArgs a, int ncs, int frames_per_col, cudaStream_t st) {
     constexpr int N2 = 4096;
     const int N = p->nfft, r0 = N / N2;
-    const Variant* v = variant_by_name(g_default_tma[12 - 8]);
+    const Variant* v = variant_by_name(g_default_tma[12 - 5]);
     if (!v) return fail(PSG_ERR_UNSUPPORTED, "no 4096-point variant for the split path");
     if (!p->d_twa) {
         std::vector<float2> t((size_t)(r0 - 1) * N2);
