@@ -90,7 +90,8 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows),
+                "note": "sampled over the timed steps and an untimed continuation of the same steps (~1 s)"}
 
 
 def synth_iq_device(torch, n, seed, device, chunk=1 << 26):
@@ -285,9 +286,19 @@ def main():
             step(kev[i])
         t_end.record()
         torch.cuda.synchronize()
+        launches_timed = engine.launch_count() - launches0
+        # the timed region of a few steps is shorter than one nvidia-smi query: keep the same load
+        # running (untimed) until the sampler has seen it for about a second
+        t_load = time.perf_counter()
+        extra_steps = 0
+        while len(clk.rows) < 6 and time.perf_counter() - t_load < 1.5:
+            for _ in range(8):
+                step()
+            extra_steps += 8
+            torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    launches = engine.launch_count() - launches0
+    launches = launches_timed
     total_ms = t_beg.elapsed_time(t_end)
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     if world > 1:

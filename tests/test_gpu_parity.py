@@ -538,6 +538,32 @@ def test_seven_worker_threads_share_the_library(dp):
         assert np.array_equal(f0, f1) and np.array_equal(s0, s1) and np.array_equal(m0, m1)
 
 
+def test_gui_maximum_counts(torch):
+    """The viewer's spin boxes go up to nint = 100000 and ntime = 100000 (drfview.py:488-503): a
+    column of 100000 frames (split over CTAs, fp64 finalize) and an image of 100000 columns."""
+    from pyspectrogram_b200 import engine
+    rng = np.random.default_rng(8)
+    nfft = 32
+    plan = engine.StiPlan(nfft)
+    # nint = 100000, three columns
+    nfr, ncol = 100000, 3
+    x = _recording(rng, nfft * nfr * ncol + 5)
+    starts = (np.arange(ncol) * nfft * nfr + np.array([0, 1, 3])).astype(np.int64)
+    lin, _ = plan.run(torch.from_numpy(x).cuda(), torch.from_numpy(starts).cuda(), nfr, nfft)
+    ref = _oracle_columns(x, starts, nfft, nfr, nfft)
+    assert_psd_close(lin.cpu().numpy()[0].T, ref.T, noise_like=False, what="nint=100000")
+    # ntime = 100000 columns of one frame (Mode R), overlapping starts one sample apart
+    ncol = 100000
+    x = _recording(rng, ncol + nfft)
+    starts = np.arange(ncol, dtype=np.int64)
+    lin, db = plan.run(torch.from_numpy(x).cuda(), torch.from_numpy(starts).cuda(), 1, nfft, want_lin=True, want_db=True)
+    pick = np.array([0, 1, 2, 4999, 50000, 99998, 99999])
+    ref = _oracle_columns(x, starts[pick], nfft, 1, nfft)
+    assert_psd_close(lin.cpu().numpy()[0][pick].T, ref.T, noise_like=False, what="ntime=100000")
+    med, _ = plan.median(lin)
+    assert np.array_equal(med.cpu().numpy(), np.median(lin.cpu().numpy(), axis=1))
+
+
 def test_large_workload_properties(torch):
     """Size-independent properties at a bench-like size (1 GiB of IQ, nfft=4096, nint=128):
     Parseval (sum of the PSD column == mean windowed frame energy * N / sum(w)^2), a unit tone
