@@ -124,3 +124,17 @@ def test_host_side_input_checks_need_no_device():
     assert dp.get_ref(dict(H5Tget_class=0, H5Tget_precision=16, H5Tget_size=2)) == 2 ** 15.5
     f = dp._freq_axis(8, 8.0)
     assert np.array_equal(f, np.array([-4., -3., -2., -1., 0., 1., 2., 3.]))
+
+
+@pytest.mark.skipif(_have_gpu(), reason="checks the no-device behaviour")
+def test_plain_c_caller_builds_and_fails_loudly_without_a_device(tmp_path):
+    """gcc + include/psg_b200.h + libpsgb200.so is all a C host needs; without a GPU the program
+    gets PSG_ERR_NODEVICE from psg_plan_create (exit code 3), not a silent CPU result."""
+    import subprocess
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.join(ROOT, "pyspectrogram_b200")
+    subprocess.run(["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-o", exe, "-L", libdir, "-lpsgb200", "-lm",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert res.returncode == 3 and "psg_plan_create: -4" in res.stdout

@@ -564,6 +564,21 @@ def test_gui_maximum_counts(torch):
     assert np.array_equal(med.cpu().numpy(), np.median(lin.cpu().numpy(), axis=1))
 
 
+def test_c_abi_from_plain_c(tmp_path):
+    """The boundary is a C ABI: a program compiled by gcc from include/psg_b200.h alone (no CUDA
+    headers, no torch, no Python) drives the path through psg_sti_host and checks it against a
+    naive float64 DFT."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.join(root, "pyspectrogram_b200")
+    subprocess.run(["gcc", "-O2", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "c", "abi_smoke.c"),
+                    "-o", exe, "-L", libdir, "-lpsgb200", "-lm", f"-Wl,-rpath,{libdir}"], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "c-abi smoke" in res.stdout and "ldg6_8x8" in res.stdout
+
+
 def test_large_workload_properties(torch):
     """Size-independent properties at a bench-like size (1 GiB of IQ, nfft=4096, nint=128):
     Parseval (sum of the PSD column == mean windowed frame energy * N / sum(w)^2), a unit tone
