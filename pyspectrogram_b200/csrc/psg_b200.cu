@@ -133,6 +133,28 @@ static const Variant g_variants[] = {
     make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 1, 2, 4>("ldg12_16x16x16_f1_x1_pf4"),
     make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 1, 2, 0, IQ_C64, 1>("tma12_16x16x16_f1_s2x1_tp"),
     make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 1, 2, 0, IQ_C64, 2>("tma12_16x16x16_f1_s2x1_tq"),
+    make_variant<12, 16, 16, 16, 16, 1, 1, M, 1, 2, 2, 0, IQ_C64, 2>("tma12_16x16x16_f1_s1x2_tq"),
+    make_variant<11, 16, 16, 16, 8, 1, 1, M, 2, 1, 4, 0, IQ_C64, 2>("tma11_16x16x8_f1_s2x1_tq"),
+    make_variant<11, 16, 8, 16, 16, 1, 1, M, 1, 2, 4, 0, IQ_C64, 2>("tma11_8x16x16_f1_s1x2_tq"),
+    make_variant<10, 16, 16, 16, 4, 1, 1, M, 2, 1, 8, 0, IQ_C64, 2>("tma10_16x16x4_f1_s2x1_tq"),
+    make_variant<10, 16, 8, 8, 16, 1, 1, M, 2, 1, 8, 0, IQ_C64, 2>("tma10_8x8x16_f1_s2x1_tq"),
+    make_variant<10, 16, 4, 16, 16, 1, 1, M, 1, 2, 8, 0, IQ_C64, 2>("tma10_4x16x16_f1_s1x2_tq"),
+    make_variant<9, 8, 8, 8, 8, 1, 1, M, 2, 1, 16, 0, IQ_C64, 1>("tma9_8x8x8_f1_s2x1_tp"),
+    make_variant<9, 16, 2, 16, 16, 1, 1, M, 2, 1, 16, 0, IQ_C64, 2>("tma9_2x16x16_f1_s2x1_tq"),
+    make_variant<8, 16, 16, 16, 1, 1, 1, M, 2, 1, 16>("tma8_16x16_f1_s2x1"),
+    make_variant<8, 16, 16, 16, 1, 1, 2, M, 2, 1, 16>("tma8_16x16_f2_s2x1"),
+    make_variant<8, 16, 16, 16, 1, 1, 4, M, 2, 1, 8>("tma8_16x16_f4_s2x1"),
+    make_variant<9, 16, 2, 16, 16, 1, 2, M, 2, 1, 8, 0, IQ_C64, 2>("tma9_2x16x16_f2_s2x1_tq"),
+    make_variant<9, 16, 2, 16, 16, 1, 1, M, 1, 2, 16, 0, IQ_C64, 2>("tma9_2x16x16_f1_s1x2_tq"),
+    make_variant<7, 16, 8, 16, 1, 1, 2, M, 2, 1, 16>("tma7_8x16_f2_s2x1"),
+    make_variant<7, 16, 8, 16, 1, 1, 4, M, 2, 1, 16>("tma7_8x16_f4_s2x1"),
+    make_variant<7, 16, 8, 16, 1, 1, 8, M, 2, 1, 8>("tma7_8x16_f8_s2x1"),
+    make_variant<6, 8, 8, 8, 1, 1, 4, M, 2, 1, 16>("tma6_8x8_f4_s2x1"),
+    make_variant<6, 8, 8, 8, 1, 1, 8, M, 2, 1, 16>("tma6_8x8_f8_s2x1"),
+    make_variant<6, 8, 8, 8, 1, 1, 16, M, 2, 1, 8>("tma6_8x8_f16_s2x1"),
+    make_variant<5, 8, 4, 8, 1, 1, 8, M, 2, 1, 16>("tma5_4x8_f8_s2x1"),
+    make_variant<5, 8, 4, 8, 1, 1, 16, M, 2, 1, 16>("tma5_4x8_f16_s2x1"),
+    make_variant<5, 8, 4, 8, 1, 1, 32, M, 2, 1, 8>("tma5_4x8_f32_s2x1"),
     make_variant<11, 16, 8, 16, 16, 1, 1, M, 2, 1, 4, 0, IQ_C64, 2>("tma11_8x16x16_f1_s2x1_tq"),
     make_variant<10, 16, 4, 16, 16, 1, 1, M, 2, 1, 8, 0, IQ_C64, 2>("tma10_4x16x16_f1_s2x1_tq"),
     make_variant<13, 16, 16, 8, 8, 8, 1, M, 2, 1, 1, 0, IQ_C64, 2>("tma13_16x8x8x8_f1_s2x1_tq"),
@@ -194,15 +216,21 @@ static const Variant* variant_by_name(const char* name) {
     return nullptr;
 }
 
-// Default variant per FFT length, from the measured sweeps (profiles/r01_sweep_*.txt, 4 GB of IQ,
-// full-coverage Mode A): small CTAs (one frame group) win from 512 up, the TMA ring with two
-// stages and one exchange buffer wins from 1024 up, the direct LDG loader below that; mid-pass
-// twiddles rebuilt from W^1 (_tq) / W^1,2,4,8 (_tp) instead of loaded win everywhere (the kernels are
-// LSU-bound, not HBM- or FMA-bound).
-static const char* const g_default_tma[] = {"ldg5_4x8_f32", "ldg6_8x8_f32", "ldg7_8x16_f16", "ldg8_16x16_f8", "ldg9_8x8x8_f1_tp", "tma10_4x16x16_f1_s2x1_tq",
-                                            "tma11_8x16x16_f1_s2x1_tq", "tma12_16x16x16_f1_s2x1_tq", "tma13_16x8x8x8_f1_s2x1_tq"};
-static const char* const g_default_ldg[] = {"ldg5_4x8_f32", "ldg6_8x8_f32", "ldg7_8x16_f16", "ldg8_16x16_f8", "ldg9_8x8x8_f1_tp", "ldg10_4x16x16_f1_tp",
-                                            "ldg11_8x16x16_f1_tp", "ldg12_16x16x16_f1_tp", "ldg13_2x16x16x16_f1_tp"};
+// Default variant per FFT length, from the measured sweeps (profiles/r01_sweep_*.txt, 4 and 12 GB of
+// IQ, full-coverage Mode A): the TMA ring wins at every size once the CTAs are small (one frame group
+// from 512 up, 4..32 frames per CTA below); mid-pass twiddles rebuilt from register-resident
+// W^1,2,4,8 (_tq) or one row load (_tp) instead of 15 loads win everywhere (the kernels are LSU-bound,
+// not HBM- or FMA-bound).
+static const char* const g_default_tma[] = {"tma5_4x8_f32_s2x1", "tma6_8x8_f16_s2x1", "tma7_8x16_f8_s2x1", "tma8_16x16_f4_s2x1",
+                                            "tma9_2x16x16_f1_s1x2_tq", "tma10_4x16x16_f1_s1x2_tq", "tma11_8x16x16_f1_s1x2_tq",
+                                            "tma12_16x16x16_f1_s2x1_tq", "tma13_16x8x8x8_f1_s2x1_tq"};
+static const char* const g_default_ldg[] = {"ldg5_4x8_f32", "ldg6_8x8_f32", "ldg7_8x16_f16", "ldg8_16x16_f8", "ldg9_8x8x8_f1_tp",
+                                            "ldg10_4x16x16_f1_tp", "ldg11_8x16x16_f1_tp", "ldg12_16x16x16_f1_tp",
+                                            "ldg13_2x16x16x16_f1_tp"};
+// raw integer IQ (suffix _i16 / _i8 appended): the instantiated subset
+static const char* const g_default_tma_int[] = {"ldg5_4x8_f32", "ldg6_8x8_f32", "ldg7_8x16_f16", "ldg8_16x16_f8", "ldg9_8x8x8_f1_tp",
+                                                "tma10_4x16x16_f1_s2x1_tq", "tma11_8x16x16_f1_s2x1_tq",
+                                                "tma12_16x16x16_f1_s2x1_tq", "tma13_16x8x8x8_f1_s2x1_tq"};
 
 static const Variant* pick_variant(int logn, bool tma_ok, int iqt) {
     {
@@ -213,7 +241,7 @@ static const Variant* pick_variant(int logn, bool tma_ok, int iqt) {
         }
     }
     if (logn < 5 || logn > 13) return nullptr;
-    std::string name = (tma_ok ? g_default_tma : g_default_ldg)[logn - 5];
+    std::string name = (tma_ok ? (iqt == IQ_C64 ? g_default_tma : g_default_tma_int) : g_default_ldg)[logn - 5];
     if (iqt == IQ_CI16) name += "_i16";
     if (iqt == IQ_CI8) name += "_i8";
     return variant_by_name(name.c_str());

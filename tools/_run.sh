@@ -1,2 +1,5 @@
 mkdir -p gpurun_out
-for mb in 128 256 512 1024 2048; do echo "slot $mb MB"; timeout 300 python tools/kernel_sweep.py --gb 4 --reps 5 --big --slot-mb $mb 2>&1 | grep nfft; done | tee gpurun_out/sweep_pipe2.log
+(timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -5)
+timeout 600 python tools/default_sweep.py --gb 12 2>&1 | tee gpurun_out/default_sweep_12gb.log
+timeout 600 python tools/default_sweep.py --gb 4 2>&1 | tee gpurun_out/default_sweep_4gb.log
+timeout 300 python tools/mode_r_probe.py 2>&1 | tee gpurun_out/mode_r_probe2.log
