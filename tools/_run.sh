@@ -1,5 +1,4 @@
 mkdir -p gpurun_out
-(timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -5)
-timeout 600 python tools/default_sweep.py --gb 12 2>&1 | tee gpurun_out/default_sweep_12gb.log
-timeout 600 python tools/default_sweep.py --gb 4 2>&1 | tee gpurun_out/default_sweep_4gb.log
-timeout 300 python tools/mode_r_probe.py 2>&1 | tee gpurun_out/mode_r_probe2.log
+timeout 600 python bench.py > gpurun_out/bench8.json 2> gpurun_out/bench8.err; echo rc=$?; python -c "
+import json; d=json.load(open('gpurun_out/bench8.json')); print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['e2e_raw_int16']['value'], d['cpu_baseline']['value'], d['clocks'])"; tail -3 gpurun_out/bench8.err
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()"
