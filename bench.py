@@ -8,7 +8,7 @@ A step = one pass of the hot path over one batch of synthetic IQ: per GPU, BASEL
 (1 channel, 25 MS/s, 60 s = 1.5e9 complex64 samples, nfft=4096, 1000 STI bins, every sample
 read once: nint=366, Mode A) -> dB image + time-median.  N > 1 is weak scaling: one such channel
 per GPU (the channel sharding of SURVEY.md section 8(e)), each rank computes its own columns and one
-NCCL gather assembles the image on rank 0 inside the timed region.
+NCCL gather assembles the dB image (and the per-channel median rows) on rank 0 inside the timed region.
 
 Prints ONE JSON line (rank 0).  ``value`` = Msamples/s with inputs resident in HBM; ``e2e`` = the same
 metric through the host-buffer C-ABI call (pinned host IQ -> H2D -> kernels -> D2H of the image);
@@ -262,14 +262,13 @@ def main():
         plan.run(iq, starts, nint, NFFT, want_lin=True, want_db=True, out_lin=out_lin, out_db=out_db)
         if evs:
             evs[1].record()
+        # the time-median is per channel: with one channel per rank it needs no other rank's columns
+        _, med_db = plan.median(out_lin, want_lin=False, want_db=True)
         if world > 1:
-            # one gather of the [ncol_local][nfft] slabs assembles the N-channel image on rank 0
+            # one gather of the [ncol_local][nfft] dB slabs assembles the N-channel image on rank 0
+            # (plus the N median rows)
             gathered = pdist.gather_columns(out_db[0], [NTIME] * world, dst=0)
-            glin = pdist.gather_columns(out_lin[0], [NTIME] * world, dst=0)
-            if rank == 0:
-                plan.median(glin.reshape(world, NTIME, NFFT), want_lin=False, want_db=True)
-        else:
-            plan.median(out_lin, want_lin=False, want_db=True)
+            pdist.gather_columns(med_db, [1] * world, dst=0)
 
     for _ in range(max(args.warmup, 3)):
         step()

@@ -1,4 +1,9 @@
 mkdir -p gpurun_out
-timeout 600 python bench.py > gpurun_out/bench8.json 2> gpurun_out/bench8.err; echo rc=$?; python -c "
-import json; d=json.load(open('gpurun_out/bench8.json')); print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['e2e_raw_int16']['value'], d['cpu_baseline']['value'], d['clocks'])"; tail -3 gpurun_out/bench8.err
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()"
+for n in 8 4 2; do
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2954$n bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/bench_n$n.json 2> gpurun_out/bench_n$n.err
+echo "N=$n rc=$?"; python -c "
+import json
+for l in open('gpurun_out/bench_n$n.json'):
+    if l.startswith('{'):
+        d=json.loads(l); print(d['n_gpus'], round(d['value']), d['ms_per_step'], round(d['roofline']['frac'],4), d['e2e'].get('value'), d['e2e'].get('ms_per_step'), d['clocks']['sm_mhz'], d['clocks']['reasons'])"; tail -2 gpurun_out/bench_n$n.err | cut -c1-300
+done
