@@ -166,6 +166,9 @@ int psg_set_variant(const char* name);
 /* Bytes of the L2-resident scratch the large-nfft split path (nfft >= 16384) works through per
  * chunk (default 2 GiB cap; only what a call needs is allocated).  Process-wide; tuning / tests. */
 int psg_set_split_scratch(int64_t bytes);
+/* One-frame-per-column launches (Mode R) use kernels that run several columns per CTA (default on;
+ * 0 selects the one-column-per-CTA kernels).  Tuning / cross-checks. */
+int psg_set_mode_r_multi(int on);
 /* Work items per resident CTA slot that the column split aims for (default 24).  Tuning. */
 int psg_set_items_per_slot(int n);
 int psg_variant_count(void);

@@ -27,7 +27,8 @@ static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_force_generic{0};
 static std::mutex g_variant_mu;
 static std::string g_variant_override;  // "" = automatic
-static std::atomic<int> g_items_per_slot{24};  // work items per resident CTA slot the column split aims for
+static std::atomic<int> g_items_per_slot{24};
+static std::atomic<int> g_use_multi{1};  // Mode R: use the multi-column twin kernels  // work items per resident CTA slot the column split aims for
 // Scratch cap of the large-nfft split path.  Measured (profiles/r01_sweep_split_scratch*.txt): L2-sized
 // chunks (16..128 MiB) lose more to the three short dependent launches per chunk than they save in
 // HBM traffic; 1..4 GiB chunks run each phase at its own roofline.
@@ -53,13 +54,13 @@ static int fail(int code, const char* fmt, ...) {
 // ------------------------------------------------------------------------------------------------
 struct Variant {
     const char* name;
-    int logn, F, loader, threads, minb, iqt, twp;
+    int logn, F, loader, threads, minb, iqt, twp, multi;
     size_t smem;
     const void* fn;
 };
 
 template <int LOGN, int E, int R0, int R1, int R2, int R3, int F, int LOADER, int STAGES, int XBUF, int MINB, int PFL2 = 0,
-          int IQT = IQ_C64, int TWP = 0>
+          int IQT = IQ_C64, int TWP = 0, int MULTI = 0>
 static Variant make_variant(const char* name) {
     using CF = FusedCfg<LOGN, E, R0, R1, R2, R3, F, LOADER, STAGES, XBUF, IQT, TWP>;
     Variant v;
@@ -71,8 +72,9 @@ static Variant make_variant(const char* name) {
     v.minb = MINB;
     v.iqt = IQT;
     v.twp = TWP;
+    v.multi = MULTI;
     v.smem = CF::smem_bytes;
-    v.fn = (const void*)sti_fused_kernel<LOGN, E, R0, R1, R2, R3, F, LOADER, STAGES, XBUF, MINB, PFL2, IQT, TWP>;
+    v.fn = (const void*)sti_fused_kernel<LOGN, E, R0, R1, R2, R3, F, LOADER, STAGES, XBUF, MINB, PFL2, IQT, TWP, MULTI>;
     return v;
 }
 
@@ -178,6 +180,16 @@ static const Variant g_variants[] = {
     make_variant<13, 16, 8, 8, 8, 16, 1, M, 1, 1, 1>("tma13_8x8x8x16_f1_s1x1"),
     make_variant<13, 16, 8, 8, 8, 16, 1, M, 2, 1, 1>("tma13_8x8x8x16_f1_s2x1"),
     make_variant<13, 16, 2, 16, 16, 16, 1, L, 1, 1, 1>("ldg13_2x16x16x16_f1"),
+    // one-frame-per-column twins (_m) of the default TMA variants: several column blocks per CTA
+    make_variant<5, 8, 4, 8, 1, 1, 32, M, 2, 1, 8, 0, IQ_C64, 0, 1>("tma5_4x8_f32_s2x1_m"),
+    make_variant<6, 8, 8, 8, 1, 1, 16, M, 2, 1, 8, 0, IQ_C64, 0, 1>("tma6_8x8_f16_s2x1_m"),
+    make_variant<7, 16, 8, 16, 1, 1, 8, M, 2, 1, 8, 0, IQ_C64, 0, 1>("tma7_8x16_f8_s2x1_m"),
+    make_variant<8, 16, 16, 16, 1, 1, 4, M, 2, 1, 8, 0, IQ_C64, 0, 1>("tma8_16x16_f4_s2x1_m"),
+    make_variant<9, 16, 2, 16, 16, 1, 1, M, 1, 2, 16, 0, IQ_C64, 2, 1>("tma9_2x16x16_f1_s1x2_tq_m"),
+    make_variant<10, 16, 4, 16, 16, 1, 1, M, 1, 2, 8, 0, IQ_C64, 2, 1>("tma10_4x16x16_f1_s1x2_tq_m"),
+    make_variant<11, 16, 8, 16, 16, 1, 1, M, 1, 2, 4, 0, IQ_C64, 2, 1>("tma11_8x16x16_f1_s1x2_tq_m"),
+    make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 1, 2, 0, IQ_C64, 2, 1>("tma12_16x16x16_f1_s2x1_tq_m"),
+    make_variant<13, 16, 16, 8, 8, 8, 1, M, 2, 1, 1, 0, IQ_C64, 2, 1>("tma13_16x8x8x8_f1_s2x1_tq_m"),
     // raw integer IQ ingest (complex int16 / int8): the default geometry of every size, both loaders
     make_variant<5, 8, 4, 8, 1, 1, 32, L, 1, 2, 8, 0, IQ_CI16>("ldg5_4x8_f32_i16"),
     make_variant<6, 8, 8, 8, 1, 1, 32, L, 1, 2, 4, 0, IQ_CI16>("ldg6_8x8_f32_i16"),
@@ -294,6 +306,7 @@ struct psg_plan {
     std::vector<char> attr_done;  // per variant: smem attribute set on this device
     std::vector<int> occ;         // per variant: resident CTAs per SM
     char variant_name[64];
+    std::string twp_name;  // variant whose pass tables d_twp holds
 };
 
 static double bessel_i0(double x) {
@@ -358,6 +371,10 @@ extern "C" int psg_set_variant(const char* name) {
 extern "C" int psg_set_split_scratch(int64_t bytes) {
     if (bytes < (1 << 20)) return fail(PSG_ERR_ARG, "psg_set_split_scratch: at least 1 MiB");
     g_split_scratch_bytes.store(bytes);
+    return PSG_OK;
+}
+extern "C" int psg_set_mode_r_multi(int on) {
+    g_use_multi.store(on ? 1 : 0);
     return PSG_OK;
 }
 extern "C" int psg_set_items_per_slot(int n) {
@@ -627,10 +644,8 @@ extern "C" const char* psg_plan_variant(const psg_plan* p) { return p ? p->varia
 // Launch one tuned fused kernel (+ the fixed-order finalize when columns are split over CTAs).
 // `a` carries everything but the launch geometry; min_iters = fewest frame iterations worth a
 // work item of its own (bounds the share of the per-item epilogue).
-static int launch_fused(psg_plan* p, const Variant* v, StiArgs a, int ncs, int frames_per_col, int min_iters,
-                        cudaStream_t st) {
+static int variant_ready(psg_plan* p, const Variant* v) {
     const int vi = (int)(v - g_variants);
-    const int N = 1 << v->logn;
     if (!p->attr_done[vi]) {
         CUDA_TRY(cudaFuncSetAttribute(v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->smem));
         int occ = 0;
@@ -638,6 +653,17 @@ static int launch_fused(psg_plan* p, const Variant* v, StiArgs a, int ncs, int f
         if (occ < 1) return fail(PSG_ERR_CUDA, "variant %s does not fit on an SM", v->name);
         p->occ[vi] = occ;
         p->attr_done[vi] = 1;
+    }
+    return PSG_OK;
+}
+
+static int launch_fused(psg_plan* p, const Variant* v, StiArgs a, int ncs, int frames_per_col, int min_iters,
+                        cudaStream_t st, const Variant** used = nullptr) {
+    const int vi = (int)(v - g_variants);
+    const int N = 1 << v->logn;
+    {
+        int rcv = variant_ready(p, v);
+        if (rcv) return rcv;
     }
     // geometry: gpc lanes per column inside a CTA, nsplit CTAs per column
     const int F = v->F;
@@ -665,8 +691,28 @@ static int launch_fused(psg_plan* p, const Variant* v, StiArgs a, int ncs, int f
         if (rc) return rc;
         a.partial = p->d_partial;
     }
-    const long long grid = (long long)colblocks * nsplit;
+    long long grid = (long long)colblocks * nsplit;
     if (grid > 2147483647ll) return fail(PSG_ERR_ARG, "psg_sti_run: grid too large");
+    a.cb = 1;
+    if (frames_per_col == 1 && !v->multi && g_use_multi.load()) {
+        // Mode R: one frame per column -> the twin kernel that runs several column blocks per CTA
+        const Variant* vm = variant_by_name((std::string(v->name) + "_m").c_str());
+        if (vm && variant_ready(p, vm) == PSG_OK) {
+            const long long slots_m = (long long)p->sms * p->occ[(int)(vm - g_variants)];
+            int cb = 16;
+            while (cb > 1 && (grid + cb - 1) / cb < slots_m * 4) cb /= 2;  // keep every slot busy for several rounds
+            if (cb > 1) {
+                a.cb = cb;
+                grid = (grid + cb - 1) / cb;
+                v = vm;
+            }
+        }
+    } else if (v->multi) {
+        if (frames_per_col != 1) return fail(PSG_ERR_ARG, "variant %s handles one frame per column only", v->name);
+        a.cb = 4;
+        grid = (grid + 3) / 4;
+    }
+    if (used) *used = v;
     void* args[] = {(void*)&a};
     CUDA_TRY(cudaLaunchKernel(v->fn, dim3((unsigned)grid), dim3(v->threads), args, v->smem, st));
     g_launches++;
@@ -947,14 +993,20 @@ extern "C" int psg_sti_run_typed(psg_plan* p, const void* iq_dev, int iq_type, i
 
     if (v) {
         // per-pass twiddle tables: one layout per radix set; rebuilt when the variant changes
-        if (strcmp(p->variant_name, v->name) != 0 || !p->d_twp) {
+        std::string base = v->name;
+        if (v->multi) base.resize(base.size() - 2);  // "_m" twins share the tables of their base variant
+        if (p->twp_name != base || !p->d_twp) {
             if (p->d_twp) { CUDA_TRY(cudaStreamSynchronize(st)); cudaFree(p->d_twp); p->d_twp = nullptr; }
             int rc = upload_pass_tables(v, &p->d_twp);
             if (rc) return rc;
-            snprintf(p->variant_name, sizeof(p->variant_name), "%s", v->name);
+            p->twp_name = base;
         }
+        snprintf(p->variant_name, sizeof(p->variant_name), "%s", v->name);
         a.twp = p->d_twp;
-        return launch_fused(p, v, a, ncs, frames_per_col, 16, st);
+        const Variant* used = v;
+        const int rcl = launch_fused(p, v, a, ncs, frames_per_col, 16, st, &used);
+        snprintf(p->variant_name, sizeof(p->variant_name), "%s", used->name);
+        return rcl;
     }
     {
         // generic radix-2 path

@@ -63,6 +63,7 @@ struct StiArgs {
     float* out_lin;     // [nsub][ncol][N] or null
     float* out_db;      // [nsub][ncol][N] or null
     float* partial;     // [nsub*ncol][nsplit][N] raw sums when nsplit > 1
+    int cb;             // MULTI kernels: consecutive column blocks per CTA
 };
 
 enum { PSG_LOADER_LDG = 0, PSG_LOADER_TMA = 1 };
@@ -303,8 +304,12 @@ struct FusedCfg {
     static constexpr size_t smem_bytes = bar_bytes + stage_bytes + xch_bytes;
 };
 
+// MULTI (one-frame columns, Mode R): the CTA runs a.cb consecutive column blocks back to back, one
+// frame per group and iteration, with the epilogue inside the loop; the TMA producer looks ahead
+// across columns, so table loads, barrier setup and the load latency are paid once per CTA instead
+// of once per frame.
 template <int LOGN, int E, int R0, int R1, int R2, int R3, int F, int LOADER, int STAGES, int XBUF, int MINB, int PFL2 = 0,
-          int IQT = IQ_C64, int TWP = 0>
+          int IQT = IQ_C64, int TWP = 0, int MULTI = 0>
 __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(const StiArgs a) {
     using CF = FusedCfg<LOGN, E, R0, R1, R2, R3, F, LOADER, STAGES, XBUF, IQT, TWP>;
     constexpr int IQB = IqBytes<IQT>::value;
@@ -337,20 +342,29 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
 
     const int ncs = a.ncol * a.nsub;
     const int item = blockIdx.x;
-    const int split = item % a.nsplit;
-    const int cs0 = (item / a.nsplit) * cpc;
+    const int split = MULTI ? 0 : item % a.nsplit;
+    // MULTI: cs0 is the first column of the item's first block; iteration j works on block j
+    const int cs0 = MULTI ? item * a.cb * cpc : (item / a.nsplit) * cpc;
     const int cs = cs0 + slot;
     const bool col_ok = cs < ncs;
     const int k0 = split * a.chunk;
     const int k1 = min(a.nfr, k0 + a.chunk);
-    const int niter = (k1 - k0 + gpc - 1) / gpc;
+    const int niter = MULTI ? min(a.cb, (ncs + cpc - 1) / cpc - item * a.cb) : (k1 - k0 + gpc - 1) / gpc;
 
     long long fbase = 0;  // element offset of frame k0+lane of this group's column
-    if (col_ok) {
+    if (!MULTI && col_ok) {
         const int col = cs % a.ncol, sub = cs / a.ncol;
         fbase = a.col_off[col] + (long long)sub * a.sub_stride + (long long)(k0 + lane) * a.hop_elems;
     }
     const long long fstep = (long long)gpc * a.hop_elems;
+    // MULTI: the one frame of this group in iteration j (column block j of the item)
+    auto frame_of = [&](int j, bool& ok) -> long long {
+        const int c = cs0 + j * cpc + slot;
+        ok = c < ncs && lane < a.nfr;
+        if (!ok) return 0;
+        const int col = c % a.ncol, sub = c / a.ncol;
+        return a.col_off[col] + (long long)sub * a.sub_stride + (long long)lane * a.hop_elems;
+    };
 
     // ---- TMA producer: thread 0 of every frame group fetches its own group's frames ----
     // iteration pj -> stage pj % STAGES, slot g; every group leader arrives once per phase
@@ -359,7 +373,9 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
     auto produce = [&]() {
         if constexpr (LOADER == PSG_LOADER_TMA) {
             uint64_t* bar = bars + (pj % STAGES);
-            if (col_ok && (k0 + pj * gpc + lane) < k1) {
+            bool pok = col_ok && (k0 + pj * gpc + lane) < k1;
+            if constexpr (MULTI) pbase = frame_of(pj, pok);
+            if (pok) {
                 const uintptr_t src = reinterpret_cast<uintptr_t>(a.iq) + (uintptr_t)(pbase * IQB);
                 const uint32_t bytes = N * IQB + ((src & 15) ? 16 : 0);
                 mbar_expect_tx(bar, bytes);
@@ -423,8 +439,55 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
 #pragma unroll
     for (int i = 0; i < E; ++i) acc[i] = 0.f;
 
+    // ---- epilogue: digit-reversed register sums -> fftshifted, coalesced 128-bit stores ----
+    // (one frame per column in Mode R makes this as hot as the transform: keep it lean)
+    auto epilogue = [&](const int cbase, float* acc) {
+        __syncthreads();
+        float* sout = reinterpret_cast<float*>(xch);  // [F][N] floats (fits: F*NPAD*8 bytes available)
+        constexpr int RL = PL::RL;
+        constexpr int NBL = E / RL;
+        // bins are swizzled in groups of four (bits 2..4 ^= bits 5..7) so that the scattered 32-bit stores
+        // spread over the banks while every aligned group of four bins stays one 128-bit word
+    #pragma unroll
+        for (int i = 0; i < NBL; ++i) {
+            const int b = t + i * T;
+            const int klow = PL::low_freq(b);
+    #pragma unroll
+            for (int jj = 0; jj < RL; ++jj) {
+                const int freq = klow + (N / RL) * jj;
+                const int idx = (freq + N / 2) & (N - 1);
+                sout[g * N + (idx ^ (((idx >> 5) & 7) << 2))] = acc[i * RL + jj];
+            }
+        }
+        __syncthreads();
+        // all NT threads cooperate: column slot s, four bins at idx; lanes summed in fixed order
+        constexpr int NQ = N / 4;
+        const float4* sout4 = reinterpret_cast<const float4*>(sout);
+        for (int e = tid; e < cpc * NQ; e += NT) {
+            const int s = e / NQ, q = e - s * NQ;
+            const int c = cbase + s;
+            if (c >= ncs) break;
+            const int sw = q ^ ((q >> 3) & 7);  // the swizzle above, in units of four bins
+            float4 v = sout4[(s * gpc) * NQ + sw];
+            for (int l = 1; l < gpc; ++l) {
+                const float4 u = sout4[(s * gpc + l) * NQ + sw];
+                v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+            }
+            if (a.nsplit > 1) {
+                reinterpret_cast<float4*>(a.partial + ((size_t)c * a.nsplit + split) * N)[q] = v;
+            } else {
+                v.x *= a.scale; v.y *= a.scale; v.z *= a.scale; v.w *= a.scale;
+                const size_t o = (size_t)c * NQ + q;
+                if (a.out_lin) reinterpret_cast<float4*>(a.out_lin)[o] = v;
+                if (a.out_db)
+                    reinterpret_cast<float4*>(a.out_db)[o] = make_float4(power_to_db(v.x, a.eps), power_to_db(v.y, a.eps),
+                                                                         power_to_db(v.z, a.eps), power_to_db(v.w, a.eps));
+            }
+        }
+    };
     for (int j = 0; j < niter; ++j, fbase += fstep) {
-        const bool valid = col_ok && (k0 + j * gpc + lane) < k1;
+        bool valid = col_ok && (k0 + j * gpc + lane) < k1;
+        if constexpr (MULTI) fbase = frame_of(j, valid);
         float2* buf = xch + (size_t)(g * XBUF + (XBUF > 1 ? (j & 1) : 0)) * NPAD;
         cf x[E];
         // ---- pass 0: samples -> registers ----
@@ -499,52 +562,16 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
             exchange_sync<L23>();
             smem_pass<E, T, R3, PL::S3, true>(buf, nullptr, t, acc);
         }
+        if constexpr (MULTI) {  // every frame is a finished column
+            epilogue(cs0 + j * cpc, acc);
+#pragma unroll
+            for (int i = 0; i < E; ++i) acc[i] = 0.f;
+            __syncthreads();  // the staging area of the epilogue aliases the exchange buffers
+        }
     }
+    if constexpr (!MULTI) epilogue(cs0, acc);
 
-    // ---- epilogue: digit-reversed register sums -> fftshifted, coalesced 128-bit stores ----
-    // (one frame per column in Mode R makes this as hot as the transform: keep it lean)
-    __syncthreads();
-    float* sout = reinterpret_cast<float*>(xch);  // [F][N] floats (fits: F*NPAD*8 bytes available)
-    constexpr int RL = PL::RL;
-    constexpr int NBL = E / RL;
-    // bins are swizzled in groups of four (bits 2..4 ^= bits 5..7) so that the scattered 32-bit stores
-    // spread over the banks while every aligned group of four bins stays one 128-bit word
-#pragma unroll
-    for (int i = 0; i < NBL; ++i) {
-        const int b = t + i * T;
-        const int klow = PL::low_freq(b);
-#pragma unroll
-        for (int jj = 0; jj < RL; ++jj) {
-            const int freq = klow + (N / RL) * jj;
-            const int idx = (freq + N / 2) & (N - 1);
-            sout[g * N + (idx ^ (((idx >> 5) & 7) << 2))] = acc[i * RL + jj];
-        }
-    }
-    __syncthreads();
-    // all NT threads cooperate: column slot s, four bins at idx; lanes summed in fixed order
-    constexpr int NQ = N / 4;
-    const float4* sout4 = reinterpret_cast<const float4*>(sout);
-    for (int e = tid; e < cpc * NQ; e += NT) {
-        const int s = e / NQ, q = e - s * NQ;
-        const int c = cs0 + s;
-        if (c >= ncs) break;
-        const int sw = q ^ ((q >> 3) & 7);  // the swizzle above, in units of four bins
-        float4 v = sout4[(s * gpc) * NQ + sw];
-        for (int l = 1; l < gpc; ++l) {
-            const float4 u = sout4[(s * gpc + l) * NQ + sw];
-            v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
-        }
-        if (a.nsplit > 1) {
-            reinterpret_cast<float4*>(a.partial + ((size_t)c * a.nsplit + split) * N)[q] = v;
-        } else {
-            v.x *= a.scale; v.y *= a.scale; v.z *= a.scale; v.w *= a.scale;
-            const size_t o = (size_t)c * NQ + q;
-            if (a.out_lin) reinterpret_cast<float4*>(a.out_lin)[o] = v;
-            if (a.out_db)
-                reinterpret_cast<float4*>(a.out_db)[o] = make_float4(power_to_db(v.x, a.eps), power_to_db(v.y, a.eps),
-                                                                     power_to_db(v.z, a.eps), power_to_db(v.w, a.eps));
-        }
-    }
+
 }
 
 // Sum the partial columns of split work items (fixed order -> deterministic), scale, store.

@@ -162,7 +162,7 @@ def test_every_variant_matches_float64_oracle(torch, variant):
     logn = dict(_all_variants())[variant]
     nfft = 1 << logn
     rng = np.random.default_rng(logn * 7 + 1)
-    nfr, ncol = 5, 7
+    nfr, ncol = (1, 23) if variant.endswith("_m") else (5, 7)  # "_m": one-frame-per-column kernels
     n = nfft * (nfr * ncol + 3) + 11
     x = _recording(rng, n)
     starts = np.sort(rng.choice(n - nfr * nfft, ncol, replace=False)).astype(np.int64)
@@ -346,6 +346,29 @@ def test_drop_in_accepts_raw_iq_and_processor_raw_ingest(dp):
     (t0, fa, sa, ma), (t1, fb, sb, mb) = out
     assert np.array_equal(fa, fb) and sa.shape == sb.shape == (1024, 16, nsub)
     assert np.abs(sa - sb).max() <= 1e-3 and np.abs(ma - mb).max() <= 1e-3
+
+
+@pytest.mark.parametrize("nfft", [32, 256, 1024, 4096, 8192])
+def test_mode_r_multi_column_kernels_match_single_column_kernels(torch, nfft):
+    """Mode R launches use kernels that run several column blocks per CTA; bit-identical to the
+    one-column-per-CTA kernels (same arithmetic, same order), ragged last block included."""
+    ncol = 200003 if nfft <= 256 else 20011
+    from pyspectrogram_b200 import _lib, engine
+    rng = np.random.default_rng(nfft + 5)
+    x = torch.from_numpy(_recording(rng, ncol * 3 + nfft + 7)).cuda()
+    starts = torch.from_numpy((np.arange(ncol) * 3).astype(np.int64)).cuda()  # overlapping, odd and even starts
+    plan = engine.StiPlan(nfft)
+    lin_m, db_m = plan.run(x, starts, 1, nfft, want_lin=True, want_db=True)
+    name_m = plan.variant
+    try:
+        _lib.check(_lib.load().psg_set_mode_r_multi(0))
+        lin_s, db_s = plan.run(x, starts, 1, nfft, want_lin=True, want_db=True)
+        name_s = plan.variant
+    finally:
+        _lib.check(_lib.load().psg_set_mode_r_multi(1))
+    # small nfft packs many columns into one CTA already: too few column blocks here to batch further
+    assert name_m == name_s + "_m" or (nfft < 1024 and name_m == name_s), (name_m, name_s)
+    assert torch.equal(lin_m, lin_s) and torch.equal(db_m, db_s)
 
 
 def test_generic_kernel_cross_checks_tuned(torch):
