@@ -34,6 +34,30 @@ def main():
         print(f"Mode R nfft={nfft:6d} ncol={ncol:6d}: {ms:8.4f} ms  {ncol / ms / 1e3:9.1f} Mcols/s  "
               f"{nbytes / ms / 1e6:7.0f} GB/s (8 B in + 4 B out per sample)  {plan.variant}", flush=True)
         del iq, out
+    # short integrations (a few frames per column): multi-column twin kernels on / off
+    from pyspectrogram_b200 import _lib
+    for nfft, nint, ncol in ((1024, 4, 50000), (4096, 4, 25000), (4096, 8, 12500), (65536, 4, 1800)):
+        n = nfft * nint * ncol
+        iq = torch.empty(n + 8, dtype=torch.complex64, device=dev)
+        torch.view_as_real(iq).normal_(0, 1e-2)
+        starts = torch.arange(ncol, device=dev, dtype=torch.int64) * (nfft * nint)
+        plan = engine.StiPlan(nfft)
+        out = torch.empty((1, ncol, nfft), dtype=torch.float32, device=dev)
+        line = f"Mode A nfft={nfft:6d} nint={nint} ncol={ncol:6d}:"
+        for multi in (1, 0):
+            _lib.check(_lib.load().psg_set_mode_r_multi(multi))
+            run = lambda: plan.run(iq, starts, nint, nfft, want_lin=False, want_db=True, out_db=out)
+            run(); torch.cuda.synchronize()
+            ts = []
+            for _ in range(7):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); run(); e1.record(); torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ms = float(np.median(ts))
+            line += f"  [{plan.variant}] {ms:.4f} ms {n / ms / 1e6:6.1f} Gs/s"
+        _lib.check(_lib.load().psg_set_mode_r_multi(1))
+        print(line, flush=True)
+        del iq, out
     # cfg1 through the drop-in API (host arrays, as the reference is called)
     rng = np.random.default_rng(0)
     d1 = ((rng.standard_normal((1024 * 97, 100)) + 1j * rng.standard_normal((1024 * 97, 100))) * 1e-2).astype(np.complex64)
