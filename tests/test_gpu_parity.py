@@ -602,6 +602,33 @@ def test_c_abi_from_plain_c(tmp_path):
     assert "c-abi smoke" in res.stdout and "6_8x8" in res.stdout
 
 
+@pytest.mark.parametrize("nchan,nfft,ntime,nint,world", [(1, 65536, 12, 2, 4), (8, 16384, 6, 3, 8), (3, 1024, 50, 4, 4)])
+def test_sharded_columns_equal_the_single_gpu_image(torch, nchan, nfft, ntime, nint, world):
+    """SURVEY.md section 8(e) on one GPU: every rank's shard (whole channels when nchan >= world, as in
+    BASELINE config 3; contiguous time-bin ranges otherwise, config 4) computed on its own and
+    concatenated in rank order is bit-identical to the image of one launch over all columns, and the
+    time-median of the assembled image equals numpy's."""
+    from pyspectrogram_b200 import dist as pdist
+    from pyspectrogram_b200 import engine
+    rng = np.random.default_rng(nfft + world)
+    n = nfft * nint * ntime + 3 * nfft
+    chans = [torch.from_numpy(_recording(rng, n)).cuda() for _ in range(nchan)]
+    starts = engine.frame_starts(5, n, nfft, nint, ntime).astype(np.int64)
+    plan = engine.StiPlan(nfft)
+    whole = torch.stack([plan.run(ch, torch.from_numpy(starts).cuda(), nint, nfft)[0][0] for ch in chans])  # [chan][t][f]
+    pieces = pdist.shard_plan(nchan, ntime, world)
+    assert sum(hi - lo for r in pieces for (_, lo, hi) in r) == nchan * ntime
+    parts = []
+    for rank_pieces in pieces:
+        for (c, lo, hi) in rank_pieces:
+            lin, _ = plan.run(chans[c], torch.from_numpy(starts[lo:hi]).cuda(), nint, nfft)
+            parts.append(lin[0])
+    assembled = torch.cat(parts, dim=0).reshape(nchan, ntime, nfft)
+    assert torch.equal(assembled, whole)
+    med, _ = plan.median(assembled)
+    assert np.array_equal(med.cpu().numpy(), np.median(whole.cpu().numpy(), axis=1))
+
+
 def test_large_workload_properties(torch):
     """Size-independent properties at a bench-like size (1 GiB of IQ, nfft=4096, nint=128):
     Parseval (sum of the PSD column == mean windowed frame energy * N / sum(w)^2), a unit tone
