@@ -84,83 +84,38 @@ static Variant make_variant(const char* name) {
 static const Variant g_variants[] = {
     //            LOGN E  R0  R1  R2 R3  F  LD ST XB MINB
     make_variant<5, 8, 4, 8, 1, 1, 32, L, 1, 2, 8>("ldg5_4x8_f32"),
-    make_variant<5, 8, 4, 8, 1, 1, 64, L, 1, 2, 4>("ldg5_4x8_f64"),
     make_variant<6, 8, 8, 8, 1, 1, 32, L, 1, 2, 4>("ldg6_8x8_f32"),
-    make_variant<6, 8, 8, 8, 1, 1, 16, L, 1, 2, 8>("ldg6_8x8_f16"),
-    make_variant<7, 8, 2, 8, 8, 1, 16, L, 1, 2, 4>("ldg7_2x8x8_f16"),
     make_variant<7, 16, 8, 16, 1, 1, 16, L, 1, 2, 4>("ldg7_8x16_f16"),
-    make_variant<7, 16, 8, 16, 1, 1, 32, L, 1, 2, 2>("ldg7_8x16_f32"),
-    make_variant<8, 16, 16, 16, 1, 1, 16, M, 3, 2, 2>("tma8_16x16_f16_s3x2"),
-    make_variant<8, 16, 16, 16, 1, 1, 16, L, 1, 2, 2>("ldg8_16x16_f16"),
     make_variant<8, 16, 16, 16, 1, 1, 8, L, 1, 2, 4>("ldg8_16x16_f8"),
-    make_variant<8, 16, 16, 16, 1, 1, 4, L, 1, 2, 8>("ldg8_16x16_f4"),
-    make_variant<8, 16, 16, 16, 1, 1, 2, L, 1, 2, 16>("ldg8_16x16_f2"),
-    make_variant<9, 16, 2, 16, 16, 1, 8, M, 3, 2, 2>("tma9_2x16x16_f8_s3x2"),
-    make_variant<9, 16, 16, 16, 2, 1, 8, M, 3, 2, 2>("tma9_16x16x2_f8_s3x2"),
-    make_variant<9, 16, 2, 16, 16, 1, 8, L, 1, 2, 2>("ldg9_2x16x16_f8"),
-    make_variant<9, 8, 8, 8, 8, 1, 4, L, 1, 2, 4>("ldg9_8x8x8_f4"),
-    make_variant<9, 8, 8, 8, 8, 1, 8, L, 1, 2, 2>("ldg9_8x8x8_f8"),
-    make_variant<9, 8, 8, 8, 8, 1, 2, L, 1, 2, 8>("ldg9_8x8x8_f2"),
     make_variant<9, 8, 8, 8, 8, 1, 1, L, 1, 2, 16>("ldg9_8x8x8_f1"),
-    make_variant<9, 16, 2, 16, 16, 1, 4, L, 1, 2, 4>("ldg9_2x16x16_f4"),
-    make_variant<9, 16, 2, 16, 16, 1, 2, L, 1, 2, 8>("ldg9_2x16x16_f2"),
-    make_variant<9, 8, 8, 8, 8, 1, 4, M, 3, 2, 4>("tma9_8x8x8_f4_s3x2"),
-    make_variant<10, 16, 4, 16, 16, 1, 4, M, 3, 2, 2>("tma10_4x16x16_f4_s3x2"),
-    make_variant<10, 16, 16, 16, 4, 1, 4, M, 3, 2, 2>("tma10_16x16x4_f4_s3x2"),
-    make_variant<10, 16, 4, 16, 16, 1, 4, L, 1, 2, 2>("ldg10_4x16x16_f4"),
-    make_variant<10, 16, 4, 16, 16, 1, 2, L, 1, 2, 4>("ldg10_4x16x16_f2"),
     make_variant<10, 16, 4, 16, 16, 1, 1, L, 1, 2, 8>("ldg10_4x16x16_f1"),
-    make_variant<10, 16, 4, 16, 16, 1, 1, L, 1, 2, 8, 2>("ldg10_4x16x16_f1_pf2"),
-    make_variant<10, 16, 4, 16, 16, 1, 1, L, 1, 1, 8, 4>("ldg10_4x16x16_f1_x1_pf4"),
-    make_variant<10, 16, 4, 16, 16, 1, 1, M, 3, 2, 8>("tma10_4x16x16_f1_s3x2"),
     make_variant<10, 16, 4, 16, 16, 1, 1, M, 2, 1, 8>("tma10_4x16x16_f1_s2x1"),
-    make_variant<10, 16, 4, 16, 16, 1, 8, L, 1, 2, 1>("ldg10_4x16x16_f8"),
-    make_variant<11, 16, 8, 16, 16, 1, 2, M, 3, 2, 2>("tma11_8x16x16_f2_s3x2"),
-    make_variant<11, 16, 16, 16, 8, 1, 2, M, 3, 2, 2>("tma11_16x16x8_f2_s3x2"),
-    make_variant<11, 16, 8, 16, 16, 1, 2, L, 1, 2, 2>("ldg11_8x16x16_f2"),
     make_variant<11, 16, 8, 16, 16, 1, 1, L, 1, 2, 4>("ldg11_8x16x16_f1"),
-    make_variant<11, 16, 8, 16, 16, 1, 1, L, 1, 1, 4>("ldg11_8x16x16_f1_x1"),
     make_variant<11, 16, 8, 16, 16, 1, 1, M, 2, 1, 4>("tma11_8x16x16_f1_s2x1"),
-    make_variant<11, 16, 8, 16, 16, 1, 1, M, 3, 2, 4>("tma11_8x16x16_f1_s3x2"),
-    make_variant<11, 16, 8, 16, 16, 1, 4, L, 1, 2, 1>("ldg11_8x16x16_f4"),
     make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 1, 2>("tma12_16x16x16_f1_s2x1"),
     make_variant<12, 16, 16, 16, 16, 1, 1, M, 1, 2, 2>("tma12_16x16x16_f1_s1x2"),
-    make_variant<12, 16, 16, 16, 16, 1, 1, M, 3, 2, 1>("tma12_16x16x16_f1_s3x2"),
-    make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 2, 1>("tma12_16x16x16_f1_s2x2"),
     make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 2, 2>("ldg12_16x16x16_f1"),
-    make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 1, 2>("ldg12_16x16x16_f1_x1"),
-    make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 1, 2, 1>("ldg12_16x16x16_f1_x1_pf1"),
     make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 1, 2, 2>("ldg12_16x16x16_f1_x1_pf2"),
-    make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 2, 2, 2>("ldg12_16x16x16_f1_x2_pf2"),
-    make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 1, 2, 4>("ldg12_16x16x16_f1_x1_pf4"),
     make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 1, 2, 0, IQ_C64, 1>("tma12_16x16x16_f1_s2x1_tp"),
     make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 1, 2, 0, IQ_C64, 2>("tma12_16x16x16_f1_s2x1_tq"),
     make_variant<12, 16, 16, 16, 16, 1, 1, M, 1, 2, 2, 0, IQ_C64, 2>("tma12_16x16x16_f1_s1x2_tq"),
-    make_variant<11, 16, 16, 16, 8, 1, 1, M, 2, 1, 4, 0, IQ_C64, 2>("tma11_16x16x8_f1_s2x1_tq"),
     make_variant<11, 16, 8, 16, 16, 1, 1, M, 1, 2, 4, 0, IQ_C64, 2>("tma11_8x16x16_f1_s1x2_tq"),
-    make_variant<10, 16, 16, 16, 4, 1, 1, M, 2, 1, 8, 0, IQ_C64, 2>("tma10_16x16x4_f1_s2x1_tq"),
     make_variant<10, 16, 8, 8, 16, 1, 1, M, 2, 1, 8, 0, IQ_C64, 2>("tma10_8x8x16_f1_s2x1_tq"),
     make_variant<10, 16, 4, 16, 16, 1, 1, M, 1, 2, 8, 0, IQ_C64, 2>("tma10_4x16x16_f1_s1x2_tq"),
     make_variant<9, 8, 8, 8, 8, 1, 1, M, 2, 1, 16, 0, IQ_C64, 1>("tma9_8x8x8_f1_s2x1_tp"),
     make_variant<9, 16, 2, 16, 16, 1, 1, M, 2, 1, 16, 0, IQ_C64, 2>("tma9_2x16x16_f1_s2x1_tq"),
-    make_variant<8, 16, 16, 16, 1, 1, 1, M, 2, 1, 16>("tma8_16x16_f1_s2x1"),
     make_variant<8, 16, 16, 16, 1, 1, 2, M, 2, 1, 16>("tma8_16x16_f2_s2x1"),
     make_variant<8, 16, 16, 16, 1, 1, 4, M, 2, 1, 8>("tma8_16x16_f4_s2x1"),
-    make_variant<9, 16, 2, 16, 16, 1, 2, M, 2, 1, 8, 0, IQ_C64, 2>("tma9_2x16x16_f2_s2x1_tq"),
     make_variant<9, 16, 2, 16, 16, 1, 1, M, 1, 2, 16, 0, IQ_C64, 2>("tma9_2x16x16_f1_s1x2_tq"),
-    make_variant<7, 16, 8, 16, 1, 1, 2, M, 2, 1, 16>("tma7_8x16_f2_s2x1"),
     make_variant<7, 16, 8, 16, 1, 1, 4, M, 2, 1, 16>("tma7_8x16_f4_s2x1"),
     make_variant<7, 16, 8, 16, 1, 1, 8, M, 2, 1, 8>("tma7_8x16_f8_s2x1"),
-    make_variant<6, 8, 8, 8, 1, 1, 4, M, 2, 1, 16>("tma6_8x8_f4_s2x1"),
     make_variant<6, 8, 8, 8, 1, 1, 8, M, 2, 1, 16>("tma6_8x8_f8_s2x1"),
     make_variant<6, 8, 8, 8, 1, 1, 16, M, 2, 1, 8>("tma6_8x8_f16_s2x1"),
-    make_variant<5, 8, 4, 8, 1, 1, 8, M, 2, 1, 16>("tma5_4x8_f8_s2x1"),
     make_variant<5, 8, 4, 8, 1, 1, 16, M, 2, 1, 16>("tma5_4x8_f16_s2x1"),
     make_variant<5, 8, 4, 8, 1, 1, 32, M, 2, 1, 8>("tma5_4x8_f32_s2x1"),
     make_variant<11, 16, 8, 16, 16, 1, 1, M, 2, 1, 4, 0, IQ_C64, 2>("tma11_8x16x16_f1_s2x1_tq"),
     make_variant<10, 16, 4, 16, 16, 1, 1, M, 2, 1, 8, 0, IQ_C64, 2>("tma10_4x16x16_f1_s2x1_tq"),
     make_variant<13, 16, 16, 8, 8, 8, 1, M, 2, 1, 1, 0, IQ_C64, 2>("tma13_16x8x8x8_f1_s2x1_tq"),
-    make_variant<9, 8, 8, 8, 8, 1, 1, L, 1, 2, 16, 0, IQ_C64, 2>("ldg9_8x8x8_f1_tq"),
     make_variant<11, 16, 8, 16, 16, 1, 1, M, 2, 1, 4, 0, IQ_C64, 1>("tma11_8x16x16_f1_s2x1_tp"),
     make_variant<10, 16, 4, 16, 16, 1, 1, M, 2, 1, 8, 0, IQ_C64, 1>("tma10_4x16x16_f1_s2x1_tp"),
     make_variant<13, 16, 16, 8, 8, 8, 1, M, 2, 1, 1, 0, IQ_C64, 1>("tma13_16x8x8x8_f1_s2x1_tp"),
@@ -171,13 +126,7 @@ static const Variant g_variants[] = {
     make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 1, 2, 2, IQ_C64, 1>("ldg12_16x16x16_f1_x1_pf2_tp"),
     make_variant<13, 16, 2, 16, 16, 16, 1, L, 1, 1, 1, 0, IQ_C64, 1>("ldg13_2x16x16x16_f1_tp"),
     make_variant<12, 8, 8, 8, 8, 8, 1, M, 2, 1, 2>("tma12_8x8x8x8_f1_s2x1"),
-    make_variant<12, 8, 8, 8, 8, 8, 1, M, 3, 2, 2>("tma12_8x8x8x8_f1_s3x2"),
-    make_variant<12, 16, 16, 4, 8, 8, 1, M, 2, 1, 2>("tma12_16x4x8x8_f1_s2x1"),
-    make_variant<13, 16, 2, 16, 16, 16, 1, M, 2, 1, 1>("tma13_2x16x16x16_f1_s2x1"),
     make_variant<13, 16, 16, 8, 8, 8, 1, M, 2, 1, 1>("tma13_16x8x8x8_f1_s2x1"),
-    make_variant<13, 16, 8, 16, 8, 8, 1, M, 2, 1, 1>("tma13_8x16x8x8_f1_s2x1"),
-    make_variant<13, 16, 16, 16, 4, 8, 1, M, 2, 1, 1>("tma13_16x16x4x8_f1_s2x1"),
-    make_variant<13, 16, 8, 8, 8, 16, 1, M, 1, 1, 1>("tma13_8x8x8x16_f1_s1x1"),
     make_variant<13, 16, 8, 8, 8, 16, 1, M, 2, 1, 1>("tma13_8x8x8x16_f1_s2x1"),
     make_variant<13, 16, 2, 16, 16, 16, 1, L, 1, 1, 1>("ldg13_2x16x16x16_f1"),
     // one-frame-per-column twins (_m) of the default TMA variants: several column blocks per CTA
