@@ -77,6 +77,40 @@ PSG_DEV void dft4(cf& a0, cf& a1, cf& a2, cf& a3) {
     a3 = csub(t1, t3);
 }
 
+// c + a*w (complex): 2 instructions
+PSG_DEV cf cfma(cf a, cf w, cf c) {
+    cf t = fma2(a, make_float2(w.x, w.x), c);
+    return fma2(make_float2(a.y, a.x), make_float2(-w.y, w.y), t);
+}
+PSG_DEV cf twice_minus(cf m, cf s) {  // 2*m - s: the difference of a butterfly from its sum, 1 instruction
+    return fma2(m, make_float2(2.0f, 2.0f), make_float2(-s.x, -s.y));
+}
+
+// 4-point DFT of (a0, W1*v1, W2*v2, W3*v3) with the constant multiplies folded into the first
+// layer: 12 instructions instead of 3 complex multiplies + 8 adds = 14.
+PSG_DEV void dft4_tw(cf& a0, cf& v1, cf& v2, cf& v3, cf W1, cf W2, cf W3) {
+    const cf t0 = cfma(v2, W2, a0), t1 = twice_minus(a0, t0);
+    const cf m1 = cmul(v1, W1);
+    const cf t2 = cfma(v3, W3, m1), d = twice_minus(m1, t2);
+    const cf t3 = mul_nj(d);
+    a0 = cadd(t0, t2);
+    v2 = csub(t0, t2);
+    v1 = cadd(t1, t3);
+    v3 = csub(t1, t3);
+}
+// same with W2 = -j (free): 11 instead of 12
+PSG_DEV void dft4_tw_nj(cf& a0, cf& v1, cf& v2, cf& v3, cf W1, cf W3) {
+    const cf r2 = mul_nj(v2);
+    const cf t0 = cadd(a0, r2), t1 = csub(a0, r2);
+    const cf m1 = cmul(v1, W1);
+    const cf t2 = cfma(v3, W3, m1), d = twice_minus(m1, t2);
+    const cf t3 = mul_nj(d);
+    a0 = cadd(t0, t2);
+    v2 = csub(t0, t2);
+    v1 = cadd(t1, t3);
+    v3 = csub(t1, t3);
+}
+
 #define PSG_SQRT1_2 0.70710678118654752440f
 #define PSG_C1_16 0.92387953251128675613f  // cos(pi/8)
 #define PSG_S1_16 0.38268343236508977173f  // sin(pi/8)
@@ -87,11 +121,9 @@ PSG_DEV void dft8(cf* a) {
     cf s1 = cadd(a[1], a[5]), d1 = csub(a[1], a[5]);
     cf s2 = cadd(a[2], a[6]), d2 = csub(a[2], a[6]);
     cf s3 = cadd(a[3], a[7]), d3 = csub(a[3], a[7]);
-    d1 = cmul(d1, make_float2(PSG_SQRT1_2, -PSG_SQRT1_2));
-    d2 = mul_nj(d2);
-    d3 = cmul(d3, make_float2(-PSG_SQRT1_2, -PSG_SQRT1_2));
     dft4(s0, s1, s2, s3);  // X[0], X[2], X[4], X[6]
-    dft4(d0, d1, d2, d3);  // X[1], X[3], X[5], X[7]
+    // X[1], X[3], X[5], X[7]: W8^1, W8^2 = -j, W8^3 on d1, d2, d3 folded into the 4-point DFT
+    dft4_tw_nj(d0, d1, d2, d3, make_float2(PSG_SQRT1_2, -PSG_SQRT1_2), make_float2(-PSG_SQRT1_2, -PSG_SQRT1_2));
     a[0] = s0; a[2] = s1; a[4] = s2; a[6] = s3;
     a[1] = d0; a[3] = d1; a[5] = d2; a[7] = d3;
 }
@@ -105,18 +137,18 @@ PSG_DEV void dft16(cf* a) {
         dft4(u[i][0], u[i][1], u[i][2], u[i][3]);  // index c
     }
     // internal twiddles W16^{i*c}
-    u[1][1] = cmul(u[1][1], make_float2(PSG_C1_16, -PSG_S1_16));      // W16^1
-    u[1][2] = cmul(u[1][2], make_float2(PSG_SQRT1_2, -PSG_SQRT1_2));  // W16^2
-    u[1][3] = cmul(u[1][3], make_float2(PSG_S1_16, -PSG_C1_16));      // W16^3
-    u[2][1] = cmul(u[2][1], make_float2(PSG_SQRT1_2, -PSG_SQRT1_2));  // W16^2
-    u[2][2] = mul_nj(u[2][2]);                                        // W16^4
-    u[2][3] = cmul(u[2][3], make_float2(-PSG_SQRT1_2, -PSG_SQRT1_2)); // W16^6
-    u[3][1] = cmul(u[3][1], make_float2(PSG_S1_16, -PSG_C1_16));      // W16^3
-    u[3][2] = cmul(u[3][2], make_float2(-PSG_SQRT1_2, -PSG_SQRT1_2)); // W16^6
-    u[3][3] = cmul(u[3][3], make_float2(-PSG_C1_16, PSG_S1_16));      // W16^9
+    // internal twiddles W16^{i*c} folded into the second layer of 4-point DFTs (index d)
+    dft4(u[0][0], u[1][0], u[2][0], u[3][0]);
+    dft4_tw(u[0][1], u[1][1], u[2][1], u[3][1], make_float2(PSG_C1_16, -PSG_S1_16),      // W16^1
+            make_float2(PSG_SQRT1_2, -PSG_SQRT1_2),                                        // W16^2
+            make_float2(PSG_S1_16, -PSG_C1_16));                                           // W16^3
+    dft4_tw_nj(u[0][2], u[1][2], u[2][2], u[3][2], make_float2(PSG_SQRT1_2, -PSG_SQRT1_2),  // W16^2, (W16^4 = -j)
+               make_float2(-PSG_SQRT1_2, -PSG_SQRT1_2));                                   // W16^6
+    dft4_tw(u[0][3], u[1][3], u[2][3], u[3][3], make_float2(PSG_S1_16, -PSG_C1_16),      // W16^3
+            make_float2(-PSG_SQRT1_2, -PSG_SQRT1_2),                                       // W16^6
+            make_float2(-PSG_C1_16, PSG_S1_16));                                           // W16^9
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        dft4(u[0][c], u[1][c], u[2][c], u[3][c]);  // index d
         a[c] = u[0][c]; a[c + 4] = u[1][c]; a[c + 8] = u[2][c]; a[c + 12] = u[3][c];
     }
 }
@@ -148,18 +180,18 @@ PSG_DEV void dft16w(cf* a, const float* w) {
         u[i][0] = a[i]; u[i][1] = a[i + 4]; u[i][2] = a[i + 8]; u[i][3] = a[i + 12];
         dft4w(u[i][0], u[i][1], u[i][2], u[i][3], w[i], w[i + 4], w[i + 8], w[i + 12]);
     }
-    u[1][1] = cmul(u[1][1], make_float2(PSG_C1_16, -PSG_S1_16));
-    u[1][2] = cmul(u[1][2], make_float2(PSG_SQRT1_2, -PSG_SQRT1_2));
-    u[1][3] = cmul(u[1][3], make_float2(PSG_S1_16, -PSG_C1_16));
-    u[2][1] = cmul(u[2][1], make_float2(PSG_SQRT1_2, -PSG_SQRT1_2));
-    u[2][2] = mul_nj(u[2][2]);
-    u[2][3] = cmul(u[2][3], make_float2(-PSG_SQRT1_2, -PSG_SQRT1_2));
-    u[3][1] = cmul(u[3][1], make_float2(PSG_S1_16, -PSG_C1_16));
-    u[3][2] = cmul(u[3][2], make_float2(-PSG_SQRT1_2, -PSG_SQRT1_2));
-    u[3][3] = cmul(u[3][3], make_float2(-PSG_C1_16, PSG_S1_16));
+    // internal twiddles W16^{i*c} folded into the second layer of 4-point DFTs (index d)
+    dft4(u[0][0], u[1][0], u[2][0], u[3][0]);
+    dft4_tw(u[0][1], u[1][1], u[2][1], u[3][1], make_float2(PSG_C1_16, -PSG_S1_16),      // W16^1
+            make_float2(PSG_SQRT1_2, -PSG_SQRT1_2),                                        // W16^2
+            make_float2(PSG_S1_16, -PSG_C1_16));                                           // W16^3
+    dft4_tw_nj(u[0][2], u[1][2], u[2][2], u[3][2], make_float2(PSG_SQRT1_2, -PSG_SQRT1_2),  // W16^2, (W16^4 = -j)
+               make_float2(-PSG_SQRT1_2, -PSG_SQRT1_2));                                   // W16^6
+    dft4_tw(u[0][3], u[1][3], u[2][3], u[3][3], make_float2(PSG_S1_16, -PSG_C1_16),      // W16^3
+            make_float2(-PSG_SQRT1_2, -PSG_SQRT1_2),                                       // W16^6
+            make_float2(-PSG_C1_16, PSG_S1_16));                                           // W16^9
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        dft4(u[0][c], u[1][c], u[2][c], u[3][c]);
         a[c] = u[0][c]; a[c + 4] = u[1][c]; a[c + 8] = u[2][c]; a[c + 12] = u[3][c];
     }
 }
