@@ -442,9 +442,8 @@ class DrfProcessor(QRunnable):
         torch = engine._torch()
         plan = engine.get_plan(nfft, self.device)
         offs = torch.from_numpy(((n_st - base) * nsub).astype(np.int64)).to(buf.device)
-        _, db = plan.run(buf, offs, frames, nfft, sample_stride=nsub, sub_stride=1, nsub=nsub, in_scale=in_scale,
-                         eps=_EPS, want_lin=True, want_db=True)
-        lin = _
+        lin, db = plan.run(buf, offs, frames, nfft, sample_stride=nsub, sub_stride=1, nsub=nsub, in_scale=in_scale,
+                           eps=_EPS, want_lin=True, want_db=True)
         _, mdb = plan.median(lin, eps=_EPS, want_lin=False, want_db=True)
         sxx_dbfs = db.permute(2, 1, 0).cpu().numpy()      # (nfft, ntime, nsub) as the viewer indexes it
         sxx_med_dbfs = mdb.t().cpu().numpy()               # (nfft, nsub)
