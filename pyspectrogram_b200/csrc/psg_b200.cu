@@ -623,7 +623,11 @@ static int launch_fused(psg_plan* p, const Variant* v, StiArgs a, int ncs, int f
     const long long slots = (long long)p->sms * p->occ[vi];
     const long long target = slots * g_items_per_slot.load();
     int nsplit = (int)std::min<long long>((target + colblocks - 1) / colblocks, 1 << 20);
-    const int smin = (iters + 255) / 256, smax = std::max(1, iters / min_iters);
+    // enough column blocks to keep every slot busy for three rounds: do not split columns at all (no
+    // partial sums, no finalize launch; measured equal kernel time on cfg2)
+    if (colblocks >= 3 * slots) nsplit = 1;
+    // at most 1024 frames per fp32 accumulator (longer columns are split and summed in fp64)
+    const int smin = (iters + 1023) / 1024, smax = std::max(1, iters / min_iters);
     nsplit = std::max(smin, std::min(nsplit, smax));
     nsplit = std::max(nsplit, 1);
     int chunk = ((iters + nsplit - 1) / nsplit) * gpc;

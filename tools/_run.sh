@@ -1,5 +1,4 @@
-mkdir -p gpurun_out
-python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-raw > gpurun_out/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_launches_bench.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-raw > gpurun_out/ncu_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:sti_fused_kernel -s 3 -c 1 -o gpurun_out/r01_full_tma12_tq_cfg2_final -f python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-raw > gpurun_out/ncu_full.log 2>&1
-tail -2 gpurun_out/ncu_full.log
+(timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4)
+for i in 1 2; do timeout 300 python bench.py --no-cpu --no-raw --no-e2e --steps 20 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value']), d['ms_per_step'], d['roofline']['frac'], d['roofline']['kernel_ms'], d['gpu_launches'])"; done
+timeout 600 python tools/default_sweep.py --gb 4 2>&1 | tail -12
