@@ -18,6 +18,7 @@
 
 #include "../../include/psg_b200.h"
 #include "sti_kernels.cuh"
+#include "sti_cluster.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -33,6 +34,7 @@ static std::atomic<int> g_use_multi{1};  // Mode R: use the multi-column twin ke
 // chunks (16..128 MiB) lose more to the three short dependent launches per chunk than they save in
 // HBM traffic; 1..4 GiB chunks run each phase at its own roofline.
 static std::atomic<long long> g_split_scratch_bytes{2048ll << 20};
+static std::atomic<int> g_cluster_rowtma{0};  // cluster path: 0 = rows loaded to registers (default), 1 = by bulk copy, 2 = DSMEM exchange
 
 static int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -229,6 +231,9 @@ struct psg_plan {
     size_t tmp_bytes = 0;
     float* d_carry = nullptr;
     size_t carry_bytes = 0;
+    // cluster path: resident clusters per kernel instantiation (0 = not queried, -1 = unavailable)
+    float2* d_xslot = nullptr;
+    size_t xslot_bytes = 0;
     // arbitrary nfft (Bluestein): convolution length 2^logm, tables
     int logm = 0;
     float2* d_aw = nullptr;
@@ -308,7 +313,8 @@ extern "C" int psg_set_variant(const char* name) {
     std::lock_guard<std::mutex> lk(g_variant_mu);
     g_variant_override = name ? name : "";
     if (!g_variant_override.empty()) {
-        bool ok = g_variant_override == "split";
+        bool ok = g_variant_override == "split" || g_variant_override == "cluster" || g_variant_override == "cluster_ldg" ||
+                  g_variant_override == "cluster_dsmem";
         for (int i = 0; i < g_nvariants; ++i) ok = ok || g_variant_override == g_variants[i].name;
         if (!ok) {
             g_variant_override.clear();
@@ -497,6 +503,7 @@ extern "C" int psg_plan_destroy(psg_plan* p) {
     cudaFree(p->d_scratch);
     cudaFree(p->d_tmp);
     cudaFree(p->d_carry);
+    cudaFree(p->d_xslot);
     cudaFree(p->d_colb);
     cudaFree(p->d_aw);
     cudaFree(p->d_bbr);
@@ -689,6 +696,165 @@ static int upload_pass_tables(const Variant* v, float2** d_out) {
     return PSG_OK;
 }
 
+// tables shared by the two large-nfft paths (nfft = r0 * 4096): first-pass twiddles W_N^{n'*k0},
+// a window of ones and the pass tables of the 4096-point sub-transform
+static int ensure_split_tables(psg_plan* p, const Variant* v) {
+    constexpr int N2 = 4096;
+    const int N = p->nfft, r0 = N / N2;
+    if (p->d_twa) return PSG_OK;
+    std::vector<float2> t((size_t)(r0 - 1) * N2);
+    for (int k = 1; k < r0; ++k)
+        for (int n = 0; n < N2; ++n) {
+            const double ang = -2.0 * M_PI * (double)((long long)n * k) / (double)N;
+            t[(size_t)(k - 1) * N2 + n] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+    std::vector<float> ones(N2, 1.0f);
+    CUDA_TRY(cudaMalloc(&p->d_twa, sizeof(float2) * t.size()));
+    CUDA_TRY(cudaMemcpy(p->d_twa, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&p->d_ones, sizeof(float) * N2));
+    CUDA_TRY(cudaMemcpy(p->d_ones, ones.data(), sizeof(float) * N2, cudaMemcpyHostToDevice));
+    return upload_pass_tables(v, &p->d_twp_sub);
+}
+
+// ---- cluster path (sti_cluster.cuh): nfft = r0 * 4096 in one kernel, r0 CTAs per frame ----------
+template <int R0, int ROWTMA>
+static const void* cluster_fn_iq(int iqt) {
+    return iqt == IQ_CI16 ? (const void*)sti_cluster_kernel<R0, IQ_CI16, ROWTMA>
+           : iqt == IQ_CI8 ? (const void*)sti_cluster_kernel<R0, IQ_CI8, ROWTMA>
+                           : (const void*)sti_cluster_kernel<R0, IQ_C64, ROWTMA>;
+}
+template <int ROWTMA>
+static const void* cluster_fn_r0(int r0, int iqt) {
+    switch (r0) {
+        case 2: return cluster_fn_iq<2, ROWTMA>(iqt);
+        case 4: return cluster_fn_iq<4, ROWTMA>(iqt);
+        case 8: return cluster_fn_iq<8, ROWTMA>(iqt);
+        case 16: return cluster_fn_iq<16, ROWTMA>(iqt);
+    }
+    return nullptr;
+}
+template <int R0>
+static const void* dsmem_fn_iq(int iqt) {
+    return iqt == IQ_CI16 ? (const void*)sti_dsmem_kernel<R0, IQ_CI16>
+           : iqt == IQ_CI8 ? (const void*)sti_dsmem_kernel<R0, IQ_CI8>
+                           : (const void*)sti_dsmem_kernel<R0, IQ_C64>;
+}
+static const void* dsmem_fn_r0(int r0, int iqt) {
+    switch (r0) {
+        case 2: return dsmem_fn_iq<2>(iqt);
+        case 4: return dsmem_fn_iq<4>(iqt);
+        case 8: return dsmem_fn_iq<8>(iqt);
+        case 16: return dsmem_fn_iq<16>(iqt);
+    }
+    return nullptr;
+}
+static size_t dsmem_smem(int r0, int iqt) {
+    const size_t iqb = iqt == IQ_C64 ? 8 : iqt == IQ_CI16 ? 4 : 2;
+    const size_t seg = (size_t)(4096 / r0) * iqb + 16;
+    return 192 + (size_t)r0 * seg + 2 * (size_t)(psg_pad(4096) + 2) * 8;
+}
+static size_t cluster_smem(int r0, int iqt) {
+    const size_t iqb = iqt == IQ_C64 ? 8 : iqt == IQ_CI16 ? 4 : 2;
+    const size_t seg = (size_t)(4096 / r0) * iqb + 16;
+    return 128 + 4 * 256 * 8 + 2 * (size_t)r0 * seg + (size_t)(psg_pad(4096) + 2) * 8;
+}
+
+// returns PSG_OK with *ran = false when the device cannot co-schedule the cluster (caller falls back)
+static int run_cluster(psg_plan* p, const StiArgs& a, int ncs, int frames_per_col, int rowtma, cudaStream_t st, bool* ran) {
+    constexpr int N2 = 4096;
+    const int N = p->nfft, r0 = N / N2;
+    *ran = false;
+    const Variant* v = variant_by_name(g_default_tma[12 - 5]);
+    if (!v || v->twp != 2) return fail(PSG_ERR_UNSUPPORTED, "cluster path needs the power-layout 4096-point tables");
+    // rowtma: 0 = exchange through L2, rows loaded to registers; 1 = L2, rows by bulk copy; 2 = DSMEM
+    const void* fn = rowtma == 2 ? dsmem_fn_r0(r0, a.iq_type) : rowtma ? cluster_fn_r0<1>(r0, a.iq_type) : cluster_fn_r0<0>(r0, a.iq_type);
+    if (!fn) return fail(PSG_ERR_UNSUPPORTED, "cluster path: r0=%d", r0);
+    const size_t smem = rowtma == 2 ? dsmem_smem(r0, a.iq_type) : cluster_smem(r0, a.iq_type);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)r0;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // occupancy depends on the element type only through the stage size; query per call signature once
+    static thread_local const void* q_fn = nullptr;
+    static thread_local int q_dev = -1, q_slots = 0;
+    if (q_fn != fn || q_dev != p->device) {
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (r0 > 8) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cfg.gridDim = dim3((unsigned)(r0 * p->sms * 2));
+        int nmax = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&nmax, fn, &cfg);
+        if (e != cudaSuccess) { cudaGetLastError(); nmax = 0; }
+        q_fn = fn;
+        q_dev = p->device;
+        q_slots = nmax;
+    }
+    if (q_slots < 1) return PSG_OK;  // not schedulable here: caller uses the split path
+    int rc = ensure_split_tables(p, v);
+    if (rc) return rc;
+    // items: whole columns when there are enough of them, else columns split into frame chunks
+    // (>= 4 frames each: the pipeline is two frames deep; <= 1024 frames per fp32 accumulator)
+    const long long want = 16ll * q_slots;
+    int nsplit = 1;
+    if (ncs < want) nsplit = (int)std::min<long long>((want + ncs - 1) / ncs, std::max(1, frames_per_col / 4));
+    nsplit = std::max(nsplit, (frames_per_col + 1023) / 1024);
+    const int chunk = (frames_per_col + nsplit - 1) / nsplit;
+    nsplit = (frames_per_col + chunk - 1) / chunk;
+    const long long nitems = (long long)ncs * nsplit;
+    const int nclusters = (int)std::min<long long>(q_slots, nitems);
+    if (rowtma != 2) {
+        rc = ensure_buffer((void**)&p->d_xslot, &p->xslot_bytes, (size_t)q_slots * 3 * N * 8);
+        if (rc) return rc;
+    }
+    rc = ensure_buffer((void**)&p->d_tmp, &p->tmp_bytes, (size_t)nitems * N * 4);
+    if (rc) return rc;
+    ClusterArgs ca;
+    ca.iq = a.iq;
+    ca.sub_stride = a.sub_stride;
+    ca.hop_elems = a.hop_elems;
+    ca.col_off = a.col_off;
+    ca.ncol = a.ncol;
+    ca.ncs = ncs;
+    ca.nfr = frames_per_col;
+    ca.chunk = chunk;
+    ca.nsplit = nsplit;
+    ca.nclusters = nclusters;
+    ca.win = p->d_win;
+    ca.twa = p->d_twa;
+    ca.twp = p->d_twp_sub;
+    ca.scratch = p->d_xslot;
+    ca.tmp = p->d_tmp;
+    cfg.gridDim = dim3((unsigned)(nclusters * r0));
+    if (getenv("PSG_DEBUG"))
+        fprintf(stderr, "[psg] cluster path r0=%d resident clusters=%d items=%lld (nsplit=%d, chunk=%d) smem=%zu\n", r0, q_slots,
+                nitems, nsplit, chunk, smem);
+    void* args[] = {(void*)&ca};
+    CUDA_TRY(cudaLaunchKernelExC(&cfg, fn, args));
+    g_launches++;
+    ClusterFinArgs fa;
+    fa.tmp = p->d_tmp;
+    fa.r0 = r0;
+    fa.nsplit = nsplit;
+    fa.scale = a.scale;
+    fa.eps = a.eps;
+    fa.out_lin = a.out_lin;
+    fa.out_db = a.out_db;
+    sti_cluster_finalize_kernel<<<dim3(N2 / 128, (unsigned)ncs), 256, 0, st>>>(fa);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    snprintf(p->variant_name, sizeof(p->variant_name), "cluster%dx4096%s%s", r0, rowtma == 2 ? "_dsmem" : rowtma ? "_tma" : "_ldg",
+             a.iq_type == IQ_CI16 ? "_i16" : a.iq_type == IQ_CI8 ? "_i8" : "");
+    *ran = true;
+    return PSG_OK;
+}
+
 // nfft = r0 * 4096 (r0 = 2..16): streaming first pass -> L2-resident scratch -> tuned 4096-point
 // fused kernel over the r0 sub-sequences -> interleave.  See sti_kernels.cuh.
 static int run_split(psg_plan* p, StiArgs a, int ncs, int frames_per_col, cudaStream_t st) {
@@ -696,20 +862,9 @@ static int run_split(psg_plan* p, StiArgs a, int ncs, int frames_per_col, cudaSt
     const int N = p->nfft, r0 = N / N2;
     const Variant* v = variant_by_name(g_default_tma[12 - 5]);
     if (!v) return fail(PSG_ERR_UNSUPPORTED, "no 4096-point variant for the split path");
-    if (!p->d_twa) {
-        std::vector<float2> t((size_t)(r0 - 1) * N2);
-        for (int k = 1; k < r0; ++k)
-            for (int n = 0; n < N2; ++n) {
-                const double ang = -2.0 * M_PI * (double)((long long)n * k) / (double)N;
-                t[(size_t)(k - 1) * N2 + n] = make_float2((float)cos(ang), (float)sin(ang));
-            }
-        std::vector<float> ones(N2, 1.0f);
-        CUDA_TRY(cudaMalloc(&p->d_twa, sizeof(float2) * t.size()));
-        CUDA_TRY(cudaMemcpy(p->d_twa, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMalloc(&p->d_ones, sizeof(float) * N2));
-        CUDA_TRY(cudaMemcpy(p->d_ones, ones.data(), sizeof(float) * N2, cudaMemcpyHostToDevice));
-        int rc = upload_pass_tables(v, &p->d_twp_sub);
-        if (rc) return rc;
+    {
+        int rct = ensure_split_tables(p, v);
+        if (rct) return rct;
     }
     snprintf(p->variant_name, sizeof(p->variant_name), "split%dx4096+%s", r0, v->name);
     // chunking: whole columns per chunk when a column's frames fit the scratch, else one column at a
@@ -936,12 +1091,28 @@ extern "C" int psg_sti_run_typed(psg_plan* p, const void* iq_dev, int iq_type, i
     const Variant* v = nullptr;
     if (!g_force_generic.load()) {
         v = pick_variant(p->logn, tma_ok, iq_type);
-        bool force_split = false;
+        bool force_split = false, force_cluster = false;
+        // Measured defaults (profiles/r01_big_nfft_cluster_vs_split.txt, 4 and 12 GB): the cluster kernel with
+        // the exchange in L2 and rows loaded to registers wins at 16384 (31 % vs 26 % of the HBM peak) and
+        // 32768 (29 % vs 27 %); at 65536 the 16-CTA clusters fill only 112 of the 148 SMs and the
+        // three-launch split path stays ahead (27 % vs 25 %).
+        int rowtma = g_cluster_rowtma.load();
         {
             std::lock_guard<std::mutex> lk(g_variant_mu);
             force_split = g_variant_override == "split";
+            force_cluster = g_variant_override == "cluster" || g_variant_override == "cluster_ldg" || g_variant_override == "cluster_dsmem";
+            if (g_variant_override == "cluster") rowtma = 1;
+            if (g_variant_override == "cluster_ldg") rowtma = 0;
+            if (g_variant_override == "cluster_dsmem") rowtma = 2;
         }
-        if (p->logn >= 13 && p->logn <= 16 && (force_split || !v)) return run_split(p, a, ncs, frames_per_col, st);
+        const bool cluster_default = !v && (p->logn == 14 || p->logn == 15);
+        if (p->logn >= 13 && p->logn <= 16 && tma_ok && !force_split && (force_cluster || cluster_default)) {
+            // one kernel, r0 CTAs per frame (sti_cluster.cuh); contiguous, 16-byte aligned recordings
+            bool ran = false;
+            const int rcc = run_cluster(p, a, ncs, frames_per_col, rowtma, st, &ran);
+            if (rcc || ran) return rcc;
+        }
+        if (p->logn >= 13 && p->logn <= 16 && (force_split || force_cluster || !v)) return run_split(p, a, ncs, frames_per_col, st);
     }
 
     if (v) {

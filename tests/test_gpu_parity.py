@@ -241,12 +241,91 @@ def test_split_path_chunking(torch, nfft, nfr, ncol, scratch_mb):
                     ref_lin=ref.T, what=f"split {nfft} dB")
 
 
-@pytest.mark.parametrize("nfft", [256, 512, 1024, 2048, 4096, 8192, 16384, 65536])
+@pytest.mark.parametrize("nfft,nfr,ncol,nsub,kind", [
+    (16384, 1, 9, 1, "c64"),      # Mode R: every frame is a finished item
+    (16384, 5, 7, 2, "c64"),      # two sub-channels, odd starts (TMA skew)
+    (16384, 640, 2, 1, "c64"),    # two long columns: split into frame chunks, fp64 sum of the splits
+    (32768, 4, 5, 1, "c64"),
+    (65536, 3, 5, 1, "c64"),
+    (65536, 1, 40, 1, "c64"),     # more items than resident clusters: several items per cluster
+    (65536, 33, 1, 1, "c64"),     # one column, ragged last chunk
+    (8192, 6, 5, 1, "c64"),       # cluster of two
+    (16384, 4, 6, 1, "i16"),
+    (65536, 2, 3, 1, "i8"),
+    (32768, 3, 4, 1, "ldg"),
+    (65536, 9, 4, 1, "ldg"),      # rows loaded straight to registers instead of by bulk copy
+    (8192, 6, 5, 1, "dsmem"),     # exchange through distributed shared memory (st.async)
+    (16384, 1, 9, 1, "dsmem"),
+    (16384, 5, 7, 2, "dsmem"),
+    (16384, 640, 2, 1, "dsmem"),
+    (32768, 4, 5, 1, "dsmem"),
+    (65536, 3, 5, 1, "dsmem"),
+    (65536, 1, 40, 1, "dsmem"),
+    (65536, 33, 1, 1, "dsmem"),
+    (16384, 4, 6, 1, "dsmem_i16"),
+    (65536, 2, 3, 1, "dsmem_i8")])
+def test_cluster_path(torch, nfft, nfr, ncol, nsub, kind):
+    """Large-nfft cluster kernel (r0 = nfft/4096 CTAs per frame, exchange through L2, one cluster
+    barrier per frame) against the float64 oracle: modes, sub-channels, skewed frame starts, item
+    scheduling (fewer / more items than clusters, split columns) and raw integer ingest."""
+    from pyspectrogram_b200 import engine
+    rng = np.random.default_rng(nfft // 1024 + nfr + ncol)
+    per_sub = nfft * nfr * ncol + 2 * nfft + 8
+    per_sub += (-per_sub) % 8  # sub-channels start 16-byte aligned whatever the sample type
+    x = _recording(rng, per_sub * nsub)
+    starts = (np.arange(ncol) * nfft * nfr + np.arange(ncol) % 3).astype(np.int64)
+    in_scale, feed = 1.0, x
+    if kind.endswith(("i16", "i8")):
+        amp, dt = (20000.0, np.int16) if kind.endswith("i16") else (100.0, np.int8)
+        feed = np.stack([np.round(x.real * amp * 8), np.round(x.imag * amp * 8)], axis=1).astype(dt)
+        in_scale = 1.0 / (amp * 8)
+        x = ((feed[:, 0].astype(np.float32) + 1j * feed[:, 1].astype(np.float32)) * np.float32(in_scale)).astype(np.complex64)
+    plan = engine.StiPlan(nfft)
+    try:
+        engine.set_variant("cluster_ldg" if kind == "ldg" else "cluster_dsmem" if kind.startswith("dsmem") else "cluster")  # "cluster": rows by bulk copy
+        lin, db = plan.run(torch.from_numpy(feed).cuda(), torch.from_numpy(starts).cuda(), nfr, nfft, sub_stride=per_sub,
+                           nsub=nsub, in_scale=in_scale, want_lin=True, want_db=True)
+        torch.cuda.synchronize()
+        assert plan.variant.startswith(f"cluster{nfft // 4096}x4096"), plan.variant
+    finally:
+        engine.set_variant(None)
+    for s in range(nsub):
+        ref = _oracle_columns(x[s * per_sub:], starts, nfft, nfr, nfft)
+        assert_psd_close(lin.cpu().numpy()[s].T, ref.T, noise_like=False, what=f"cluster {nfft} sub {s}")
+        assert_db_close(db.cpu().numpy()[s].T, 10 * np.log10(ref.T.astype(np.float32) + np.float32(1e-15)),
+                        ref_lin=ref.T, what=f"cluster {nfft} dB")
+
+
+def test_large_nfft_defaults_and_fallback(torch):
+    """16384 / 32768 run the cluster kernel, 65536 the split path (measured defaults); a recording
+    whose base is not 16-byte aligned cannot use bulk copies and takes the split path at every size."""
+    from pyspectrogram_b200 import engine
+    for nfft, want in ((16384, "cluster4x4096_ldg"), (32768, "cluster8x4096_ldg"), (65536, "split16x4096")):
+        x = torch.from_numpy(_recording(np.random.default_rng(nfft), nfft * 9)).cuda()
+        starts = torch.from_numpy(np.arange(4, dtype=np.int64) * 2 * nfft).cuda()
+        plan = engine.StiPlan(nfft)
+        lin, _ = plan.run(x, starts, 2, nfft)
+        torch.cuda.synchronize()
+        assert plan.variant.startswith(want), plan.variant
+        ref = _oracle_columns(x.cpu().numpy(), starts.cpu().numpy(), nfft, 2, nfft)
+        assert_psd_close(lin.cpu().numpy()[0].T, ref.T, noise_like=False, what=f"default {nfft}")
+        lin2, _ = plan.run(x.view(torch.float32)[2:].view(torch.complex64), starts, 2, nfft)
+        torch.cuda.synchronize()
+        assert plan.variant.startswith("split"), plan.variant
+        ref = _oracle_columns(x.cpu().numpy()[1:], starts.cpu().numpy(), nfft, 2, nfft)
+        assert_psd_close(lin2.cpu().numpy()[0].T, ref.T, noise_like=False, what=f"split fallback {nfft}")
+
+
+@pytest.mark.parametrize("nfft", [256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536, (16384, "cluster"), (32768, "cluster_dsmem"),
+                                  (65536, "cluster_ldg"), (65536, "cluster_dsmem")])
 def test_repeated_runs_are_bit_identical(torch, nfft):
     """Race canary (compute-sanitizer is not available on the GPU pool): the kernels have no
     atomics and sum in a fixed order, so 12 back-to-back runs on two streams must agree bit for
     bit; a missing barrier in an exchange shows up as run-to-run differences."""
     from pyspectrogram_b200 import engine
+    variant = None
+    if isinstance(nfft, tuple):
+        nfft, variant = nfft
     rng = np.random.default_rng(nfft)
     nfr = 37 if nfft <= 4096 else 9
     ncol = 301 if nfft <= 4096 else 24
@@ -257,14 +336,18 @@ def test_repeated_runs_are_bit_identical(torch, nfft):
     ref = None
     streams = [torch.cuda.Stream(), torch.cuda.Stream()]
     torch.cuda.synchronize()
-    for i in range(12):
-        with torch.cuda.stream(streams[i % 2]):
-            lin, db = plan.run(x, starts, nfr, nfft, want_lin=True, want_db=True)
-        torch.cuda.synchronize()
-        if ref is None:
-            ref = (lin.clone(), db.clone())
-        else:
-            assert torch.equal(lin, ref[0]) and torch.equal(db, ref[1]), (nfft, i, plan.variant)
+    try:
+        engine.set_variant(variant)
+        for i in range(12):
+            with torch.cuda.stream(streams[i % 2]):
+                lin, db = plan.run(x, starts, nfr, nfft, want_lin=True, want_db=True)
+            torch.cuda.synchronize()
+            if ref is None:
+                ref = (lin.clone(), db.clone())
+            else:
+                assert torch.equal(lin, ref[0]) and torch.equal(db, ref[1]), (nfft, i, plan.variant)
+    finally:
+        engine.set_variant(None)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -1,4 +1,5 @@
-(timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4)
-for i in 1 2; do timeout 300 python bench.py --no-cpu --no-raw --no-e2e --steps 20 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value']), d['ms_per_step'], d['roofline']['frac'], d['roofline']['kernel_ms'], d['gpu_launches'])"; done
-timeout 600 python tools/default_sweep.py --gb 4 2>&1 | tail -12
+(timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -6) > gpurun_out/pytest_gpu.log 2>&1
+cat gpurun_out/pytest_gpu.log
+timeout 300 python tools/big_nfft_probe.py --gb 4 --variants cluster_ldg,cluster,cluster_dsmem,split,default > gpurun_out/big_nfft_probe_4gb.log 2>&1
+timeout 300 python tools/big_nfft_probe.py --gb 12 --variants cluster_ldg,cluster,cluster_dsmem,split,default > gpurun_out/big_nfft_probe_12gb.log 2>&1
+cat gpurun_out/big_nfft_probe_4gb.log gpurun_out/big_nfft_probe_12gb.log | cut -c1-110
