@@ -135,6 +135,26 @@ int psg_median_time(psg_plan* plan, const float* img_dev, int nsub, int ncol, in
                     float eps, float* med_lin_dev, float* med_db_dev, void* cuda_stream);
 
 /*
+ * Viewer-side reductions on the finished image, so that only what is
+ * drawn crosses PCIe:
+ *   psg_minmax_time   minimum and maximum over the time axis per (sub-channel, bin) -- the "min" and
+ *                     "max" spectra proc_data's docstring promises next to the median
+ *                     (drfProc.py:430-433; np.min / np.max semantics, NaN propagates).  Any output may
+ *                     be NULL (not all four).
+ *   psg_gather_bins   out[r][j] = clamp(img[r][idx[j]], clamp_lo, clamp_hi) for the rows = nsub*ncol
+ *                     rows of an image (or rows = nsub for a median vector): idx is the viewer's
+ *                     plotindices list -- frequency-range selection and decimation to at most 2^15
+ *                     points (drfview.py:1005-1023) -- and the clamp is the colour-range clip of the
+ *                     PNG export (drfview.py:1515-1518); clamp_lo > clamp_hi disables it.
+ */
+int psg_minmax_time(psg_plan* plan, const float* img_dev, int nsub, int ncol, int nfft, float eps,
+                    float* min_lin_dev, float* max_lin_dev, float* min_db_dev, float* max_db_dev,
+                    void* cuda_stream);
+int psg_gather_bins(psg_plan* plan, const float* img_dev, int64_t rows, int nfft,
+                    const int32_t* idx_dev, int count, float clamp_lo, float clamp_hi,
+                    float* out_dev, void* cuda_stream);
+
+/*
  * Host-buffer entry point (what drfProc.sti_proc_data / proc_data call): takes the IQ array in
  * host memory, streams it to the device in column chunks overlapped with the kernels
  * (two CUDA streams, double-buffered staging), runs psg_sti_run + psg_median_time and copies the

@@ -125,3 +125,33 @@ def read_sti_from_array(recording, st_sample, en_sample, nfft, nint, ntime,
         chunk = recording[lo:lo + span] / ref
         pieces.append(chunk[:, np.newaxis])
     return starts, np.concatenate(pieces, axis=1)
+
+
+def plot_indices(freqs, cfrange_khz, max_nfreqs=2 ** 15):
+    """The viewer's frequency selection and decimation (drfview.py:1005-1023), statement by statement.
+
+    ``freqs``: the fftshifted frequency axis in Hz; ``cfrange_khz``: (low, high) in kHz.
+    Returns ``(plotindices, plotfreqs, fscale)``.
+    """
+    keepvals = np.all((np.greater_equal(freqs, 1e3 * cfrange_khz[0]), np.less_equal(freqs, 1e3 * cfrange_khz[1])), axis=0)
+    kept = freqs[keepvals]
+    inds = np.argwhere(keepvals)
+    fscale = int(np.ceil(len(kept) / max_nfreqs))
+    relplotindices = range(int(np.floor(fscale / 2)), len(kept), fscale)
+    plotindices = [inds[i][0] for i in relplotindices]
+    plotfreqs = np.array([kept[i] for i in relplotindices])
+    return plotindices, plotfreqs, fscale
+
+
+def clip_to_colour_range(spectra, colorrange):
+    """Colour-range clip of the PNG export (drfview.py:1515-1516), on a copy."""
+    spectra = np.array(spectra, copy=True)
+    spectra[spectra < colorrange[0]] = colorrange[0]
+    spectra[spectra > colorrange[1]] = colorrange[1]
+    return spectra
+
+
+def proc_data_min_max(sxx_int):
+    """The minimum and maximum across time that proc_data's docstring lists after the median
+    (drfProc.py:430-433; the shipped function stops at the median, drfProc.py:451-453)."""
+    return np.min(sxx_int, axis=-1), np.max(sxx_int, axis=-1)

@@ -56,6 +56,8 @@ _SIGS = {
     "psg_sti_host_typed": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int, _P, C.c_int, C.c_int,
                                      C.c_int64, C.c_float, C.c_float, _P, _P, _P, _P]),
     "psg_median_time": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P]),
+    "psg_minmax_time": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P, _P]),
+    "psg_gather_bins": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, C.c_int, C.c_float, C.c_float, _P, _P]),
     "psg_sti_host": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, _P, C.c_int, C.c_int,
                                C.c_int64, C.c_float, C.c_float, _P, _P, _P, _P]),
     "psg_set_force_generic": (C.c_int, [C.c_int]),

@@ -1225,6 +1225,37 @@ extern "C" int psg_median_time(psg_plan* p, const float* img_dev, int nsub, int 
     return PSG_OK;
 }
 
+extern "C" int psg_minmax_time(psg_plan* p, const float* img_dev, int nsub, int ncol, int nfft, float eps,
+                               float* min_lin_dev, float* max_lin_dev, float* min_db_dev, float* max_db_dev,
+                               void* cuda_stream) {
+    if (!p) return fail(PSG_ERR_ARG, "psg_minmax_time: plan is NULL");
+    if (!img_dev || (!min_lin_dev && !max_lin_dev && !min_db_dev && !max_db_dev))
+        return fail(PSG_ERR_ARG, "psg_minmax_time: NULL pointer");
+    if (nsub < 1 || ncol < 1 || nfft < 1) return fail(PSG_ERR_ARG, "psg_minmax_time: bad shape");
+    CUDA_TRY(cudaSetDevice(p->device));
+    const long long blocks = (long long)nsub * ((nfft + 31) / 32);
+    minmax_time_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(img_dev, nsub, ncol, nfft, eps, min_lin_dev,
+                                                                               max_lin_dev, min_db_dev, max_db_dev);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PSG_OK;
+}
+
+extern "C" int psg_gather_bins(psg_plan* p, const float* img_dev, int64_t rows, int nfft, const int32_t* idx_dev, int count,
+                               float clamp_lo, float clamp_hi, float* out_dev, void* cuda_stream) {
+    if (!p) return fail(PSG_ERR_ARG, "psg_gather_bins: plan is NULL");
+    if (!img_dev || !idx_dev || !out_dev) return fail(PSG_ERR_ARG, "psg_gather_bins: NULL pointer");
+    if (rows < 1 || nfft < 1 || count < 1) return fail(PSG_ERR_ARG, "psg_gather_bins: bad shape");
+    CUDA_TRY(cudaSetDevice(p->device));
+    const size_t total = (size_t)rows * (size_t)count;
+    const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)p->sms * 16);
+    gather_bins_kernel<<<blocks, 256, 0, (cudaStream_t)cuda_stream>>>(img_dev, (size_t)rows, nfft, idx_dev, count, clamp_lo,
+                                                                     clamp_hi, out_dev);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PSG_OK;
+}
+
 extern "C" int psg_sti_host(psg_plan* p, const void* iq_host, int64_t iq_host_elems, int64_t sample_stride,
                             int64_t sub_stride, int nsub, const int64_t* col_offset_host, int ncol,
                             int frames_per_col, int64_t hop, float in_scale, float eps, float* out_lin_host,

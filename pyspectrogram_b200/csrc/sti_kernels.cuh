@@ -734,6 +734,68 @@ __global__ void __launch_bounds__(256) median_time_kernel(const float* __restric
     }
 }
 
+// ---- viewer-side reductions on the finished image ----------------------
+// Minimum and maximum over the time axis, the two spectra proc_data's docstring promises next to the
+// median (drfProc.py:430-433).  img [nsub][ncol][nfft]; a CTA owns 32 adjacent bins x 8 column slices,
+// rows are read coalesced, slices meet in shared memory.  NaNs propagate like np.min / np.max.
+__global__ void __launch_bounds__(256) minmax_time_kernel(const float* __restrict__ img, int nsub, int ncol, int nfft,
+                                                          float eps, float* min_lin, float* max_lin, float* min_db,
+                                                          float* max_db) {
+    __shared__ float smin[8][32], smax[8][32];
+    const int b = threadIdx.x & 31, s = threadIdx.x >> 5;
+    const int blocks_per_sub = (nfft + 31) / 32;
+    const int sub = blockIdx.x / blocks_per_sub;
+    const int bin = (blockIdx.x - sub * blocks_per_sub) * 32 + b;
+    const bool live = bin < nfft;
+    const float* p = img + (size_t)sub * ncol * nfft + (live ? bin : nfft - 1);
+    float lo = INFINITY, hi = -INFINITY;
+    bool nan = false;
+    for (int c = s; c < ncol; c += 8) {
+        const float v = __ldg(p + (size_t)c * nfft);
+        nan |= (v != v);
+        lo = fminf(lo, v);
+        hi = fmaxf(hi, v);
+    }
+    if (nan) lo = hi = __int_as_float(0x7fc00000);
+    smin[s][b] = lo;
+    smax[s][b] = hi;
+    __syncthreads();
+    if (s == 0 && live) {
+#pragma unroll
+        for (int q = 1; q < 8; ++q) {
+            const float a = smin[q][b], c2 = smax[q][b];
+            if (a != a) lo = hi = a;
+            else if (lo == lo) { lo = fminf(lo, a); hi = fmaxf(hi, c2); }
+        }
+        const size_t o = (size_t)sub * nfft + bin;
+        if (min_lin) min_lin[o] = lo;
+        if (max_lin) max_lin[o] = hi;
+        if (min_db) min_db[o] = power_to_db(lo, eps);
+        if (max_db) max_db[o] = power_to_db(hi, eps);
+    }
+}
+
+// The bins the viewer actually draws: out[s][c][j] = clamp(img[s][c][idx[j]], lo, hi).  idx is the
+// viewer's plotindices list (frequency-range selection and decimation to at most 2^15 points,
+// drfview.py:1005-1023); the clamp is the colour-range clip of the PNG export (drfview.py:1515-1518;
+// lo > hi disables it).  Shrinks the device-to-host copy to what is plotted.
+__global__ void __launch_bounds__(256) gather_bins_kernel(const float* __restrict__ img, size_t rows, int nfft,
+                                                          const int* __restrict__ idx, int count, float lo, float hi,
+                                                          float* __restrict__ out) {
+    const bool clamp = lo <= hi;
+    const size_t total = rows * (size_t)count;
+    for (size_t gi = blockIdx.x * (size_t)blockDim.x + threadIdx.x; gi < total; gi += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = gi / count;
+        const int j = (int)(gi - r * count);
+        float v = __ldg(img + r * nfft + __ldg(idx + j));
+        if (clamp) {  // spectra[spectra < lo] = lo; spectra[spectra > hi] = hi  (NaN stays NaN)
+            if (v < lo) v = lo;
+            if (v > hi) v = hi;
+        }
+        out[gi] = v;
+    }
+}
+
 // ---- large nfft (N = R0 * 4096, R0 = 2..16): two phases through an L2-resident scratch -----------
 // A frame of N >= 16384 points does not fit the shared memory of one SM together with its
 // pipeline (65536 points are 512 KB).  The first radix-R0 pass therefore runs as its own streaming

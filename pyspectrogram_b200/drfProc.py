@@ -15,7 +15,10 @@ Reference anchors
 
 Extensions (keyword-only, defaults reproduce the reference): ``integrate=True`` averages all
 ``nint`` frames of each time bin (Mode A, the averaging ``read_sti`` reads the data for,
-drfProc.py:158); ``device=`` selects the GPU.
+drfProc.py:158); ``device=`` selects the GPU; ``proc_data(..., minmax=True)`` also returns the minimum
+and maximum spectra its docstring lists (drfProc.py:430-433).  ``plot_indices`` / ``sti_plot_data``
+ do the viewer's frequency selection, decimation and colour clip
+(drfview.py:1005-1023, :1515-1518) on the GPU so that only the drawn bins are copied back.
 """
 from __future__ import annotations
 
@@ -30,7 +33,7 @@ from . import engine
 from ._lib import PsgUnsupported
 
 __all__ = ["DrfInput", "DrfProcessor", "ThreadProcessorSignals", "get_ref", "proc_data", "sti_proc_data",
-           "sti_proc_data_db"]
+           "sti_proc_data_db", "plot_indices", "sti_plot_data"]
 
 _EPS = 1e-15  # drfProc.py:308
 
@@ -128,12 +131,14 @@ def sti_proc_data_db(d1, sr, nfft, *, integrate=False, device=0, eps=_EPS, ref=1
     return f, out["db"], out["med_db"]
 
 
-def proc_data(d1, sr, nfft, dt, *, device=0):
+def proc_data(d1, sr, nfft, dt, *, device=0, minmax=False):
     """``proc_data`` (drfProc.py:406-453): overlapped spectrogram averaged in groups of ``n_int``.
 
     Returns ``(t_out, f, sxx_int, sxx_med)``; scipy's default overlap ``nfft//8``
     (scipy:_spectral_py.py:1129), segment times ``(nfft/2 + j*hop)/fs``
     (scipy:_spectral_py.py:2324-2325), last group always dropped (drfProc.py:440-447).
+    ``minmax=True`` appends ``sxx_min, sxx_max`` (minimum / maximum across time, the two outputs
+    the reference's docstring lists, drfProc.py:430-433, and its body never computes).
     """
     nfft = int(nfft)
     arr, out_dtype = _as_c64(d1)
@@ -151,14 +156,86 @@ def proc_data(d1, sr, nfft, dt, *, device=0):
     f = _freq_axis(nfft, sr)
     t_out = t[n1][:-1]
     if ncol < 1:
-        return t_out, f, np.zeros((nfft, 0), out_dtype), np.full(nfft, np.nan, out_dtype)
+        empty = (t_out, f, np.zeros((nfft, 0), out_dtype), np.full(nfft, np.nan, out_dtype))
+        return empty + (np.full(nfft, np.nan, out_dtype),) * 2 if minmax else empty
     plan = engine.get_plan(nfft, device)
-    res = plan.host(arr, n1[:-1].astype(np.int64) * hop, n_int, hop, want=("lin", "med"))
-    sxx = res["lin"][0].T
-    med = res["med"][0]
+    offs = n1[:-1].astype(np.int64) * hop
+    if not minmax:
+        res = plan.host(arr, offs, n_int, hop, want=("lin", "med"))
+        sxx = res["lin"][0].T
+        outs = [res["med"][0]]
+    else:
+        import torch
+        dev = torch.device("cuda", device)
+        lin, _ = plan.run(torch.from_numpy(arr).to(dev), torch.from_numpy(offs).to(dev), n_int, hop)
+        med, _ = plan.median(lin)
+        mn, mx, _, _ = plan.minmax(lin)
+        sxx = lin[0].cpu().numpy().T
+        outs = [v[0].cpu().numpy() for v in (med, mn, mx)]
+    if out_dtype != np.float32:
+        sxx, outs = sxx.astype(out_dtype), [v.astype(out_dtype) for v in outs]
+    return (t_out, f, sxx, *outs)
+
+
+def plot_indices(freqs, cfrange_khz, max_nfreqs=2 ** 15):
+    """Bins the viewer draws (drfview.py:1005-1023): those with ``1e3*cfrange[0] <= f <= 1e3*cfrange[1]``,
+    decimated by ``fscale = ceil(n / max_nfreqs)`` starting at ``floor(fscale / 2)``.
+
+    Returns ``(plotindices int64 array, plotfreqs, fscale)`` -- the three values the viewer stores
+    (``stats["plotindices"]``, ``data["plotfreqs"]``, ``stats["fscale"]``).  An empty selection raises
+    ``ValueError`` exactly where the reference's ``range(..., step=0)`` does.
+    """
+    freqs = np.asarray(freqs)
+    kept = np.flatnonzero((freqs >= 1e3 * cfrange_khz[0]) & (freqs <= 1e3 * cfrange_khz[1]))
+    fscale = -(-len(kept) // int(max_nfreqs))
+    if fscale == 0:
+        raise ValueError("range() arg 3 must not be zero")  # drfview.py:1017 with no frequency in range
+    sel = kept[fscale // 2::fscale]
+    return sel.astype(np.int64), freqs[sel], int(fscale)
+
+
+def sti_plot_data(d1, sr, nfft, cfrange_khz, *, max_nfreqs=2 ** 15, crange=None, integrate=False, device=0, eps=_EPS,
+                  ref=1.0):
+    """What the viewer draws from one ``sti_proc_data`` call, reduced on the GPU before the copy back.
+
+    The viewer converts the STI and its median to dB (drfProc.py:308-310), keeps ``plotindices``
+    (drfview.py:1005-1023, indexing at :1289-1295) and, for the PNG export, clips to the colour range
+    (drfview.py:1515-1518).  Returns ``(plotfreqs, sxx_db[:, plotindices...], med_db[plotindices...])``
+    with the reference's orientation ``(nfreq, ntime[, nsub])`` / ``(nfreq[, nsub])``; ``crange=None``
+    leaves the values unclipped (the on-screen plot clips through ``vmin``/``vmax``).
+    """
+    import torch
+    nfft = int(nfft)
+    arr, out_dtype = _as_c64(d1)
+    shape = arr.shape
+    if len(shape) not in (2, 3):
+        raise ValueError("d1 must be (rows, ntime) or (rows, ntime, nsub)")
+    rows, ntime = int(shape[0]), int(shape[1])
+    nsub = int(shape[2]) if len(shape) == 3 else 1
+    if rows < nfft:
+        raise ValueError("window is longer than input signal")
+    f = _freq_axis(nfft, sr)
+    idx, plotfreqs, _ = plot_indices(f, cfrange_khz, max_nfreqs)
+    plan = engine.get_plan(nfft, device)
+    dev = torch.device("cuda", device)
+    nfr = rows // nfft if integrate else 1
+    span = nfr * nfft
+    # (rows, ntime, nsub) C-order: sample stride ntime*nsub, column offset c*nsub, sub-channel stride 1;
+    # only the rows the columns touch are uploaded
+    flat = arr[:span].reshape(-1)
+    offs = torch.from_numpy(np.arange(ntime, dtype=np.int64) * nsub).to(dev)
+    lin, db = plan.run(torch.from_numpy(flat).to(dev), offs, nfr, nfft, sample_stride=ntime * nsub, sub_stride=1, nsub=nsub,
+                       in_scale=1.0 / float(ref), eps=eps, want_lin=True, want_db=True)
+    _, med_db = plan.median(lin, eps=eps, want_lin=False, want_db=True)
+    sel_db = plan.gather_bins(db, idx, clamp=crange)
+    sel_med = plan.gather_bins(med_db, idx, clamp=crange)
+    sxx = np.moveaxis(sel_db.cpu().numpy(), (0, 1, 2), (2, 1, 0))  # [nsub][ntime][k] -> (k, ntime, nsub)
+    med = sel_med.cpu().numpy().T
+    if len(shape) == 2:
+        sxx, med = sxx[..., 0], med[..., 0]
     if out_dtype != np.float32:
         sxx, med = sxx.astype(out_dtype), med.astype(out_dtype)
-    return t_out, f, sxx, med
+    return plotfreqs, sxx, med
 
 
 def get_ref(prop_dict):

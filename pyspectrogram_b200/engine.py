@@ -140,6 +140,50 @@ class StiPlan:
                 C.c_void_p(db.data_ptr() if db is not None else None), C.c_void_p(stream)))
         return lin, db
 
+    def minmax(self, img, *, eps=DB_EPS, want_lin=True, want_db=False):
+        """Minimum and maximum over time of a ``[nsub][ncol][nfft]`` linear image (the "min" and "max"
+        spectra of proc_data's docstring, drfProc.py:430-433).  Returns ``(min_lin, max_lin, min_db, max_db)``."""
+        torch = _torch()
+        if not img.is_cuda or img.dtype != torch.float32 or not img.is_contiguous() or img.dim() != 3:
+            raise ValueError("img must be a contiguous CUDA float32 [nsub][ncol][nfft] tensor")
+        nsub, ncol, nfft = (int(v) for v in img.shape)
+        outs = [torch.empty((nsub, nfft), dtype=torch.float32, device=img.device) if w else None
+                for w in (want_lin, want_lin, want_db, want_db)]
+        stream = torch.cuda.current_stream(img.device).cuda_stream
+        with self._lock:
+            _lib.check(self._lib.psg_minmax_time(
+                self._h, C.c_void_p(img.data_ptr()), nsub, ncol, nfft, float(eps),
+                *[C.c_void_p(o.data_ptr() if o is not None else None) for o in outs], C.c_void_p(stream)))
+        return tuple(outs)
+
+    def gather_bins(self, img, indices, *, clamp=None):
+        """``img[..., indices]`` (the viewer's ``plotindices``, drfview.py:1005-1023) on the device, with the
+        optional colour-range clip of the PNG export (drfview.py:1515-1518).  ``img``: contiguous CUDA
+        float32 ``[..., nfft]``; ``indices``: int sequence / array / CUDA int32 tensor."""
+        torch = _torch()
+        if not img.is_cuda or img.dtype != torch.float32 or not img.is_contiguous() or img.dim() < 1:
+            raise ValueError("img must be a contiguous CUDA float32 tensor [..., nfft]")
+        nfft = int(img.shape[-1])
+        if not isinstance(indices, torch.Tensor):
+            ind = np.asarray(indices)
+            if ind.size and (ind.min() < -nfft or ind.max() >= nfft):
+                raise IndexError(f"index out of bounds for axis of size {nfft}")
+            indices = torch.from_numpy(np.ascontiguousarray(np.where(ind < 0, ind + nfft, ind).astype(np.int32))).to(img.device)
+        if indices.dtype != torch.int32 or not indices.is_contiguous() or indices.dim() != 1:
+            raise TypeError("indices must be a contiguous 1-D int32 tensor")
+        count = int(indices.numel())
+        rows = int(img.numel() // nfft)
+        out = torch.empty(tuple(img.shape[:-1]) + (count,), dtype=torch.float32, device=img.device)
+        if count == 0 or rows == 0:
+            return out
+        lo, hi = (1.0, 0.0) if clamp is None else (float(clamp[0]), float(clamp[1]))
+        stream = torch.cuda.current_stream(img.device).cuda_stream
+        with self._lock:
+            _lib.check(self._lib.psg_gather_bins(
+                self._h, C.c_void_p(img.data_ptr()), rows, nfft, C.c_void_p(indices.data_ptr()), count, lo, hi,
+                C.c_void_p(out.data_ptr()), C.c_void_p(stream)))
+        return out
+
     # ---- host path -------------------------------------------------------------------------
     def host(self, iq: np.ndarray, col_offsets, frames_per_col=1, hop=None, *, sample_stride=1, sub_stride=0,
              nsub=1, in_scale=1.0, eps=DB_EPS, want=("lin", "med")):

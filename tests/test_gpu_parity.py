@@ -739,3 +739,77 @@ def test_large_workload_properties(torch):
     assert float((db[0, :, nfft // 2 + k]).abs().max()) <= 2e-3  # unit tone + noise -> 0 dBFS
     lin2, _ = plan.run(iq, starts, nint, nfft, in_scale=0.25)
     assert float(((lin2 - lin * 0.0625).abs() / lin).max()) <= 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# viewer-side reductions on the device
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nsub,ncol,nfft", [(1, 1, 33), (2, 7, 100), (1, 100, 1024), (3, 1000, 256), (1, 9000, 64)])
+def test_minmax_over_time_is_exact(torch, nsub, ncol, nfft):
+    """np.min / np.max over the time axis of the same image, bit for bit (order statistics)."""
+    from pyspectrogram_b200 import engine
+    rng = np.random.default_rng(nsub * 1000 + ncol)
+    img = rng.random((nsub, ncol, nfft), dtype=np.float32) ** 8
+    plan = engine.StiPlan(max(nfft, 2))
+    mn, mx, mn_db, mx_db = plan.minmax(torch.from_numpy(img).cuda(), want_db=True)
+    assert np.array_equal(mn.cpu().numpy(), img.min(axis=1)) and np.array_equal(mx.cpu().numpy(), img.max(axis=1))
+    assert np.abs(mn_db.cpu().numpy() - 10 * np.log10(img.min(axis=1) + np.float32(1e-15))).max() <= 1e-3
+    assert np.abs(mx_db.cpu().numpy() - 10 * np.log10(img.max(axis=1) + np.float32(1e-15))).max() <= 1e-3
+    img[0, ncol // 2, 5] = np.nan  # np.min / np.max propagate NaN
+    mn, mx, _, _ = plan.minmax(torch.from_numpy(img).cuda())
+    assert np.array_equal(mn.cpu().numpy(), img.min(axis=1), equal_nan=True)
+    assert np.array_equal(mx.cpu().numpy(), img.max(axis=1), equal_nan=True)
+
+
+def test_proc_data_minmax_matches_reference_golden(dp):
+    """proc_data(minmax=True): the first four outputs are the reference's, min / max are np.min / np.max
+    of the reference's own STI within the PSD tolerance and exact on the returned STI."""
+    from oracle import ref_port
+    g = load("proc_1024")
+    t_out, f, sxx, med, mn, mx = dp.proc_data(g["x"], float(g["sr"]), int(g["nfft"]), float(g["dt"]), minmax=True)
+    assert np.array_equal(t_out, g["t_out"]) and np.array_equal(f, g["f"])
+    assert_psd_close(sxx, g["sxx"], noise_like=False, what="proc_1024 minmax sxx")
+    assert_psd_close(med, g["med"], noise_like=False, what="proc_1024 minmax median")
+    rmn, rmx = ref_port.proc_data_min_max(g["sxx"])
+    assert_psd_close(mn, rmn, noise_like=False, what="proc_1024 min")
+    assert_psd_close(mx, rmx, noise_like=False, what="proc_1024 max")
+    assert np.array_equal(mn, sxx.min(axis=-1)) and np.array_equal(mx, sxx.max(axis=-1))
+    assert mn.dtype == g["sxx"].dtype and mn.shape == (int(g["nfft"]),)
+
+
+@pytest.mark.parametrize("shape,count", [((3, 40, 1024), 100), ((1, 1, 65536), 32768), ((2, 2048), 7), ((5,), 5)])
+def test_gather_bins_and_clip_are_exact(torch, shape, count):
+    from oracle import ref_port
+    from pyspectrogram_b200 import engine
+    rng = np.random.default_rng(count)
+    img = (rng.standard_normal(shape) * 40 - 60).astype(np.float32)
+    idx = np.sort(rng.choice(shape[-1], count, replace=False))
+    plan = engine.StiPlan(64)
+    t = torch.from_numpy(img).cuda()
+    assert np.array_equal(plan.gather_bins(t, idx).cpu().numpy(), img[..., idx])
+    got = plan.gather_bins(t, idx, clamp=(-90.0, -30.0)).cpu().numpy()
+    assert np.array_equal(got, ref_port.clip_to_colour_range(img[..., idx], (-90.0, -30.0)))
+    assert np.array_equal(plan.gather_bins(t, [-1, 0]).cpu().numpy(), img[..., [-1, 0]])
+    with pytest.raises(IndexError):
+        plan.gather_bins(t, [shape[-1]])
+
+
+@pytest.mark.parametrize("nfft,cfrange,maxn", [(1024, (-400.0, 400.0), 2 ** 15), (65536, (-500.0, 500.0), 2 ** 15),
+                                              (65536, (-100.0, 250.0), 1000), (4096, (12.0, 13.0), 2 ** 15)])
+def test_sti_plot_data_matches_viewer_selection(dp, nfft, cfrange, maxn):
+    """The reduced arrays equal the full dB result indexed with the viewer's plotindices
+    (drfview.py:1005-1023) and clipped like the PNG export (drfview.py:1515-1518)."""
+    from oracle import ref_port
+    rng = np.random.default_rng(nfft)
+    ntime = 6
+    d1 = _recording(rng, nfft * ntime).reshape(nfft, ntime)
+    sr = 1.0e6
+    f, sdb, mdb = dp.sti_proc_data_db(d1, sr, nfft)
+    pidx, pfreqs, fscale = ref_port.plot_indices(f, cfrange, maxn)
+    idx, freqs, fs2 = dp.plot_indices(f, cfrange, maxn)
+    assert list(idx) == list(pidx) and np.array_equal(freqs, pfreqs) and fs2 == fscale and len(idx) <= maxn
+    pf, sxx, med = dp.sti_plot_data(d1, sr, nfft, cfrange, max_nfreqs=maxn)
+    assert np.array_equal(pf, pfreqs) and np.array_equal(sxx, sdb[pidx]) and np.array_equal(med, mdb[pidx])
+    pf, sxx, med = dp.sti_plot_data(d1, sr, nfft, cfrange, max_nfreqs=maxn, crange=(-100.0, -50.0))
+    assert np.array_equal(sxx, ref_port.clip_to_colour_range(sdb[pidx], (-100.0, -50.0)))
+    assert np.array_equal(med, ref_port.clip_to_colour_range(mdb[pidx], (-100.0, -50.0)))

@@ -205,3 +205,28 @@ def test_median_even_count_is_mean_of_middle_pair_in_float32():
     srt = np.sort(g["sxx"], axis=1)
     want = ((srt[:, 4, :] + srt[:, 5, :]) * np.float32(0.5)).astype(np.float32)
     np.testing.assert_array_equal(g["med"], want)
+
+
+@pytest.mark.parametrize("nfft,cfrange,maxn", [(1024, (-400.0, 400.0), 2 ** 15), (65536, (-500.0, 500.0), 2 ** 15),
+                                              (65536, (-100.0, 250.0), 1000), (4096, (12.0, 13.0), 2 ** 15),
+                                              (1000, (-1e9, 1e9), 7), (33, (0.0, 0.0), 4)])
+def test_plot_indices_host_logic_matches_viewer_restatement(nfft, cfrange, maxn):
+    """pyspectrogram_b200.drfProc.plot_indices (closed form) against the statement-by-statement
+    restatement of drfview.py:1005-1023; pure host logic, no GPU."""
+    from oracle import ref_port
+    from pyspectrogram_b200.drfProc import plot_indices
+    f = np.fft.fftshift(np.fft.fftfreq(nfft, 1 / 1.0e6))
+    pidx, pfreqs, fscale = ref_port.plot_indices(f, cfrange, maxn)
+    idx, freqs, fs2 = plot_indices(f, cfrange, maxn)
+    assert list(idx) == list(pidx) and np.array_equal(freqs, pfreqs) and fs2 == fscale
+    assert len(idx) <= maxn and idx.dtype == np.int64
+
+
+def test_plot_indices_empty_selection_raises_like_the_viewer():
+    from oracle import ref_port
+    from pyspectrogram_b200.drfProc import plot_indices
+    f = np.fft.fftshift(np.fft.fftfreq(64, 1 / 1.0e6))
+    with pytest.raises(ValueError):
+        ref_port.plot_indices(f, (900.0, 901.0))
+    with pytest.raises(ValueError):
+        plot_indices(f, (900.0, 901.0))
