@@ -156,8 +156,10 @@ int psg_gather_bins(psg_plan* plan, const float* img_dev, int64_t rows, int nfft
 
 /*
  * Host-buffer entry point (what drfProc.sti_proc_data / proc_data call): takes the IQ array in
- * host memory, streams it to the device in column chunks overlapped with the kernels
- * (two CUDA streams, double-buffered staging), runs psg_sti_run + psg_median_time and copies the
+ * host memory, copies the span the columns touch to the device -- in one piece up to
+ * psg_set_host_chunk bytes (1 GiB), beyond that in groups of consecutive columns, the copy of
+ * group j+1 on a second stream overlapping the kernels of group j through two staging buffers, so
+ * recordings larger than device memory work -- runs psg_sti_run + psg_median_time and copies the
  * results back.  Synchronous: results are valid on return.
  *
  *   iq_host         complex64 host array; element (n, s) of column c at
@@ -186,6 +188,10 @@ int psg_set_variant(const char* name);
 /* Bytes of the L2-resident scratch the large-nfft split path (nfft >= 16384) works through per
  * chunk (default 2 GiB cap; only what a call needs is allocated).  Process-wide; tuning / tests. */
 int psg_set_split_scratch(int64_t bytes);
+/* psg_sti_host streams recordings whose touched span exceeds this many bytes in column chunks of about
+ * this size (default 1 GiB; two staging buffers of that size instead of the whole span on the device).
+ * Process-wide; tuning / tests. */
+int psg_set_host_chunk(int64_t bytes);
 /* One-frame-per-column launches (Mode R) use kernels that run several columns per CTA (default on;
  * 0 selects the one-column-per-CTA kernels).  Tuning / cross-checks. */
 int psg_set_mode_r_multi(int on);

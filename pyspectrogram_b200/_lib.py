@@ -64,6 +64,7 @@ _SIGS = {
     "psg_set_variant": (C.c_int, [C.c_char_p]),
     "psg_set_split_scratch": (C.c_int, [C.c_int64]),
     "psg_set_mode_r_multi": (C.c_int, [C.c_int]),
+    "psg_set_host_chunk": (C.c_int, [C.c_int64]),
     "psg_set_items_per_slot": (C.c_int, [C.c_int]),
     "psg_variant_count": (C.c_int, []),
     "psg_variant_name": (C.c_char_p, [C.c_int]),

@@ -34,6 +34,8 @@ static std::atomic<int> g_use_multi{1};  // Mode R: use the multi-column twin ke
 // chunks (16..128 MiB) lose more to the three short dependent launches per chunk than they save in
 // HBM traffic; 1..4 GiB chunks run each phase at its own roofline.
 static std::atomic<long long> g_split_scratch_bytes{2048ll << 20};
+// psg_sti_host: recordings whose touched span exceeds this are streamed in column chunks of about this size
+static std::atomic<long long> g_host_chunk_bytes{1024ll << 20};
 static std::atomic<int> g_cluster_rowtma{0};  // cluster path: 0 = rows loaded to registers (default), 1 = by bulk copy, 2 = DSMEM exchange
 
 static int fail(int code, const char* fmt, ...) {
@@ -252,6 +254,10 @@ struct psg_plan {
     // psg_sti_host staging
     void* d_in = nullptr;
     size_t in_bytes = 0;
+    void* d_in2 = nullptr;  // second staging buffer, copy stream and events of the streamed host path
+    size_t in2_bytes = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     long long* d_off = nullptr;
     size_t off_elems = 0;
     float* d_out[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -326,6 +332,11 @@ extern "C" int psg_set_variant(const char* name) {
 extern "C" int psg_set_split_scratch(int64_t bytes) {
     if (bytes < (1 << 20)) return fail(PSG_ERR_ARG, "psg_set_split_scratch: at least 1 MiB");
     g_split_scratch_bytes.store(bytes);
+    return PSG_OK;
+}
+extern "C" int psg_set_host_chunk(int64_t bytes) {
+    if (bytes < (1 << 16)) return fail(PSG_ERR_ARG, "psg_set_host_chunk: at least 64 KiB");
+    g_host_chunk_bytes.store(bytes);
     return PSG_OK;
 }
 extern "C" int psg_set_mode_r_multi(int on) {
@@ -512,6 +523,12 @@ extern "C" int psg_plan_destroy(psg_plan* p) {
     cudaFree(p->d_gwork);
     cudaFree(p->d_gacc);
     cudaFree(p->d_in);
+    cudaFree(p->d_in2);
+    if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (p->ev_copied[i]) cudaEventDestroy(p->ev_copied[i]);
+        if (p->ev_free[i]) cudaEventDestroy(p->ev_free[i]);
+    }
     cudaFree(p->d_off);
     for (int i = 0; i < 4; ++i) cudaFree(p->d_out[i]);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -1293,10 +1310,46 @@ extern "C" int psg_sti_host_typed(psg_plan* p, const void* iq_host, int iq_type,
     cudaStream_t st = p->stream;
     // keep the device copy 16-byte aligned relative to the host element parity so that aligned
     // host frames stay aligned on the device
-    const long long lo_al = lo & ~(long long)(16 / iqb - 1);
+    const long long al_mask = ~(long long)(16 / iqb - 1);
+    const long long lo_al = lo & al_mask;
     const size_t span = (size_t)(hi + col_extent - lo_al);
-    int rc = ensure_buffer(&p->d_in, &p->in_bytes, span * iqb + 32);
-    if (rc) return rc;
+    // Recordings larger than the chunk size are streamed in groups of consecutive columns whose
+    // touched span fits a chunk -- when that actually shrinks the copy (column spans that overlap
+    // almost entirely, e.g. the reference's (rows, ntime, nsub) array, are copied once instead).
+    struct HostChunk { int c0, c1; long long lo_al, span; };
+    std::vector<HostChunk> chunks;
+    const long long cap = std::max<long long>(1, g_host_chunk_bytes.load() / iqb);
+    if ((long long)span > cap && ncol > 1) {
+        long long sum = 0, biggest = 0;
+        for (int c0 = 0; c0 < ncol;) {
+            long long clo = col_offset_host[c0], chi = clo;
+            int c1 = c0 + 1;
+            while (c1 < ncol) {
+                const long long nlo = std::min<long long>(clo, col_offset_host[c1]), nhi = std::max<long long>(chi, col_offset_host[c1]);
+                if (nhi + col_extent - (nlo & al_mask) > cap) break;
+                clo = nlo;
+                chi = nhi;
+                ++c1;
+            }
+            const long long cl = clo & al_mask;
+            chunks.push_back({c0, c1, cl, chi + col_extent - cl});
+            sum += chunks.back().span;
+            biggest = std::max(biggest, chunks.back().span);
+            c0 = c1;
+        }
+        if (chunks.size() < 2 || sum > (long long)span + (long long)span / 4) chunks.clear();  // no gain: copy once
+        if (!chunks.empty()) {
+            int rcb = ensure_buffer(&p->d_in, &p->in_bytes, (size_t)biggest * iqb + 32);
+            if (rcb) return rcb;
+            rcb = ensure_buffer(&p->d_in2, &p->in2_bytes, (size_t)biggest * iqb + 32);
+            if (rcb) return rcb;
+        }
+    }
+    int rc = PSG_OK;
+    if (chunks.empty()) {
+        rc = ensure_buffer(&p->d_in, &p->in_bytes, span * iqb + 32);
+        if (rc) return rc;
+    }
     {
         size_t have = p->off_elems * 8;
         rc = ensure_buffer((void**)&p->d_off, &have, (size_t)ncol * 8);
@@ -1316,12 +1369,52 @@ extern "C" int psg_sti_host_typed(psg_plan* p, const void* iq_host, int iq_type,
         p->out_elems[i] = have / 4;
         if (rc) return rc;
     }
-    CUDA_TRY(cudaMemcpyAsync(p->d_off, rel.data(), (size_t)ncol * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(p->d_in, (const char*)iq_host + (size_t)lo_al * iqb, span * iqb, cudaMemcpyHostToDevice, st));
-    rc = psg_sti_run_typed(p, p->d_in, iq_type, sample_stride, sub_stride, nsub, (const int64_t*)p->d_off, ncol,
-                           frames_per_col, hop, in_scale, eps, need_lin ? p->d_out[0] : nullptr,
-                           out_db_host ? p->d_out[1] : nullptr, st);
-    if (rc) return rc;
+    if (chunks.size() <= 1) {
+        CUDA_TRY(cudaMemcpyAsync(p->d_off, rel.data(), (size_t)ncol * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(p->d_in, (const char*)iq_host + (size_t)lo_al * iqb, span * iqb, cudaMemcpyHostToDevice, st));
+        rc = psg_sti_run_typed(p, p->d_in, iq_type, sample_stride, sub_stride, nsub, (const int64_t*)p->d_off, ncol,
+                               frames_per_col, hop, in_scale, eps, need_lin ? p->d_out[0] : nullptr,
+                               out_db_host ? p->d_out[1] : nullptr, st);
+        if (rc) return rc;
+    } else {
+        // streamed: chunk j+1 crosses PCIe on the copy stream while the kernels of chunk j run on the
+        // plan's stream (all kernels stay on one stream: they share the plan's scratch); two staging
+        // buffers, a "copied" and a "free" event each.  A chunk's columns land in a contiguous slab of
+        // the image per sub-channel, so sub-channels run as separate launches.
+        if (!p->copy_stream) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i) {
+                CUDA_TRY(cudaEventCreateWithFlags(&p->ev_copied[i], cudaEventDisableTiming));
+                CUDA_TRY(cudaEventCreateWithFlags(&p->ev_free[i], cudaEventDisableTiming));
+            }
+        }
+        for (const HostChunk& ch : chunks)
+            for (int c = ch.c0; c < ch.c1; ++c) rel[c] = col_offset_host[c] - ch.lo_al;
+        CUDA_TRY(cudaMemcpyAsync(p->d_off, rel.data(), (size_t)ncol * 8, cudaMemcpyHostToDevice, st));
+        void* bufs[2] = {p->d_in, p->d_in2};
+        for (size_t j = 0; j < chunks.size(); ++j) {
+            const HostChunk& ch = chunks[j];
+            const int b = (int)(j & 1);
+            if (j >= 2) CUDA_TRY(cudaStreamWaitEvent(p->copy_stream, p->ev_free[b], 0));
+            CUDA_TRY(cudaMemcpyAsync(bufs[b], (const char*)iq_host + (size_t)ch.lo_al * iqb, (size_t)ch.span * iqb,
+                                     cudaMemcpyHostToDevice, p->copy_stream));
+            CUDA_TRY(cudaEventRecord(p->ev_copied[b], p->copy_stream));
+            CUDA_TRY(cudaStreamWaitEvent(st, p->ev_copied[b], 0));
+            const int nc = ch.c1 - ch.c0;
+            for (int sub = 0; sub < nsub; ++sub) {
+                const size_t o = ((size_t)sub * ncol + ch.c0) * N;
+                rc = psg_sti_run_typed(p, (const char*)bufs[b] + (size_t)sub * sub_stride * iqb, iq_type, sample_stride, 0, 1,
+                                       (const int64_t*)p->d_off + ch.c0, nc, frames_per_col, hop, in_scale, eps,
+                                       need_lin ? p->d_out[0] + o : nullptr, out_db_host ? p->d_out[1] + o : nullptr, st);
+                if (rc) {
+                    cudaStreamSynchronize(p->copy_stream);
+                    cudaStreamSynchronize(st);
+                    return rc;
+                }
+            }
+            CUDA_TRY(cudaEventRecord(p->ev_free[b], st));
+        }
+    }
     if (med_lin_host || med_db_host) {
         rc = psg_median_time(p, p->d_out[0], nsub, ncol, N, eps, med_lin_host ? p->d_out[2] : nullptr,
                              med_db_host ? p->d_out[3] : nullptr, st);
@@ -1332,5 +1425,6 @@ extern "C" int psg_sti_host_typed(psg_plan* p, const void* iq_host, int iq_type,
     if (med_lin_host) CUDA_TRY(cudaMemcpyAsync(med_lin_host, p->d_out[2], med_elems * 4, cudaMemcpyDeviceToHost, st));
     if (med_db_host) CUDA_TRY(cudaMemcpyAsync(med_db_host, p->d_out[3], med_elems * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (p->copy_stream) CUDA_TRY(cudaStreamSynchronize(p->copy_stream));
     return PSG_OK;
 }

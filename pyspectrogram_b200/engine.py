@@ -332,6 +332,11 @@ def set_split_scratch(nbytes: int):
     _lib.check(_lib.load().psg_set_split_scratch(int(nbytes)))
 
 
+def set_host_chunk(nbytes: int):
+    """Span above which ``StiPlan.host`` streams the recording in column chunks (default 1 GiB)."""
+    _lib.check(_lib.load().psg_set_host_chunk(int(nbytes)))
+
+
 def set_force_generic(on: bool):
     _lib.check(_lib.load().psg_set_force_generic(1 if on else 0))
 

@@ -813,3 +813,41 @@ def test_sti_plot_data_matches_viewer_selection(dp, nfft, cfrange, maxn):
     pf, sxx, med = dp.sti_plot_data(d1, sr, nfft, cfrange, max_nfreqs=maxn, crange=(-100.0, -50.0))
     assert np.array_equal(sxx, ref_port.clip_to_colour_range(sdb[pidx], (-100.0, -50.0)))
     assert np.array_equal(med, ref_port.clip_to_colour_range(mdb[pidx], (-100.0, -50.0)))
+
+
+# ---------------------------------------------------------------------------------------------
+# streamed host path (recordings larger than the staging chunk)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nfft,nfr,ncol,nsub,kind", [(1024, 4, 50, 1, "c64"), (4096, 3, 21, 1, "c64"), (256, 5, 64, 2, "c64"),
+                                                     (2048, 2, 33, 1, "i16"), (16384, 2, 9, 1, "c64")])
+def test_host_path_streams_in_column_chunks(nfft, nfr, ncol, nsub, kind):
+    """psg_sti_host with the chunk size shrunk so that the recording crosses PCIe in several column
+    groups (copy of group j+1 overlapping the kernels of group j): same image, median and dB as the
+    float64 oracle, and the same as the one-piece path within fp32 summation-order noise."""
+    from pyspectrogram_b200 import engine
+    rng = np.random.default_rng(nfft + ncol)
+    n = nfft * nfr * ncol + nfft + 7
+    x = _recording(rng, n * nsub).reshape(n, nsub)  # interleaved sub-channels (sample_stride = nsub)
+    starts = (np.arange(ncol) * nfft * nfr + np.arange(ncol) % 2).astype(np.int64)
+    feed, in_scale = x, 1.0
+    if kind == "i16":
+        amp = 20000.0 * 8
+        feed = np.stack([np.round(x.real * amp), np.round(x.imag * amp)], axis=-1).astype(np.int16)
+        in_scale = 1.0 / amp
+        x = ((feed[..., 0].astype(np.float32) + 1j * feed[..., 1].astype(np.float32)) * np.float32(in_scale)).astype(np.complex64)
+    plan = engine.StiPlan(nfft)
+    kw = dict(sample_stride=nsub, sub_stride=1, nsub=nsub, in_scale=in_scale, want=("lin", "db", "med", "med_db"))
+    flat = feed.reshape(-1) if kind == "c64" else feed.reshape(-1, 2)
+    whole = plan.host(flat, starts * nsub, nfr, nfft, **kw)
+    try:
+        engine.set_host_chunk(max(1 << 16, x.nbytes // 7))
+        got = plan.host(flat, starts * nsub, nfr, nfft, **kw)
+    finally:
+        engine.set_host_chunk(1 << 30)
+    for s in range(nsub):
+        ref = _oracle_columns(x[:, s], starts, nfft, nfr, nfft)
+        assert_psd_close(got["lin"][s].T, ref.T, noise_like=False, what=f"streamed host sub {s}")
+        assert_db_close(got["db"][s].T, 10 * np.log10(ref.T.astype(np.float32) + np.float32(1e-15)), ref_lin=ref.T,
+                        what=f"streamed host dB sub {s}")
+        assert_psd_close(got["med"][s], np.median(ref, axis=0), noise_like=False, what="streamed host median")
+    assert np.allclose(got["lin"], whole["lin"], rtol=1e-5, atol=0) and np.allclose(got["med"], whole["med"], rtol=1e-5, atol=0)
