@@ -577,9 +577,16 @@ def test_resident_recording_cache_matches_per_bin_reads(dp, nsub, raw_ingest):
                 cache = proc._cache["ch0"]
                 assert cache.samples_read == cache.hi - cache.lo <= n
                 nreads = len(reader.reads)
+                from pyspectrogram_b200 import engine
+                launches = engine.launch_count()
                 again = proc.iterate_once(1)
                 assert len(reader.reads) == nreads and cache.samples_read == cache.hi - cache.lo
                 assert np.array_equal(again[2], outs[-1][2]) and np.array_equal(again[3], outs[-1][3])
+                # incremental recompute: same window, same settings -> no kernel launched at all
+                assert engine.launch_count() == launches and proc.recomputes_skipped == 1
+                proc.updatesettings_slot(256.0, 4.0, 50.0, proc.drfIn.time_bnds[0], proc.drfIn.time_bnds[1])
+                changed = proc.iterate_once(2)
+                assert changed[2].shape[0] == 256 and engine.launch_count() > launches and proc.recomputes_skipped == 1
         (t0, f0, s0, m0), (t1, f1, s1, m1) = outs
         assert np.array_equal(f0, f1) and np.array_equal(t0, t1)
         assert s1.shape == (512, 50, nsub) and m1.shape == (512, nsub)

@@ -1,4 +1,9 @@
-(timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "streams_in_column or host or golden" 2>&1 | tail -25) > gpurun_out/host_tests.log 2>&1
-cat gpurun_out/host_tests.log
-for i in 1 2; do timeout 300 python bench.py --no-cpu --steps 10 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value']), d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['e2e']['ms_per_step'], d['e2e_raw_int16']['value'])"; done
+(timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -6) > gpurun_out/pytest_gpu.log 2>&1
+cat gpurun_out/pytest_gpu.log
+timeout 600 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
+tail -c 600 gpurun_out/bench_final.json
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_final_ref.json 2>/dev/null
+timeout 600 python tools/default_sweep.py --gb 12 > gpurun_out/default_sweep_12gb_final.log 2>&1
+cat gpurun_out/default_sweep_12gb_final.log
+timeout 300 python bench.py --no-cpu --no-raw --no-e2e --steps 2 --warmup 3 > /dev/null 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_launches_bench_final.csv python bench.py --no-cpu --no-raw --no-e2e --steps 2 --warmup 3 > gpurun_out/ncu_launch.log 2>&1
