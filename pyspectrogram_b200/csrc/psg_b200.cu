@@ -19,6 +19,7 @@
 #include "../../include/psg_b200.h"
 #include "sti_kernels.cuh"
 #include "sti_cluster.cuh"
+#include "sti_whole.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -320,7 +321,8 @@ extern "C" int psg_set_variant(const char* name) {
     g_variant_override = name ? name : "";
     if (!g_variant_override.empty()) {
         bool ok = g_variant_override == "split" || g_variant_override == "cluster" || g_variant_override == "cluster_ldg" ||
-                  g_variant_override == "cluster_dsmem";
+                  g_variant_override == "cluster_dsmem" || g_variant_override == "whole" || g_variant_override == "whole_s2" ||
+                  g_variant_override == "whole_s8";
         for (int i = 0; i < g_nvariants; ++i) ok = ok || g_variant_override == g_variants[i].name;
         if (!ok) {
             g_variant_override.clear();
@@ -872,6 +874,84 @@ static int run_cluster(psg_plan* p, const StiArgs& a, int ncs, int frames_per_co
     return PSG_OK;
 }
 
+// ---- whole-frame path (sti_whole.cuh): nfft = 8192 / 16384 with the frame resident in one SM -----
+template <int R0, int NST>
+static const void* whole_fn_iq(int iqt) {
+    return iqt == IQ_CI16 ? (const void*)sti_whole_kernel<R0, IQ_CI16, NST>
+           : iqt == IQ_CI8 ? (const void*)sti_whole_kernel<R0, IQ_CI8, NST>
+                           : (const void*)sti_whole_kernel<R0, IQ_C64, NST>;
+}
+static size_t whole_smem(int r0, int iqt, int nst) {
+    const size_t iqb = iqt == IQ_C64 ? 8 : iqt == IQ_CI16 ? 4 : 2;
+    return 128 + (size_t)nst * r0 * (512 * iqb + 16) + (size_t)(psg_pad(r0 * 4096) + 2) * 8;
+}
+
+static int run_whole(psg_plan* p, const StiArgs& a0, int ncs, int frames_per_col, int nst, cudaStream_t st) {
+    constexpr int N2 = 4096;
+    const int N = p->nfft, r0 = N / N2;
+    const Variant* v = variant_by_name(g_default_tma[12 - 5]);
+    if (!v || v->twp != 2) return fail(PSG_ERR_UNSUPPORTED, "whole-frame path needs the power-layout 4096-point tables");
+    const void* fn = nullptr;
+    if (r0 == 4 && nst == 4) fn = whole_fn_iq<4, 4>(a0.iq_type);
+    else if (r0 == 4 && nst == 2) fn = whole_fn_iq<4, 2>(a0.iq_type);
+    else if (r0 == 2 && nst == 4) fn = whole_fn_iq<2, 4>(a0.iq_type);
+    else if (r0 == 2 && nst == 8) fn = whole_fn_iq<2, 8>(a0.iq_type);
+    if (!fn) return fail(PSG_ERR_UNSUPPORTED, "whole-frame path: nfft=%d stages=%d", N, nst);
+    const size_t smem = whole_smem(r0, a0.iq_type, nst);
+    static thread_local const void* q_fn = nullptr;
+    static thread_local int q_dev = -1;
+    if (q_fn != fn || q_dev != p->device) {
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        q_fn = fn;
+        q_dev = p->device;
+    }
+    int rc = ensure_split_tables(p, v);
+    if (rc) return rc;
+    // items: whole columns when they keep every SM busy for three rounds, else columns split into
+    // frame chunks (>= 8 frames each; <= 1024 frames per fp32 accumulator), summed in fp64 afterwards
+    const long long slots = p->sms;
+    int nsplit = 1;
+    if (ncs < 3 * slots) nsplit = (int)std::min<long long>((8 * slots + ncs - 1) / ncs, std::max(1, frames_per_col / 8));
+    nsplit = std::max(nsplit, (frames_per_col + 1023) / 1024);
+    const int chunk = (frames_per_col + nsplit - 1) / nsplit;
+    nsplit = (frames_per_col + chunk - 1) / chunk;
+    WholeArgs wa;
+    wa.s = a0;
+    wa.s.twp = p->d_twp_sub;
+    wa.s.gpc = 1;
+    wa.s.chunk = chunk;
+    wa.s.nsplit = nsplit;
+    wa.s.nfr = frames_per_col;
+    for (int q = 0; q < 2; ++q)
+        for (int m = 0; m < 8; ++m) {
+            const double ang = -2.0 * M_PI * (double)((512ll * m << q) % N) / (double)N;
+            wa.cm[q][m] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+    if (nsplit > 1) {
+        size_t have_b = p->partial_elems * sizeof(float);
+        rc = ensure_buffer((void**)&p->d_partial, &have_b, (size_t)ncs * nsplit * N * sizeof(float));
+        p->partial_elems = have_b / sizeof(float);
+        if (rc) return rc;
+        wa.s.partial = p->d_partial;
+    }
+    const long long grid = (long long)ncs * nsplit;
+    if (grid > 2147483647ll) return fail(PSG_ERR_ARG, "psg_sti_run: grid too large");
+    void* args[] = {(void*)&wa};
+    CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(512), args, smem, st));
+    g_launches++;
+    if (nsplit > 1) {
+        const size_t total = (size_t)ncs * N;
+        const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)p->sms * 16);
+        sti_finalize_kernel<<<blocks, 256, 0, st>>>(wa.s.partial, nsplit, N, (size_t)ncs, wa.s.scale, wa.s.eps, wa.s.out_lin,
+                                                    wa.s.out_db);
+        g_launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    snprintf(p->variant_name, sizeof(p->variant_name), "whole%dx4096_s%d%s", r0, nst,
+             a0.iq_type == IQ_CI16 ? "_i16" : a0.iq_type == IQ_CI8 ? "_i8" : "");
+    return PSG_OK;
+}
+
 // nfft = r0 * 4096 (r0 = 2..16): streaming first pass -> L2-resident scratch -> tuned 4096-point
 // fused kernel over the r0 sub-sequences -> interleave.  See sti_kernels.cuh.
 static int run_split(psg_plan* p, StiArgs a, int ncs, int frames_per_col, cudaStream_t st) {
@@ -1109,6 +1189,7 @@ extern "C" int psg_sti_run_typed(psg_plan* p, const void* iq_dev, int iq_type, i
     if (!g_force_generic.load()) {
         v = pick_variant(p->logn, tma_ok, iq_type);
         bool force_split = false, force_cluster = false;
+        int whole_nst = 0;  // whole-frame path forced with this many ring stages
         // Measured defaults (profiles/r01_big_nfft_cluster_vs_split.txt, 4 and 12 GB): the cluster kernel with
         // the exchange in L2 and rows loaded to registers wins at 16384 (31 % vs 26 % of the HBM peak) and
         // 32768 (29 % vs 27 %); at 65536 the 16-CTA clusters fill only 112 of the 148 SMs and the
@@ -1121,7 +1202,14 @@ extern "C" int psg_sti_run_typed(psg_plan* p, const void* iq_dev, int iq_type, i
             if (g_variant_override == "cluster") rowtma = 1;
             if (g_variant_override == "cluster_ldg") rowtma = 0;
             if (g_variant_override == "cluster_dsmem") rowtma = 2;
+            if (g_variant_override == "whole") whole_nst = 4;
+            if (g_variant_override == "whole_s2") whole_nst = 2;
+            if (g_variant_override == "whole_s8") whole_nst = 8;
         }
+        // 16384 points: the whole frame in one SM (sti_whole.cuh) is the measured default (39 % of the HBM peak
+        // against 30 % for the 4-CTA cluster kernel, profiles/r01_whole_frame_16384.txt)
+        if (p->logn == 14 && tma_ok && !v && !force_split && !force_cluster && !whole_nst) whole_nst = 4;
+        if ((p->logn == 13 || p->logn == 14) && tma_ok && whole_nst) return run_whole(p, a, ncs, frames_per_col, whole_nst, st);
         const bool cluster_default = !v && (p->logn == 14 || p->logn == 15);
         if (p->logn >= 13 && p->logn <= 16 && tma_ok && !force_split && (force_cluster || cluster_default)) {
             // one kernel, r0 CTAs per frame (sti_cluster.cuh); contiguous, 16-byte aligned recordings

@@ -296,11 +296,54 @@ def test_cluster_path(torch, nfft, nfr, ncol, nsub, kind):
                         ref_lin=ref.T, what=f"cluster {nfft} dB")
 
 
-def test_large_nfft_defaults_and_fallback(torch):
-    """16384 / 32768 run the cluster kernel, 65536 the split path (measured defaults); a recording
-    whose base is not 16-byte aligned cannot use bulk copies and takes the split path at every size."""
+@pytest.mark.parametrize("nfft,nfr,ncol,nsub,kind", [
+    (16384, 1, 9, 1, "whole"),       # Mode R: one frame per item
+    (16384, 5, 7, 2, "whole"),       # two sub-channels, odd starts (TMA skew)
+    (16384, 640, 2, 1, "whole"),     # two long columns: split into frame chunks, fp64 sum of the splits
+    (16384, 3, 500, 1, "whole"),     # more items than SMs (several waves)
+    (16384, 5, 7, 1, "whole_s2"),    # two-stage ring
+    (8192, 6, 5, 1, "whole"),        # radix-2 first pass
+    (8192, 6, 5, 1, "whole_s8"),
+    (16384, 4, 6, 1, "whole_i16"),
+    (16384, 2, 3, 1, "whole_i8")])
+def test_whole_frame_path(torch, nfft, nfr, ncol, nsub, kind):
+    """Whole-frame kernel (sti_whole.cuh: 8192 / 16384 points resident in one SM, first pass fed in
+    slabs through a bulk-copy ring refilled by the last reader) against the float64 oracle: modes,
+    sub-channels, skewed frame starts, split columns, several waves, raw integer ingest."""
     from pyspectrogram_b200 import engine
-    for nfft, want in ((16384, "cluster4x4096_ldg"), (32768, "cluster8x4096_ldg"), (65536, "split16x4096")):
+    rng = np.random.default_rng(nfft // 1024 + nfr + ncol)
+    per_sub = nfft * nfr * ncol + 2 * nfft + 8
+    per_sub += (-per_sub) % 8
+    x = _recording(rng, per_sub * nsub)
+    starts = (np.arange(ncol) * nfft * nfr + np.arange(ncol) % 3).astype(np.int64)
+    in_scale, feed = 1.0, x
+    if kind.endswith(("i16", "i8")):
+        amp, dt = (20000.0, np.int16) if kind.endswith("i16") else (100.0, np.int8)
+        feed = np.stack([np.round(x.real * amp * 8), np.round(x.imag * amp * 8)], axis=1).astype(dt)
+        in_scale = 1.0 / (amp * 8)
+        x = ((feed[:, 0].astype(np.float32) + 1j * feed[:, 1].astype(np.float32)) * np.float32(in_scale)).astype(np.complex64)
+    plan = engine.StiPlan(nfft)
+    try:
+        engine.set_variant(kind if kind in ("whole_s2", "whole_s8") else "whole")
+        lin, db = plan.run(torch.from_numpy(feed).cuda(), torch.from_numpy(starts).cuda(), nfr, nfft, sub_stride=per_sub,
+                           nsub=nsub, in_scale=in_scale, want_lin=True, want_db=True)
+        torch.cuda.synchronize()
+        assert plan.variant.startswith(f"whole{nfft // 4096}x4096"), plan.variant
+    finally:
+        engine.set_variant(None)
+    for s in range(nsub):
+        ref = _oracle_columns(x[s * per_sub:], starts, nfft, nfr, nfft)
+        assert_psd_close(lin.cpu().numpy()[s].T, ref.T, noise_like=False, what=f"whole {nfft} sub {s}")
+        assert_db_close(db.cpu().numpy()[s].T, 10 * np.log10(ref.T.astype(np.float32) + np.float32(1e-15)),
+                        ref_lin=ref.T, what=f"whole {nfft} dB")
+
+
+def test_large_nfft_defaults_and_fallback(torch):
+    """16384 runs the whole-frame kernel, 32768 the cluster kernel, 65536 the split path (measured
+    defaults); a recording whose base is not 16-byte aligned cannot use bulk copies and takes the split
+    path at every size."""
+    from pyspectrogram_b200 import engine
+    for nfft, want in ((16384, "whole4x4096_s4"), (32768, "cluster8x4096_ldg"), (65536, "split16x4096")):
         x = torch.from_numpy(_recording(np.random.default_rng(nfft), nfft * 9)).cuda()
         starts = torch.from_numpy(np.arange(4, dtype=np.int64) * 2 * nfft).cuda()
         plan = engine.StiPlan(nfft)
@@ -317,11 +360,12 @@ def test_large_nfft_defaults_and_fallback(torch):
 
 
 @pytest.mark.parametrize("nfft", [256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536, (16384, "cluster"), (32768, "cluster_dsmem"),
-                                  (65536, "cluster_ldg"), (65536, "cluster_dsmem")])
+                                  (65536, "cluster_ldg"), (65536, "cluster_dsmem"), (16384, "whole"), (8192, "whole")])
 def test_repeated_runs_are_bit_identical(torch, nfft):
-    """Race canary (compute-sanitizer is not available on the GPU pool): the kernels have no
-    atomics and sum in a fixed order, so 12 back-to-back runs on two streams must agree bit for
-    bit; a missing barrier in an exchange shows up as run-to-run differences."""
+    """Race canary (compute-sanitizer is not available on the GPU pool): no atomic touches data (the
+    whole-frame kernel counts stage readers with one, which only decides WHO issues the next copy) and
+    sums run in a fixed order, so 12 back-to-back runs on two streams must agree bit for bit; a
+    missing barrier in an exchange shows up as run-to-run differences."""
     from pyspectrogram_b200 import engine
     variant = None
     if isinstance(nfft, tuple):

@@ -38,8 +38,12 @@ def main():
             plan = engine.StiPlan(nfft)
             try:
                 engine.set_variant(None if var == "default" else var)
-                for _ in range(2):
-                    plan.run(iq, starts, nint, nfft, want_lin=False, want_db=True, out_db=out)
+                try:
+                    for _ in range(2):
+                        plan.run(iq, starts, nint, nfft, want_lin=False, want_db=True, out_db=out)
+                except (NotImplementedError, ValueError, RuntimeError) as e:
+                    print(f"nfft={nfft:6d} {var:13s} not available: {e}", flush=True)
+                    continue
                 torch.cuda.synchronize()
                 ts = []
                 for _ in range(args.reps):
