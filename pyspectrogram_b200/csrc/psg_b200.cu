@@ -20,6 +20,7 @@
 #include "sti_kernels.cuh"
 #include "sti_cluster.cuh"
 #include "sti_whole.cuh"
+#include "sti_bluestein.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -242,6 +243,10 @@ struct psg_plan {
     float2* d_aw = nullptr;
     float2* d_bbr = nullptr;
     float2* d_twm = nullptr;
+    // high-radix Bluestein (sti_bluestein.cuh, M <= 16384): B in the position order of the radix plan, full W_M table
+    float2* d_bpos = nullptr;
+    float2* d_twf = nullptr;
+    int bs_npass = 0, bs_radix[4] = {0, 0, 0, 0};
     long long* d_colb = nullptr;
     size_t colb_bytes = 0;
     std::vector<long long> h_colb;
@@ -322,7 +327,7 @@ extern "C" int psg_set_variant(const char* name) {
     if (!g_variant_override.empty()) {
         bool ok = g_variant_override == "split" || g_variant_override == "cluster" || g_variant_override == "cluster_ldg" ||
                   g_variant_override == "cluster_dsmem" || g_variant_override == "whole" || g_variant_override == "whole_s2" ||
-                  g_variant_override == "whole_s8";
+                  g_variant_override == "whole_s8" || g_variant_override == "bluestein_r2";
         for (int i = 0; i < g_nvariants; ++i) ok = ok || g_variant_override == g_variants[i].name;
         if (!ok) {
             g_variant_override.clear();
@@ -445,6 +450,33 @@ static int build_bluestein(psg_plan* p) {
         const double ang = -2.0 * M_PI * (double)m / (double)M;
         twm[m] = make_float2((float)cos(ang), (float)sin(ang));
     }
+    if (logm <= 14) {
+        // radix plan: 2^(logm % 4) first, then 16s; after the forward passes position pos = sum_q k_q S_q holds
+        // frequency k_0 + R_0 k_1 + R_0 R_1 k_2 + ... (index algebra of sti_kernels.cuh)
+        int np = 0;
+        if (logm % 4) p->bs_radix[np++] = 1 << (logm % 4);
+        for (int i = 0; i < logm / 4; ++i) p->bs_radix[np++] = 16;
+        p->bs_npass = np;
+        std::vector<float2> bpos(M), twf(M);
+        for (size_t pos = 0; pos < M; ++pos) {
+            size_t rem = pos, s = M, freq = 0, mul = 1;
+            for (int q = 0; q < np; ++q) {
+                s /= (size_t)p->bs_radix[q];
+                freq += (rem / s) * mul;
+                rem %= s;
+                mul *= (size_t)p->bs_radix[q];
+            }
+            bpos[pos] = make_float2((float)(br[freq] / (double)M), (float)(bi[freq] / (double)M));
+        }
+        for (size_t m = 0; m < M; ++m) {
+            const double ang = -2.0 * M_PI * (double)m / (double)M;
+            twf[m] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+        CUDA_TRY(cudaMalloc(&p->d_bpos, sizeof(float2) * M));
+        CUDA_TRY(cudaMalloc(&p->d_twf, sizeof(float2) * M));
+        CUDA_TRY(cudaMemcpy(p->d_bpos, bpos.data(), sizeof(float2) * M, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(p->d_twf, twf.data(), sizeof(float2) * M, cudaMemcpyHostToDevice));
+    }
     CUDA_TRY(cudaMalloc(&p->d_aw, sizeof(float2) * N));
     CUDA_TRY(cudaMalloc(&p->d_bbr, sizeof(float2) * M));
     CUDA_TRY(cudaMalloc(&p->d_twm, sizeof(float2) * (M / 2)));
@@ -521,6 +553,8 @@ extern "C" int psg_plan_destroy(psg_plan* p) {
     cudaFree(p->d_aw);
     cudaFree(p->d_bbr);
     cudaFree(p->d_twm);
+    cudaFree(p->d_bpos);
+    cudaFree(p->d_twf);
     cudaFree(p->d_partial);
     cudaFree(p->d_gwork);
     cudaFree(p->d_gacc);
@@ -1063,11 +1097,85 @@ static int run_split(psg_plan* p, StiArgs a, int ncs, int frames_per_col, cudaSt
     return PSG_OK;
 }
 
-// non power-of-two nfft: Bluestein kernel, work buffer in shared memory up to M = 16384
+// non power-of-two nfft, M <= 16384: Bluestein with mixed-radix passes in shared memory (sti_bluestein.cuh)
+static int run_bluestein16(psg_plan* p, StiArgs a, int ncs, int frames_per_col, cudaStream_t st) {
+    const int N = p->nfft;
+    const size_t M = (size_t)1 << p->logm;
+    // frame groups of tpf threads (one radix-16 butterfly per thread and pass), as many as fit 256 threads
+    // (512 for the two largest M) and half the shared memory of an SM
+    const int tpf = (int)std::min<size_t>(512, std::max<size_t>(16, M / 16));
+    const size_t group_bytes = (size_t)(psg_pad((int)M) + 2) * 8 + (size_t)((N + 3) & ~3) * 4;
+    int groups = std::max(1, (M >= 8192 ? 512 : 256) / tpf);
+    while (groups > 1 && groups * group_bytes > 100 * 1024) groups /= 2;
+    groups = std::min(groups, std::max(1, floor_pow2(frames_per_col)));
+    const int threads = tpf * groups;
+    const size_t smem = groups * group_bytes;
+    const void* fn = (const void*)sti_bluestein16_kernel;
+    static thread_local int q_dev = -1;
+    if (q_dev != p->device) {
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        q_dev = p->device;
+    }
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem));
+    if (occ < 1) return fail(PSG_ERR_CUDA, "bluestein16 (M=%zu) does not fit on an SM", M);
+    const long long slots = (long long)p->sms * occ;
+    // items: columns, split into frame chunks (>= 4 frames, <= 1024 per fp32 accumulator) when there are too few
+    int nsplit = std::max(1, (frames_per_col + 1023) / 1024);
+    if ((long long)ncs * nsplit < 2 * slots)
+        nsplit = (int)std::max<long long>(nsplit, std::min<long long>(std::max(1, frames_per_col / (4 * groups)), (2 * slots + ncs - 1) / ncs));
+    const int chunk = (frames_per_col + nsplit - 1) / nsplit;
+    nsplit = (frames_per_col + chunk - 1) / chunk;
+    a.gpc = 1;
+    a.chunk = chunk;
+    a.nsplit = nsplit;
+    if (nsplit > 1) {
+        size_t have_b = p->partial_elems * sizeof(float);
+        int rc = ensure_buffer((void**)&p->d_partial, &have_b, (size_t)ncs * nsplit * N * sizeof(float));
+        p->partial_elems = have_b / sizeof(float);
+        if (rc) return rc;
+        a.partial = p->d_partial;
+    }
+    const long long items = (long long)ncs * nsplit;
+    const long long grid = std::min<long long>(items, slots);
+    Bluestein16Args b;
+    b.aw = p->d_aw;
+    b.bpos = p->d_bpos;
+    b.twf = p->d_twf;
+    b.n = N;
+    b.logm = p->logm;
+    b.tpf = tpf;
+    b.npass = p->bs_npass;
+    for (int i = 0; i < 4; ++i) b.radix[i] = p->bs_radix[i];
+    void* args[] = {(void*)&a, (void*)&b};
+    CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(threads), args, smem, st));
+    g_launches++;
+    if (nsplit > 1) {
+        const size_t total = (size_t)ncs * N;
+        const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)p->sms * 16);
+        sti_finalize_kernel<<<blocks, 256, 0, st>>>(a.partial, nsplit, N, (size_t)ncs, a.scale, a.eps, a.out_lin, a.out_db);
+        g_launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    std::string name = "bluestein_m" + std::to_string(M) + "_";
+    for (int i = 0; i < p->bs_npass; ++i) name += (i ? "x" : "") + std::to_string(p->bs_radix[i]);
+    snprintf(p->variant_name, sizeof(p->variant_name), "%s", name.c_str());
+    return PSG_OK;
+}
+
+// non power-of-two nfft: radix-2 Bluestein kernel (M > 16384: work buffer in global scratch; or forced)
 static int run_bluestein(psg_plan* p, StiArgs a, int ncs, int frames_per_col, cudaStream_t st) {
     const int N = p->nfft;
     const size_t M = (size_t)1 << p->logm;
-    snprintf(p->variant_name, sizeof(p->variant_name), "bluestein_m%zu", M);
+    {
+        bool force_r2 = false;
+        {
+            std::lock_guard<std::mutex> lk(g_variant_mu);
+            force_r2 = g_variant_override == "bluestein_r2";
+        }
+        if (p->d_bpos && !force_r2) return run_bluestein16(p, a, ncs, frames_per_col, st);
+    }
+    snprintf(p->variant_name, sizeof(p->variant_name), "bluestein_m%zu_r2", M);
     const size_t smem_need = M * 8 + (size_t)N * 4;
     const bool in_smem = smem_need <= 200 * 1024;
     const int iters = frames_per_col;

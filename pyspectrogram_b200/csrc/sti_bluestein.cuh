@@ -1,0 +1,186 @@
+// Arbitrary (non power-of-two) nfft, Bluestein's chirp-z algorithm with high-radix passes.
+//
+// Same mathematics as sti_bluestein_kernel (sti_kernels.cuh): with c[n] = exp(+j*pi*n^2/N),
+//   |X[k]|^2 = |(a (*) c)[k]|^2,  a[n] = x[n] w[n] conj(c[n]),
+// the circular convolution of length M = 2^m >= 2N-1 computed as IFFT_M(FFT_M(a) .* B), B = FFT_M(c)/M.
+// That kernel runs 2*log2(M) radix-2 passes over shared memory per frame (22 exchanges at M = 2048);
+// this one runs the M-point transforms as mixed-radix passes (first radix 2, 4 or 8, then 16s -- the
+// butterflies of cplx.cuh) in the padded in-place layout of the tuned kernels:
+//   forward   pass p splits n_rest = n_p*S_p + n', R_p-point DFT over n_p, output k_p times
+//             W_M^{n' k_p M/(R_p S_p)}, stored in place of n_p (the index algebra of sti_kernels.cuh).  Pass 0
+//             reads the samples straight from global memory (zero beyond N) and applies a[n]; the last pass
+//             multiplies by B, which the host stores in the order the positions come out (digit-reversed).
+//   inverse   the transposed network, passes P-1 .. 0: conjugate twiddle, then the inverse R_p-point DFT
+//             (conj . DFT . conj) over k_p; positions come back in natural order and the last pass adds
+//             |y[n]|^2, n < N, to the column's accumulators in shared memory instead of storing y.
+// 2P-1 exchanges per frame (5 at M = 2048, 7 at M = 16384).  A CTA is G frame groups of max(16, M/16)
+// threads working on G frames of one work item (column, frame chunk) at a time; the radix-2 kernel remains
+// the path for M > 16384 (global scratch).
+#pragma once
+#include "sti_cluster.cuh"
+
+struct Bluestein16Args {
+    const float2* aw;    // [N]  w[n]/sum(w) * conj(c[n])
+    const float2* bpos;  // [M]  FFT_M(c)[freq(pos)] / M, indexed by position after the forward passes
+    const float2* twf;   // [M]  exp(-2*pi*j*m/M)
+    int n, logm;
+    int tpf;  // threads per frame group (divides the CTA size)
+    int npass;
+    int radix[4];  // radix[0] in {2, 4, 8, 16}, the rest 16
+};
+
+PSG_DEV cf cconj(cf a) { return make_float2(a.x, -a.y); }
+
+// forward pass: FIRST reads global samples * aw, LAST multiplies by B
+template <int R>
+PSG_DEV void bs_forward_pass(float2* __restrict__ buf, int logS, int M, int Mv, int tid, int nt, const float2* __restrict__ twf,
+                             bool first, bool last, const StiArgs& a, long long src, const Bluestein16Args& b) {
+    const int S = 1 << logS;
+    constexpr int NPW = psg_npow(R);
+    const int tstride = M / (R << logS);  // W_{R S}^{e} = W_M^{e * tstride}
+    for (int bf = tid; bf < Mv / R; bf += nt) {
+        const int npr = bf & (S - 1);
+        const int base = ((bf >> logS) * R << logS) + npr;
+        cf v[R];
+        if (first) {
+#pragma unroll
+            for (int n = 0; n < R; ++n) {
+                const int i = base + (n << logS);
+                v[n] = (i < b.n) ? cmul(ldg_iq_rt(a.iq_type, a.iq, src + (long long)i * a.sample_stride), __ldg(b.aw + i))
+                                 : make_float2(0.f, 0.f);
+            }
+        } else {
+#pragma unroll
+            for (int n = 0; n < R; ++n) v[n] = buf[psg_pad(base + (n << logS))];
+        }
+        dftR<R>(v);
+        if (last) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) v[k] = cmul(v[k], __ldg(b.bpos + base + (k << logS)));
+        } else {
+            // W^k, k < R, from W^1, W^2, W^4, W^8 (four loads instead of fifteen; sti_cluster.cuh)
+            cf pw[NPW];
+#pragma unroll
+            for (int q = 0; q < NPW; ++q) pw[q] = __ldg(twf + ((npr * tstride) << q));
+            twiddle_dfs<R>(v, pw);
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) buf[psg_pad(base + (k << logS))] = v[k];
+    }
+}
+
+// inverse of the forward pass with the same (R, S): FIRST here is the pass that has no twiddle (the
+// forward network's last pass), FINAL accumulates |y|^2 for n < nvalid instead of storing
+template <int R>
+PSG_DEV void bs_inverse_pass(float2* __restrict__ buf, int logS, int M, int Mv, int tid, int nt, const float2* __restrict__ twf,
+                             bool notw, bool final_pass, float* __restrict__ accs, int nvalid) {
+    const int S = 1 << logS;
+    constexpr int NPW = psg_npow(R);
+    const int tstride = M / (R << logS);
+    for (int bf = tid; bf < Mv / R; bf += nt) {
+        const int npr = bf & (S - 1);
+        const int base = ((bf >> logS) * R << logS) + npr;
+        cf v[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) v[k] = buf[psg_pad(base + (k << logS))];
+        if (!notw) {
+            cf pw[NPW];
+#pragma unroll
+            for (int q = 0; q < NPW; ++q) pw[q] = cconj(__ldg(twf + ((npr * tstride) << q)));
+            twiddle_dfs<R>(v, pw);
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) v[k] = cconj(v[k]);
+        dftR<R>(v);  // conj(IDFT) of the inputs: the conjugate is undone below or irrelevant for |.|^2
+        if (final_pass) {
+#pragma unroll
+            for (int n = 0; n < R; ++n) {
+                const int i = base + (n << logS);
+                if (i < nvalid) accs[i] = fmaf(v[n].x, v[n].x, fmaf(v[n].y, v[n].y, accs[i]));
+            }
+        } else {
+#pragma unroll
+            for (int n = 0; n < R; ++n) buf[psg_pad(base + (n << logS))] = cconj(v[n]);
+        }
+    }
+}
+
+PSG_DEV void bs_forward_dispatch(int R, float2* buf, int logS, int M, int Mv, int tid, int nt, const float2* twf, bool first,
+                                 bool last, const StiArgs& a, long long src, const Bluestein16Args& b) {
+    switch (R) {
+        case 2: bs_forward_pass<2>(buf, logS, M, Mv, tid, nt, twf, first, last, a, src, b); break;
+        case 4: bs_forward_pass<4>(buf, logS, M, Mv, tid, nt, twf, first, last, a, src, b); break;
+        case 8: bs_forward_pass<8>(buf, logS, M, Mv, tid, nt, twf, first, last, a, src, b); break;
+        default: bs_forward_pass<16>(buf, logS, M, Mv, tid, nt, twf, first, last, a, src, b); break;
+    }
+}
+PSG_DEV void bs_inverse_dispatch(int R, float2* buf, int logS, int M, int Mv, int tid, int nt, const float2* twf, bool notw,
+                                 bool final_pass, float* accs, int nvalid) {
+    switch (R) {
+        case 2: bs_inverse_pass<2>(buf, logS, M, Mv, tid, nt, twf, notw, final_pass, accs, nvalid); break;
+        case 4: bs_inverse_pass<4>(buf, logS, M, Mv, tid, nt, twf, notw, final_pass, accs, nvalid); break;
+        case 8: bs_inverse_pass<8>(buf, logS, M, Mv, tid, nt, twf, notw, final_pass, accs, nvalid); break;
+        default: bs_inverse_pass<16>(buf, logS, M, Mv, tid, nt, twf, notw, final_pass, accs, nvalid); break;
+    }
+}
+
+__global__ void __launch_bounds__(512) sti_bluestein16_kernel(const StiArgs a, const Bluestein16Args b) {
+    const int N = b.n, M = 1 << b.logm;
+    extern __shared__ __align__(16) float2 bs_smem[];
+    // frame groups of b.tpf threads: group g transforms frames k0 + g, k0 + g + G, ... of the item in its own
+    // buffer and adds into its own accumulators; the groups are summed in fixed order in the epilogue
+    const int T = b.tpf, G = blockDim.x / T;
+    const int g = threadIdx.x / T, t = threadIdx.x - g * T;
+    const int bstride = psg_pad(M) + 2;          // complex per group buffer (even: 16-byte aligned)
+    const int astride = (N + 3) & ~3;            // floats per group accumulator
+    float2* buf = bs_smem + (size_t)g * bstride;
+    float* acc0 = reinterpret_cast<float*>(bs_smem + (size_t)G * bstride);
+    float* accs = acc0 + (size_t)g * astride;
+    const int ncs = a.ncol * a.nsub;
+    const int P = b.npass;
+    for (int item = blockIdx.x; item < ncs * a.nsplit; item += gridDim.x) {
+        const int split = item % a.nsplit;
+        const int cs = item / a.nsplit;
+        const int col = cs % a.ncol, sub = cs / a.ncol;
+        const int k0 = split * a.chunk;
+        const int k1 = min(a.nfr, k0 + a.chunk);
+        const long long src0 = a.col_off[col] + (long long)sub * a.sub_stride;
+        __syncthreads();  // the previous item's epilogue is done with the accumulators
+        for (int i = t; i < N; i += T) accs[i] = 0.f;
+        const int niter = (k1 - k0 + G - 1) / G;
+        for (int j = 0; j < niter; ++j) {
+            const int k = k0 + j * G + g;
+            const int Mv = (k < k1) ? M : 0;  // a group without a frame runs the barriers only
+            const long long src = src0 + (long long)k * a.hop_elems;
+            int logS = b.logm;
+            for (int p = 0; p < P; ++p) {
+                const int R = b.radix[p];
+                logS -= (R == 16) ? 4 : (R == 8) ? 3 : (R == 4) ? 2 : 1;
+                __syncthreads();  // p = 0: the previous frame's last inverse pass has read buf (and accs are zeroed)
+                bs_forward_dispatch(R, buf, logS, M, Mv, t, T, b.twf, p == 0, p == P - 1, a, src, b);
+            }
+            // logS == 0 here; walk the strides back up
+            for (int p = P - 1; p >= 0; --p) {
+                const int R = b.radix[p];
+                __syncthreads();
+                bs_inverse_dispatch(R, buf, logS, M, Mv, t, T, b.twf, p == P - 1, p == 0, accs, N);
+                logS += (R == 16) ? 4 : (R == 8) ? 3 : (R == 4) ? 2 : 1;
+            }
+        }
+        __syncthreads();
+        const int half = N / 2;  // np.fft.fftshift: out[(k + N//2) mod N] = in[k]
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+            float sum = acc0[i];
+            for (int gg = 1; gg < G; ++gg) sum += acc0[(size_t)gg * astride + i];
+            int idx = i + half;
+            if (idx >= N) idx -= N;
+            if (a.nsplit > 1) {
+                a.partial[((size_t)cs * a.nsplit + split) * N + idx] = sum;
+            } else {
+                const float pw = sum * a.scale;
+                if (a.out_lin) a.out_lin[(size_t)cs * N + idx] = pw;
+                if (a.out_db) a.out_db[(size_t)cs * N + idx] = power_to_db(pw, a.eps);
+            }
+        }
+    }
+}

@@ -100,10 +100,37 @@ def test_arbitrary_nfft_against_float64_oracle(torch, nfft, mode):
     plan = engine.StiPlan(nfft)
     lin, db = plan.run(torch.from_numpy(x).cuda(), torch.from_numpy(starts).cuda(), nfr, nfft, want_lin=True, want_db=True)
     assert plan.variant.startswith("bluestein")
+    # convolution lengths up to 16384 run the mixed-radix kernel, longer ones the radix-2 kernel
+    assert plan.variant.endswith("_r2") == (2 * nfft - 1 > 16384), plan.variant
     ref = _oracle_columns(x, starts, nfft, nfr, nfft)
     assert_psd_close(lin.cpu().numpy()[0].T, ref.T, noise_like=False, what=f"nfft={nfft} {plan.variant}")
     assert_db_close(db.cpu().numpy()[0].T, 10 * np.log10(ref.T.astype(np.float32) + np.float32(1e-15)),
                     ref_lin=ref.T, what=f"nfft={nfft} dB")
+
+
+@pytest.mark.parametrize("nfft,nfr,ncol", [(1000, 700, 2), (96, 5, 300), (6000, 2, 3)])
+def test_bluestein_kernels_agree(torch, nfft, nfr, ncol):
+    """The mixed-radix Bluestein kernel (default up to M = 16384) against the radix-2 one on the same
+    input, including columns split into frame chunks and more items than resident CTAs."""
+    from pyspectrogram_b200 import engine
+    rng = np.random.default_rng(nfft + nfr)
+    x = torch.from_numpy(_recording(rng, nfft * nfr * ncol + 5)).cuda()
+    starts = torch.from_numpy((np.arange(ncol) * nfft * nfr + np.arange(ncol) % 2).astype(np.int64)).cuda()
+    plan = engine.StiPlan(nfft)
+    lin, _ = plan.run(x, starts, nfr, nfft)
+    torch.cuda.synchronize()
+    assert not plan.variant.endswith("_r2"), plan.variant
+    try:
+        engine.set_variant("bluestein_r2")
+        lin2, _ = plan.run(x, starts, nfr, nfft)
+        torch.cuda.synchronize()
+        assert plan.variant.endswith("_r2"), plan.variant
+    finally:
+        engine.set_variant(None)
+    a, b = lin.cpu().numpy()[0], lin2.cpu().numpy()[0]
+    assert_psd_close(a.T, b.T.astype(np.float64), noise_like=False, what=f"bluestein16 vs radix-2 nfft={nfft}")
+    ref = _oracle_columns(x.cpu().numpy(), starts.cpu().numpy()[:2], nfft, nfr, nfft)
+    assert_psd_close(a[:2].T, ref.T, noise_like=False, what=f"bluestein16 nfft={nfft}")
 
 
 def test_short_input_raises_value_error(dp):

@@ -16,6 +16,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gb", type=float, default=4.0)
     ap.add_argument("--ntime", type=int, default=1000)
+    ap.add_argument("--nffts", default="64,256,512,1000,1024,2048,4096,8192,16384,32768,65536")
+    ap.add_argument("--variant", default=None, help="force a kernel variant / path (psg_set_variant)")
     args = ap.parse_args()
     import torch
     from pyspectrogram_b200 import engine
@@ -25,10 +27,11 @@ def main():
     n = int(args.gb * 1e9 / 8)
     iq = torch.empty(n + 8, dtype=torch.complex64, device=dev)
     torch.view_as_real(iq).normal_(0.0, 1e-2)
-    for nfft in (64, 256, 512, 1000, 1024, 2048, 4096, 8192, 16384, 32768, 65536):
+    for nfft in [int(v) for v in args.nffts.split(",")]:
         nint = n // args.ntime // nfft
         starts = torch.from_numpy(engine.frame_starts(0, n, nfft, nint, args.ntime).astype(np.int64)).to(dev)
         plan = engine.StiPlan(nfft)
+        engine.set_variant(args.variant)
         out = torch.empty((1, args.ntime, nfft), dtype=torch.float32, device=dev)
         for _ in range(2):
             plan.run(iq, starts, nint, nfft, want_lin=False, want_db=True, out_db=out)
