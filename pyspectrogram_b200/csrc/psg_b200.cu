@@ -920,6 +920,30 @@ static size_t whole_smem(int r0, int iqt, int nst) {
     return 128 + (size_t)nst * r0 * (512 * iqb + 16) + (size_t)(psg_pad(r0 * 4096) + 2) * 8;
 }
 
+static void fill_whole_constants(WholeArgs& wa, int N) {
+    for (int q = 0; q < 4; ++q)
+        for (int m = 0; m < 8; ++m) {
+            const double ang = -2.0 * M_PI * (double)((512ll * m << q) % N) / (double)N;
+            wa.cm[q][m] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+}
+
+// items of the whole-frame kernels: whole columns, or columns split into frame chunks (>= 8 frames each,
+// <= 1024 per fp32 accumulator) when that fills the last wave of `slots` concurrent items better
+static int whole_nsplit(int ncs, int frames_per_col, long long slots) {
+    const int smin = (frames_per_col + 1023) / 1024;
+    const int smax = std::max(smin, frames_per_col / 8);
+    int best = smin;
+    double best_eff = 0.0;
+    for (int ns = smin; ns <= std::min(smax, smin + 15); ++ns) {
+        const long long items = (long long)ncs * ns;
+        const long long waves = (items + slots - 1) / slots;
+        const double eff = (double)items / (double)(waves * slots) - 0.01 * (ns - smin);  // mild preference for fewer splits
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = ns; }
+    }
+    return best;
+}
+
 static int run_whole(psg_plan* p, const StiArgs& a0, int ncs, int frames_per_col, int nst, cudaStream_t st) {
     constexpr int N2 = 4096;
     const int N = p->nfft, r0 = N / N2;
@@ -941,12 +965,7 @@ static int run_whole(psg_plan* p, const StiArgs& a0, int ncs, int frames_per_col
     }
     int rc = ensure_split_tables(p, v);
     if (rc) return rc;
-    // items: whole columns when they keep every SM busy for three rounds, else columns split into
-    // frame chunks (>= 8 frames each; <= 1024 frames per fp32 accumulator), summed in fp64 afterwards
-    const long long slots = p->sms;
-    int nsplit = 1;
-    if (ncs < 3 * slots) nsplit = (int)std::min<long long>((8 * slots + ncs - 1) / ncs, std::max(1, frames_per_col / 8));
-    nsplit = std::max(nsplit, (frames_per_col + 1023) / 1024);
+    int nsplit = whole_nsplit(ncs, frames_per_col, p->sms);
     const int chunk = (frames_per_col + nsplit - 1) / nsplit;
     nsplit = (frames_per_col + chunk - 1) / chunk;
     WholeArgs wa;
@@ -956,11 +975,7 @@ static int run_whole(psg_plan* p, const StiArgs& a0, int ncs, int frames_per_col
     wa.s.chunk = chunk;
     wa.s.nsplit = nsplit;
     wa.s.nfr = frames_per_col;
-    for (int q = 0; q < 2; ++q)
-        for (int m = 0; m < 8; ++m) {
-            const double ang = -2.0 * M_PI * (double)((512ll * m << q) % N) / (double)N;
-            wa.cm[q][m] = make_float2((float)cos(ang), (float)sin(ang));
-        }
+    fill_whole_constants(wa, N);
     if (nsplit > 1) {
         size_t have_b = p->partial_elems * sizeof(float);
         rc = ensure_buffer((void**)&p->d_partial, &have_b, (size_t)ncs * nsplit * N * sizeof(float));
@@ -983,6 +998,92 @@ static int run_whole(psg_plan* p, const StiArgs& a0, int ncs, int frames_per_col
     CUDA_TRY(cudaGetLastError());
     snprintf(p->variant_name, sizeof(p->variant_name), "whole%dx4096_s%d%s", r0, nst,
              a0.iq_type == IQ_CI16 ? "_i16" : a0.iq_type == IQ_CI8 ? "_i8" : "");
+    return PSG_OK;
+}
+
+// ---- clustered whole-frame path (sti_whole.cuh): nfft = 32768 / 65536 on clusters of 2 / 4 CTAs ---------
+template <int CL>
+static const void* wholec_fn_iq(int iqt) {
+    return iqt == IQ_CI16 ? (const void*)sti_wholec_kernel<CL, IQ_CI16>
+           : iqt == IQ_CI8 ? (const void*)sti_wholec_kernel<CL, IQ_CI8>
+                           : (const void*)sti_wholec_kernel<CL, IQ_C64>;
+}
+
+// returns PSG_OK with *ran = false when the device cannot co-schedule the cluster (caller falls back)
+static int run_wholec(psg_plan* p, const StiArgs& a0, int ncs, int frames_per_col, cudaStream_t st, bool* ran) {
+    constexpr int N2 = 4096;
+    const int N = p->nfft, cl = N / (4 * N2);
+    *ran = false;
+    const Variant* v = variant_by_name(g_default_tma[12 - 5]);
+    if (!v || v->twp != 2) return fail(PSG_ERR_UNSUPPORTED, "whole-frame path needs the power-layout 4096-point tables");
+    const void* fn = cl == 2 ? wholec_fn_iq<2>(a0.iq_type) : cl == 4 ? wholec_fn_iq<4>(a0.iq_type) : nullptr;
+    if (!fn) return fail(PSG_ERR_UNSUPPORTED, "clustered whole-frame path: nfft=%d", N);
+    const size_t smem = whole_smem(4, a0.iq_type, 4);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(512);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static thread_local const void* q_fn = nullptr;
+    static thread_local int q_dev = -1, q_slots = 0;
+    if (q_fn != fn || q_dev != p->device) {
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cfg.gridDim = dim3((unsigned)(cl * p->sms));
+        int nmax = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&nmax, fn, &cfg);
+        if (e != cudaSuccess) { cudaGetLastError(); nmax = 0; }
+        q_fn = fn;
+        q_dev = p->device;
+        q_slots = nmax;
+    }
+    if (q_slots < 1) return PSG_OK;
+    int rc = ensure_split_tables(p, v);
+    if (rc) return rc;
+    int nsplit = whole_nsplit(ncs, frames_per_col, q_slots);
+    const int chunk = (frames_per_col + nsplit - 1) / nsplit;
+    nsplit = (frames_per_col + chunk - 1) / chunk;
+    WholeArgs wa;
+    wa.s = a0;
+    wa.s.twp = p->d_twp_sub;
+    wa.s.gpc = 1;
+    wa.s.chunk = chunk;
+    wa.s.nsplit = nsplit;
+    wa.s.nfr = frames_per_col;
+    fill_whole_constants(wa, N);
+    if (nsplit > 1) {
+        size_t have_b = p->partial_elems * sizeof(float);
+        rc = ensure_buffer((void**)&p->d_partial, &have_b, (size_t)ncs * nsplit * N * sizeof(float));
+        p->partial_elems = have_b / sizeof(float);
+        if (rc) return rc;
+        wa.s.partial = p->d_partial;
+    }
+    const long long grid = (long long)ncs * nsplit * cl;
+    if (grid > 2147483647ll) return fail(PSG_ERR_ARG, "psg_sti_run: grid too large");
+    cfg.gridDim = dim3((unsigned)grid);
+    if (getenv("PSG_DEBUG"))
+        fprintf(stderr, "[psg] clustered whole-frame path cl=%d resident clusters=%d items=%lld (nsplit=%d, chunk=%d)\n", cl, q_slots,
+                (long long)ncs * nsplit, nsplit, chunk);
+    void* args[] = {(void*)&wa};
+    CUDA_TRY(cudaLaunchKernelExC(&cfg, fn, args));
+    g_launches++;
+    if (nsplit > 1) {
+        const size_t total = (size_t)ncs * N;
+        const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)p->sms * 16);
+        sti_finalize_kernel<<<blocks, 256, 0, st>>>(wa.s.partial, nsplit, N, (size_t)ncs, wa.s.scale, wa.s.eps, wa.s.out_lin,
+                                                    wa.s.out_db);
+        g_launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    snprintf(p->variant_name, sizeof(p->variant_name), "whole%dx4096_c%d%s", 4 * cl, cl,
+             a0.iq_type == IQ_CI16 ? "_i16" : a0.iq_type == IQ_CI8 ? "_i8" : "");
+    *ran = true;
     return PSG_OK;
 }
 
@@ -1316,9 +1417,16 @@ extern "C" int psg_sti_run_typed(psg_plan* p, const void* iq_dev, int iq_type, i
         }
         // 16384 points: the whole frame in one SM (sti_whole.cuh) is the measured default (39 % of the HBM peak
         // against 30 % for the 4-CTA cluster kernel, profiles/r01_whole_frame_16384.txt)
-        if (p->logn == 14 && tma_ok && !v && !force_split && !force_cluster && !whole_nst) whole_nst = 4;
+        // 32768 points: the same kernel on clusters of two CTAs (36 % against 29 %); at 65536 (clusters of four: 24 %)
+        // the split path stays ahead (27 %)
+        if ((p->logn == 14 || p->logn == 15) && tma_ok && !v && !force_split && !force_cluster && !whole_nst) whole_nst = 4;
         if ((p->logn == 13 || p->logn == 14) && tma_ok && whole_nst) return run_whole(p, a, ncs, frames_per_col, whole_nst, st);
-        const bool cluster_default = !v && (p->logn == 14 || p->logn == 15);
+        if ((p->logn == 15 || p->logn == 16) && tma_ok && whole_nst == 4) {
+            bool ran = false;
+            const int rcw = run_wholec(p, a, ncs, frames_per_col, st, &ran);
+            if (rcw || ran) return rcw;
+        }
+        const bool cluster_default = false;  // superseded by the whole-frame kernels (kept selectable)
         if (p->logn >= 13 && p->logn <= 16 && tma_ok && !force_split && (force_cluster || cluster_default)) {
             // one kernel, r0 CTAs per frame (sti_cluster.cuh); contiguous, 16-byte aligned recordings
             bool ran = false;

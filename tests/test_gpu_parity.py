@@ -332,7 +332,17 @@ def test_cluster_path(torch, nfft, nfr, ncol, nsub, kind):
     (8192, 6, 5, 1, "whole"),        # radix-2 first pass
     (8192, 6, 5, 1, "whole_s8"),
     (16384, 4, 6, 1, "whole_i16"),
-    (16384, 2, 3, 1, "whole_i8")])
+    (16384, 2, 3, 1, "whole_i8"),
+    (32768, 1, 9, 1, "whole"),       # cluster of two CTAs, half of the first-pass outputs through DSMEM
+    (32768, 5, 7, 2, "whole"),
+    (32768, 320, 2, 1, "whole"),
+    (32768, 3, 200, 1, "whole"),
+    (32768, 4, 6, 1, "whole_i16"),
+    (65536, 1, 9, 1, "whole"),       # cluster of four
+    (65536, 5, 5, 2, "whole"),
+    (65536, 160, 2, 1, "whole"),
+    (65536, 3, 100, 1, "whole"),
+    (65536, 2, 3, 1, "whole_i8")])
 def test_whole_frame_path(torch, nfft, nfr, ncol, nsub, kind):
     """Whole-frame kernel (sti_whole.cuh: 8192 / 16384 points resident in one SM, first pass fed in
     slabs through a bulk-copy ring refilled by the last reader) against the float64 oracle: modes,
@@ -366,11 +376,11 @@ def test_whole_frame_path(torch, nfft, nfr, ncol, nsub, kind):
 
 
 def test_large_nfft_defaults_and_fallback(torch):
-    """16384 runs the whole-frame kernel, 32768 the cluster kernel, 65536 the split path (measured
+    """16384 runs the whole-frame kernel, 32768 its two-CTA cluster form, 65536 the split path (measured
     defaults); a recording whose base is not 16-byte aligned cannot use bulk copies and takes the split
     path at every size."""
     from pyspectrogram_b200 import engine
-    for nfft, want in ((16384, "whole4x4096_s4"), (32768, "cluster8x4096_ldg"), (65536, "split16x4096")):
+    for nfft, want in ((16384, "whole4x4096_s4"), (32768, "whole8x4096_c2"), (65536, "split16x4096")):
         x = torch.from_numpy(_recording(np.random.default_rng(nfft), nfft * 9)).cuda()
         starts = torch.from_numpy(np.arange(4, dtype=np.int64) * 2 * nfft).cuda()
         plan = engine.StiPlan(nfft)
@@ -387,7 +397,7 @@ def test_large_nfft_defaults_and_fallback(torch):
 
 
 @pytest.mark.parametrize("nfft", [256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536, (16384, "cluster"), (32768, "cluster_dsmem"),
-                                  (65536, "cluster_ldg"), (65536, "cluster_dsmem"), (16384, "whole"), (8192, "whole")])
+                                  (65536, "cluster_ldg"), (65536, "cluster_dsmem"), (16384, "whole"), (8192, "whole"), (32768, "whole"), (65536, "whole")])
 def test_repeated_runs_are_bit_identical(torch, nfft):
     """Race canary (compute-sanitizer is not available on the GPU pool): no atomic touches data (the
     whole-frame kernel counts stage readers with one, which only decides WHO issues the next copy) and

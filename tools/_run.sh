@@ -1,6 +1,4 @@
-(timeout 900 python -m pytest tests/test_gpu_parity.py -k "bluestein or arbitrary or non_power" -x -q 2>&1 | tail -15) > gpurun_out/bluestein_tests.log 2>&1
-cat gpurun_out/bluestein_tests.log
-timeout 600 python tools/default_sweep.py --gb 4 --nffts 100,1000,3000,5000,8000 > gpurun_out/bluestein_sweep_4gb.log 2>&1
-cat gpurun_out/bluestein_sweep_4gb.log
-timeout 600 python tools/default_sweep.py --gb 4 --nffts 100,1000,3000,5000,8000 --variant bluestein_r2 > gpurun_out/bluestein_r2_sweep_4gb.log 2>&1
-cat gpurun_out/bluestein_r2_sweep_4gb.log
+(timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -6) > gpurun_out/pytest_gpu.log 2>&1
+cat gpurun_out/pytest_gpu.log
+timeout 600 python tools/default_sweep.py --gb 12 > gpurun_out/default_sweep_12gb_whole.log 2>&1
+cat gpurun_out/default_sweep_12gb_whole.log
