@@ -327,7 +327,8 @@ extern "C" int psg_set_variant(const char* name) {
     if (!g_variant_override.empty()) {
         bool ok = g_variant_override == "split" || g_variant_override == "cluster" || g_variant_override == "cluster_ldg" ||
                   g_variant_override == "cluster_dsmem" || g_variant_override == "whole" || g_variant_override == "whole_s2" ||
-                  g_variant_override == "whole_s8" || g_variant_override == "bluestein_r2";
+                  g_variant_override == "whole_s8" || g_variant_override == "whole_r2" || g_variant_override == "whole_r4" ||
+                  g_variant_override == "bluestein_r2";
         for (int i = 0; i < g_nvariants; ++i) ok = ok || g_variant_override == g_variants[i].name;
         if (!ok) {
             g_variant_override.clear();
@@ -922,9 +923,9 @@ static size_t whole_smem(int r0, int iqt, int nst) {
 
 static void fill_whole_constants(WholeArgs& wa, int N) {
     for (int q = 0; q < 4; ++q)
-        for (int m = 0; m < 8; ++m) {
-            const double ang = -2.0 * M_PI * (double)((512ll * m << q) % N) / (double)N;
-            wa.cm[q][m] = make_float2((float)cos(ang), (float)sin(ang));
+        for (int j = 0; j < 16; ++j) {
+            const double ang = -2.0 * M_PI * (double)((256ll * j << q) % N) / (double)N;
+            wa.cm[q][j] = make_float2((float)cos(ang), (float)sin(ang));
         }
 }
 
@@ -1002,23 +1003,32 @@ static int run_whole(psg_plan* p, const StiArgs& a0, int ncs, int frames_per_col
 }
 
 // ---- clustered whole-frame path (sti_whole.cuh): nfft = 32768 / 65536 on clusters of 2 / 4 CTAs ---------
-template <int CL>
+template <int CL, int ROWS>
 static const void* wholec_fn_iq(int iqt) {
-    return iqt == IQ_CI16 ? (const void*)sti_wholec_kernel<CL, IQ_CI16>
-           : iqt == IQ_CI8 ? (const void*)sti_wholec_kernel<CL, IQ_CI8>
-                           : (const void*)sti_wholec_kernel<CL, IQ_C64>;
+    return iqt == IQ_CI16 ? (const void*)sti_wholec_kernel<CL, ROWS, IQ_CI16>
+           : iqt == IQ_CI8 ? (const void*)sti_wholec_kernel<CL, ROWS, IQ_CI8>
+                           : (const void*)sti_wholec_kernel<CL, ROWS, IQ_C64>;
 }
 
-// returns PSG_OK with *ran = false when the device cannot co-schedule the cluster (caller falls back)
-static int run_wholec(psg_plan* p, const StiArgs& a0, int ncs, int frames_per_col, cudaStream_t st, bool* ran) {
+// rows = 4: 512 threads, one CTA per SM (32768 on 2 CTAs, 65536 on 4); rows = 2: 256 threads, two CTAs per SM
+// (16384 on 2 CTAs, 32768 on 4, 65536 on 8).  Returns PSG_OK with *ran = false when the device cannot
+// co-schedule the cluster (caller falls back)
+static int run_wholec(psg_plan* p, const StiArgs& a0, int ncs, int frames_per_col, int rows, cudaStream_t st, bool* ran) {
     constexpr int N2 = 4096;
-    const int N = p->nfft, cl = N / (4 * N2);
+    const int N = p->nfft, cl = N / (rows * N2);
     *ran = false;
     const Variant* v = variant_by_name(g_default_tma[12 - 5]);
     if (!v || v->twp != 2) return fail(PSG_ERR_UNSUPPORTED, "whole-frame path needs the power-layout 4096-point tables");
-    const void* fn = cl == 2 ? wholec_fn_iq<2>(a0.iq_type) : cl == 4 ? wholec_fn_iq<4>(a0.iq_type) : nullptr;
-    if (!fn) return fail(PSG_ERR_UNSUPPORTED, "clustered whole-frame path: nfft=%d", N);
-    const size_t smem = whole_smem(4, a0.iq_type, 4);
+    const void* fn = nullptr;
+    if (rows == 4 && cl == 2) fn = wholec_fn_iq<2, 4>(a0.iq_type);
+    else if (rows == 4 && cl == 4) fn = wholec_fn_iq<4, 4>(a0.iq_type);
+    else if (rows == 2 && cl == 2) fn = wholec_fn_iq<2, 2>(a0.iq_type);
+    else if (rows == 2 && cl == 4) fn = wholec_fn_iq<4, 2>(a0.iq_type);
+    else if (rows == 2 && cl == 8) fn = wholec_fn_iq<8, 2>(a0.iq_type);
+    if (!fn) return fail(PSG_ERR_UNSUPPORTED, "clustered whole-frame path: nfft=%d rows=%d", N, rows);
+    const size_t iqb = a0.iq_type == IQ_C64 ? 8 : a0.iq_type == IQ_CI16 ? 4 : 2;
+    const int threads = 128 * rows;
+    const size_t smem = 128 + 4 * 4 * ((size_t)threads * iqb + 16) + (size_t)(psg_pad(rows * N2) + 2) * 8;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cudaLaunchAttribute attr[1];
@@ -1026,7 +1036,7 @@ static int run_wholec(psg_plan* p, const StiArgs& a0, int ncs, int frames_per_co
     attr[0].val.clusterDim.x = (unsigned)cl;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
-    cfg.blockDim = dim3(512);
+    cfg.blockDim = dim3((unsigned)threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cfg.attrs = attr;
@@ -1035,7 +1045,7 @@ static int run_wholec(psg_plan* p, const StiArgs& a0, int ncs, int frames_per_co
     static thread_local int q_dev = -1, q_slots = 0;
     if (q_fn != fn || q_dev != p->device) {
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cfg.gridDim = dim3((unsigned)(cl * p->sms));
+        cfg.gridDim = dim3((unsigned)(cl * p->sms * 2));
         int nmax = 0;
         cudaError_t e = cudaOccupancyMaxActiveClusters(&nmax, fn, &cfg);
         if (e != cudaSuccess) { cudaGetLastError(); nmax = 0; }
@@ -1068,8 +1078,8 @@ static int run_wholec(psg_plan* p, const StiArgs& a0, int ncs, int frames_per_co
     if (grid > 2147483647ll) return fail(PSG_ERR_ARG, "psg_sti_run: grid too large");
     cfg.gridDim = dim3((unsigned)grid);
     if (getenv("PSG_DEBUG"))
-        fprintf(stderr, "[psg] clustered whole-frame path cl=%d resident clusters=%d items=%lld (nsplit=%d, chunk=%d)\n", cl, q_slots,
-                (long long)ncs * nsplit, nsplit, chunk);
+        fprintf(stderr, "[psg] clustered whole-frame path cl=%d rows=%d resident clusters=%d items=%lld (nsplit=%d, chunk=%d)\n", cl,
+                rows, q_slots, (long long)ncs * nsplit, nsplit, chunk);
     void* args[] = {(void*)&wa};
     CUDA_TRY(cudaLaunchKernelExC(&cfg, fn, args));
     g_launches++;
@@ -1081,7 +1091,7 @@ static int run_wholec(psg_plan* p, const StiArgs& a0, int ncs, int frames_per_co
         g_launches++;
     }
     CUDA_TRY(cudaGetLastError());
-    snprintf(p->variant_name, sizeof(p->variant_name), "whole%dx4096_c%d%s", 4 * cl, cl,
+    snprintf(p->variant_name, sizeof(p->variant_name), "whole%dx4096_c%d%s%s", rows * cl, cl, rows == 2 ? "r2" : "",
              a0.iq_type == IQ_CI16 ? "_i16" : a0.iq_type == IQ_CI8 ? "_i8" : "");
     *ran = true;
     return PSG_OK;
@@ -1398,7 +1408,8 @@ extern "C" int psg_sti_run_typed(psg_plan* p, const void* iq_dev, int iq_type, i
     if (!g_force_generic.load()) {
         v = pick_variant(p->logn, tma_ok, iq_type);
         bool force_split = false, force_cluster = false;
-        int whole_nst = 0;  // whole-frame path forced with this many ring stages
+        int whole_nst = 0;   // whole-frame path forced with this many ring stages
+        int whole_rows = 0;  // ... and this many rows per CTA (0: the default form of the size)
         // Measured defaults (profiles/r01_big_nfft_cluster_vs_split.txt, 4 and 12 GB): the cluster kernel with
         // the exchange in L2 and rows loaded to registers wins at 16384 (31 % vs 26 % of the HBM peak) and
         // 32768 (29 % vs 27 %); at 65536 the 16-CTA clusters fill only 112 of the 148 SMs and the
@@ -1412,6 +1423,8 @@ extern "C" int psg_sti_run_typed(psg_plan* p, const void* iq_dev, int iq_type, i
             if (g_variant_override == "cluster_ldg") rowtma = 0;
             if (g_variant_override == "cluster_dsmem") rowtma = 2;
             if (g_variant_override == "whole") whole_nst = 4;
+            if (g_variant_override == "whole_r2") { whole_nst = 4; whole_rows = 2; }
+            if (g_variant_override == "whole_r4") { whole_nst = 4; whole_rows = 4; }
             if (g_variant_override == "whole_s2") whole_nst = 2;
             if (g_variant_override == "whole_s8") whole_nst = 8;
         }
@@ -1420,12 +1433,12 @@ extern "C" int psg_sti_run_typed(psg_plan* p, const void* iq_dev, int iq_type, i
         // 32768 points: the same kernel on clusters of two CTAs (36 % against 29 %); at 65536 (clusters of four: 24 %)
         // the split path stays ahead (27 %)
         if ((p->logn == 14 || p->logn == 15) && tma_ok && !v && !force_split && !force_cluster && !whole_nst) whole_nst = 4;
-        if ((p->logn == 13 || p->logn == 14) && tma_ok && whole_nst) return run_whole(p, a, ncs, frames_per_col, whole_nst, st);
-        if ((p->logn == 15 || p->logn == 16) && tma_ok && whole_nst == 4) {
+        if (p->logn >= 14 && p->logn <= 16 && tma_ok && whole_nst == 4 && (whole_rows == 2 || p->logn >= 15)) {
             bool ran = false;
-            const int rcw = run_wholec(p, a, ncs, frames_per_col, st, &ran);
+            const int rcw = run_wholec(p, a, ncs, frames_per_col, whole_rows ? whole_rows : 4, st, &ran);
             if (rcw || ran) return rcw;
         }
+        if ((p->logn == 13 || p->logn == 14) && tma_ok && whole_nst) return run_whole(p, a, ncs, frames_per_col, whole_nst, st);
         const bool cluster_default = false;  // superseded by the whole-frame kernels (kept selectable)
         if (p->logn >= 13 && p->logn <= 16 && tma_ok && !force_split && (force_cluster || cluster_default)) {
             // one kernel, r0 CTAs per frame (sti_cluster.cuh); contiguous, 16-byte aligned recordings

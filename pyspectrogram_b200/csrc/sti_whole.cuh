@@ -26,7 +26,7 @@
 
 struct WholeArgs {
     StiArgs s;        // tw = full table W_N^m, twp = pass tables of the 4096-point 16x16x16 plan (power layout)
-    float2 cm[4][8];  // W_N^{512 * m * 2^q}, m < 8, q < 4
+    float2 cm[4][16];  // W_N^{256 * j * 2^q}, j < 16, q < 4
 };
 
 template <int R0, int IQT, int NST>
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(512, 1) sti_whole_kernel(const WholeArgs wa) {
                 const int m = 2 * mp + h;
                 cf pw[NPWA];
 #pragma unroll
-                for (int qq = 0; qq < NPWA; ++qq) pw[qq] = (m == 0) ? wt[qq] : cmul(wt[qq], wa.cm[qq][m]);
+                for (int qq = 0; qq < NPWA; ++qq) pw[qq] = (m == 0) ? wt[qq] : cmul(wt[qq], wa.cm[qq][2 * m]);
                 twiddle_dfs<R0>(x[h], pw);
             }
             if (mp == 0) __syncthreads();  // the last pass of the previous frame is done with the exchange buffer
@@ -252,44 +252,48 @@ __global__ void __launch_bounds__(512, 1) sti_whole_kernel(const WholeArgs wa) {
     }
 }
 
-// ---- 32768 / 65536 points: the same kernel on a cluster of CL = 2 / 4 CTAs, four 4096-point rows each ----
-// N = R0 x 4096 with R0 = 4 CL.  Split the first-pass index n0 = CL a + b (a < 4, b < CL) and the row index
-// k0 = r + 4 s (r < 4, s < CL):
-//   X[r + 4 s] = sum_b W_CL^{b s} * W_R0^{b r} * ( sum_a w x[(CL a + b) 4096 + n'] W_4^{a r} )
-// CTA s of the cluster owns rows 4 s .. 4 s + 3, i.e. exactly the 16384-position exchange buffer of the
-// single-CTA kernel, and passes 1-3 are unchanged.  The first pass of CTA c covers n' in [c 4096/CL, (c+1) 4096/CL)
-// in eight steps (slab m of 512 n', then b): a step stages the four samples a = 0..3 of one b (16 KB: the ring
-// and its stages are those of the single-CTA kernel), does the windowed 4-point DFT over a, applies the
-// constant W_R0^{b r} and adds into the thread's R0 outputs with the trivial factors W_CL^{b s}; after the
-// last b the outputs get W_N^{n' k0} and go to the owners' buffers -- a quarter / half of them local stores,
-// the rest st.shared::cluster into the peer's shared memory, already in the padded layout.
+// ---- the same kernel on a thread-block cluster: CL CTAs of ROWS 4096-point rows each ------------------------
+// N = R0 x 4096 with R0 = ROWS CL = 4 NB.  Split the first-pass index n0 = NB a + b (a < 4, b < NB) and the row
+// index k0 = r + 4 s (r < 4, s < NB):
+//   X[r + 4 s] = sum_b W_NB^{b s} * W_R0^{b r} * ( sum_a w x[(NB a + b) 4096 + n'] W_4^{a r} )
+// CTA c of the cluster owns rows c ROWS .. c ROWS + ROWS - 1 in its exchange buffer and runs passes 1-3 on
+// them exactly like the single-CTA kernel.  Its share of the first pass is n' in [c 4096/CL, (c+1) 4096/CL), in
+// eight steps (slab m of T columns, then b): a step stages the four samples a = 0..3 of one b (the stages of
+// the single-CTA kernel), does the windowed 4-point DFT over a, applies the constant W_R0^{b r} and adds into
+// the thread's R0 outputs with the trivial factors W_NB^{b s}; after the last b the outputs get W_N^{n' k0} and
+// go to the row owners' buffers, already in the padded layout: ROWS of them with local stores, the rest with
+// st.async into the peers' shared memory.
+//   ROWS = 4, 512 threads, one CTA per SM:   32768 on 2 CTAs (default), 65536 on 4
+//   ROWS = 2, 256 threads, two CTAs per SM:  16384 on 2 CTAs, 32768 on 4, 65536 on 8 -- the two CTAs of an SM
+//            belong to different clusters, so the stalls of one first pass hide behind the other's passes
 // Synchronisation per frame: one cluster barrier "every CTA is done with the previous frame's last pass"
 // (relaxed arrive right after that pass -- nothing is published, so no fence -- wait before the first
 // store of the next frame), and for "all first-pass outputs have landed" a CTA barrier for the local
 // stores plus an mbarrier that counts the bytes the peers send with st.async (a release / acquire cluster
 // barrier here costs a MEMBAR + ERRBAR per thread behind the remote stores: 10 % of all stall samples).
-template <int CL, int IQT>
+template <int CL, int ROWS, int IQT>
 struct WholeClCfg {
-    static constexpr int N2 = 4096, T = 512, W = 512, NST = 4, NSTEP = 8;
-    static constexpr int R0 = 4 * CL, N = R0 * N2;
+    static constexpr int N2 = 4096, T = 128 * ROWS, W = T, NST = 4, NSTEP = 8;
+    static constexpr int R0 = ROWS * CL, N = R0 * N2, NB = R0 / 4;
     static constexpr int NPC = N2 / CL;  // n' per CTA
     static constexpr int IQB = IqBytes<IQT>::value;
     static constexpr int SEG = W * IQB + 16;
     static constexpr int STAGE = 4 * SEG;
-    static constexpr int NPAD = psg_pad(4 * N2) + 2;  // four rows
+    static constexpr int NPAD = psg_pad(ROWS * N2) + 2;
     static constexpr int HDR = 128;
     static constexpr size_t smem_bytes = HDR + (size_t)NST * STAGE + (size_t)NPAD * 8;
+    static_assert((NPC / W) * NB == NSTEP, "eight steps per frame");
 };
 
 PSG_DEV void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
-// W_16^K = exp(-2 pi j K / 16), K = 0..15
+// W_16^K = exp(-2 pi j K / 16)
 template <int K>
 PSG_DEV cf w16_const() {
     constexpr float c[16] = {1.f, PSG_C1_16, PSG_SQRT1_2, PSG_S1_16, 0.f, -PSG_S1_16, -PSG_SQRT1_2, -PSG_C1_16,
                              -1.f, -PSG_C1_16, -PSG_SQRT1_2, -PSG_S1_16, 0.f, PSG_S1_16, PSG_SQRT1_2, PSG_C1_16};
     return make_float2(c[K & 15], -c[(K + 12) & 15]);  // sin(x) = cos(x - pi/2): index K - 4 = K + 12 (mod 16)
 }
-// acc += v * (-j)^K
+// acc + v * (-j)^K
 template <int K>
 PSG_DEV cf add_rot(cf acc, cf v) {
     if constexpr ((K & 3) == 0) return cadd(acc, v);
@@ -297,52 +301,55 @@ PSG_DEV cf add_rot(cf acc, cf v) {
     else if constexpr ((K & 3) == 2) return csub(acc, v);
     else return csub(acc, mul_nj(v));
 }
-template <int K>
-PSG_DEV cf rot(cf v) {
-    if constexpr ((K & 3) == 0) return v;
-    else if constexpr ((K & 3) == 1) return mul_nj(v);
-    else if constexpr ((K & 3) == 2) return make_float2(-v.x, -v.y);
-    else return mul_pj(v);
-}
 
-// step E of the first pass for one thread: y[r] (the windowed 4-point DFT over a, already computed in x) ->
-// out[r + 4 s] (+)= W_CL^{b s} W_R0^{b r} y[r]
-template <int CL, int B>
+// step b of a slab for one thread: y[r] (the windowed 4-point DFT over a) -> out[r + 4 s] (+)= W_NB^{b s} W_R0^{b r} y[r]
+template <int NB, int B>
 PSG_DEV void wholec_accumulate(cf* out, cf* y) {
-    constexpr int R0 = 4 * CL;
-    if constexpr (B > 0) {
+    constexpr int R0 = 4 * NB;
+    if constexpr (B > 0 && B < NB) {
         y[1] = cmul(y[1], w16_const<(16 / R0) * B * 1>());
         y[2] = cmul(y[2], w16_const<(16 / R0) * B * 2>());
         y[3] = cmul(y[3], w16_const<(16 / R0) * B * 3>());
     }
+    if constexpr (B < NB) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        if constexpr (B == 0) {
-            out[r] = y[r];
-            if constexpr (CL >= 2) out[r + 4] = y[r];
-            if constexpr (CL >= 4) { out[r + 8] = y[r]; out[r + 12] = y[r]; }
-        } else {
-            // W_CL^{b s} = (-j)^{(4 / CL) b s}
-            out[r] = cadd(out[r], y[r]);
-            if constexpr (CL >= 2) out[r + 4] = add_rot<(4 / CL) * B * 1>(out[r + 4], y[r]);
-            if constexpr (CL >= 4) {
-                out[r + 8] = add_rot<(4 / CL) * B * 2>(out[r + 8], y[r]);
-                out[r + 12] = add_rot<(4 / CL) * B * 3>(out[r + 12], y[r]);
+        for (int r = 0; r < 4; ++r) {
+            if constexpr (B == 0) {
+                out[r] = y[r];
+                if constexpr (NB >= 2) out[r + 4] = y[r];
+                if constexpr (NB >= 4) { out[r + 8] = y[r]; out[r + 12] = y[r]; }
+            } else {
+                // W_NB^{b s} = (-j)^{(4 / NB) b s}
+                out[r] = cadd(out[r], y[r]);
+                if constexpr (NB >= 2) out[r + 4] = add_rot<(4 / NB) * B * 1>(out[r + 4], y[r]);
+                if constexpr (NB >= 4) {
+                    out[r + 8] = add_rot<(4 / NB) * B * 2>(out[r + 8], y[r]);
+                    out[r + 12] = add_rot<(4 / NB) * B * 3>(out[r + 12], y[r]);
+                }
             }
         }
     }
 }
+template <int NB>
+PSG_DEV void wholec_accumulate_b(int b, cf* out, cf* y) {  // b is a compile-time constant after unrolling
+    switch (b) {
+        case 0: wholec_accumulate<NB, 0>(out, y); break;
+        case 1: wholec_accumulate<NB, 1>(out, y); break;
+        case 2: wholec_accumulate<NB, 2>(out, y); break;
+        default: wholec_accumulate<NB, 3>(out, y); break;
+    }
+}
 
-template <int CL, int IQT>
-__global__ void __launch_bounds__(512, 1) sti_wholec_kernel(const WholeArgs wa) {
-    using CF = WholeClCfg<CL, IQT>;
-    constexpr int N2 = CF::N2, N = CF::N, T = CF::T, W = CF::W, R0 = CF::R0, NPC = CF::NPC, NSTEP = CF::NSTEP, NST = CF::NST,
-                  IQB = CF::IQB, SEG = CF::SEG;
+template <int CL, int ROWS, int IQT>
+__global__ void __launch_bounds__(128 * ROWS, 4 / ROWS) sti_wholec_kernel(const WholeArgs wa) {
+    using CF = WholeClCfg<CL, ROWS, IQT>;
+    constexpr int N2 = CF::N2, N = CF::N, T = CF::T, W = CF::W, R0 = CF::R0, NB = CF::NB, NPC = CF::NPC, NSTEP = CF::NSTEP,
+                  NST = CF::NST, IQB = CF::IQB, SEG = CF::SEG;
     constexpr int NW = T / 32, NBT = 2;
     constexpr int NPWA = psg_npow(R0);
     using PL4 = Plan<N2, 16, 16, 16, 1, 2>;
     using PLN = Plan<N, R0, 16, 16, 16, 2>;
-    static_assert(CL == 2 || CL == 4, "cluster of two or four CTAs");
+    static_assert((ROWS == 4 || ROWS == 2) && CL >= 2 && R0 >= 4 && R0 <= 16, "rows per CTA and cluster size");
     const StiArgs& a = wa.s;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
@@ -350,7 +357,7 @@ __global__ void __launch_bounds__(512, 1) sti_wholec_kernel(const WholeArgs wa) 
     uint64_t* landed = reinterpret_cast<uint64_t*>(smem_raw + 96);  // bytes of first-pass outputs received from the peers
     unsigned char* stage = smem_raw + CF::HDR;
     float2* xch = reinterpret_cast<float2*>(smem_raw + CF::HDR + (size_t)NST * CF::STAGE);
-    constexpr uint32_t PEER_BYTES = (uint32_t)(CL - 1) * NPC * 4 * 8;  // (CL-1) peers x NPC columns x 4 rows
+    constexpr uint32_t PEER_BYTES = (uint32_t)(CL - 1) * NPC * ROWS * 8;  // (CL-1) peers x NPC columns x ROWS rows
 
     const int t = threadIdx.x;
     const int c = (int)cluster_ctarank();
@@ -361,10 +368,10 @@ __global__ void __launch_bounds__(512, 1) sti_wholec_kernel(const WholeArgs wa) 
     const int kf0 = split * a.chunk;
     const int nfr = min(a.nfr, kf0 + a.chunk) - kf0;
     const long long fbase = a.col_off[col] + (long long)sub * a.sub_stride + (long long)kf0 * a.hop_elems + c * NPC;
-    const int nsteps = nfr * NSTEP;  // step q = (frame q / 8, slab (q % 8) / CL, b = q % CL) -> stage q % NST
+    const int nsteps = nfr * NSTEP;  // step q = (frame q / 8, slab (q % 8) / NB, b = q % NB) -> stage q % NST
 
     auto issue = [&](int q) {  // one thread
-        const int f = q / NSTEP, e = q % NSTEP, m = e / CL, b = e % CL, s = q % NST;
+        const int f = q / NSTEP, e = q % NSTEP, m = e / NB, b = e % NB, s = q % NST;
         const uintptr_t src0 =
             reinterpret_cast<uintptr_t>(a.iq) + (uintptr_t)((fbase + (long long)f * a.hop_elems + b * N2 + m * W) * IQB);
         const uint32_t bytes = W * IQB + ((src0 & 15) ? 16 : 0);
@@ -373,7 +380,7 @@ __global__ void __launch_bounds__(512, 1) sti_wholec_kernel(const WholeArgs wa) 
         unsigned char* dst = stage + (size_t)s * CF::STAGE;
 #pragma unroll
         for (int aa = 0; aa < 4; ++aa)
-            bulk_g2s(dst + aa * SEG, reinterpret_cast<const void*>((src0 & ~(uintptr_t)15) + (uintptr_t)aa * CL * N2 * IQB), bytes,
+            bulk_g2s(dst + aa * SEG, reinterpret_cast<const void*>((src0 & ~(uintptr_t)15) + (uintptr_t)aa * NB * N2 * IQB), bytes,
                      bar);
     };
     if (t == 0) {
@@ -407,17 +414,17 @@ __global__ void __launch_bounds__(512, 1) sti_wholec_kernel(const WholeArgs wa) 
     __syncthreads();   // barriers and counters initialised, "landed" armed
     cluster_arrive();  // matches the wait before the first store of frame 0 (release: the peers see the armed barrier)
 
-    // window of step e: samples (CL a + b) 4096 + c NPC + 512 m + t, a = 0..3
+    // window of step e: samples (NB a + b) 4096 + c NPC + T m + t, a = 0..3
     const float* const winp = a.win + c * NPC + t;
     float wq[NSTEP][4];
     auto load_window = [&](int e, float* w) {
-        const int m = e / CL, b = e % CL;
+        const int m = e / NB, b = e % NB;
 #pragma unroll
-        for (int aa = 0; aa < 4; ++aa) w[aa] = __ldg(winp + (CL * aa + b) * N2 + m * W);
+        for (int aa = 0; aa < 4; ++aa) w[aa] = __ldg(winp + (NB * aa + b) * N2 + m * W);
     };
     // steps requested before the last pass of the previous frame / at the top of the first pass; the rest two
-    // pairs ahead of their use.  Four CTAs: two steps less in flight (16 outputs per thread: registers)
-    constexpr int WQA = (CL == 4) ? 2 : 4, WQB = WQA + 2;
+    // pairs ahead of their use.  Sixteen outputs per thread: two steps less in flight (registers)
+    constexpr int WQA = (NB == 4) ? 2 : 4, WQB = WQA + 2;
 #pragma unroll
     for (int e = 0; e < WQA; ++e) load_window(e, wq[e]);
     for (int f = 0; f < nfr; ++f) {
@@ -458,32 +465,23 @@ __global__ void __launch_bounds__(512, 1) sti_wholec_kernel(const WholeArgs wa) 
                     if ((old & (NW - 1)) == NW - 1 && q + NST < nsteps) issue(q + NST);
                 }
             }
-            // CL = 2: the pair is (b = 0, b = 1) of slab pp; CL = 4: the pair is b = 0,1 or b = 2,3 of slab pp / 2
-            if constexpr (CL == 2) {
-                wholec_accumulate<CL, 0>(out, x[0]);
-                wholec_accumulate<CL, 1>(out, x[1]);
-            } else {
-                if ((pp & 1) == 0) {
-                    wholec_accumulate<CL, 0>(out, x[0]);
-                    wholec_accumulate<CL, 1>(out, x[1]);
-                } else {
-                    wholec_accumulate<CL, 2>(out, x[0]);
-                    wholec_accumulate<CL, 3>(out, x[1]);
-                }
-            }
-            if (CL == 2 || (pp & 1) == 1) {  // slab complete: twiddle, store to the row owners
-                const int m = (CL == 2) ? pp : pp / 2;
-                cf pw[NPWA];
 #pragma unroll
-                for (int qq = 0; qq < NPWA; ++qq) pw[qq] = (m == 0) ? wt[qq] : cmul(wt[qq], wa.cm[qq][m]);
-                twiddle_dfs<R0>(out, pw);
-                if (m == 0) cluster_wait();  // every CTA is done with the last pass of the previous frame
+            for (int h = 0; h < 2; ++h) {
+                const int e = 2 * pp + h, m = e / NB, b = e % NB;
+                wholec_accumulate_b<NB>(b, out, x[h]);
+                if (b == NB - 1) {  // slab complete: twiddle, send to the row owners
+                    cf pw[NPWA];
 #pragma unroll
-                for (int k0 = 0; k0 < R0; ++k0) {
-                    const int s = k0 >> 2, r = k0 & 3;
-                    const int off = pad_off(r * N2 + m * W);
-                    if (s == c) p0[off] = out[k0];
-                    else st_async_cf(rbase[s] + (uint32_t)off * 8u, out[k0], rbar[s]);
+                    for (int qq = 0; qq < NPWA; ++qq) pw[qq] = (m == 0) ? wt[qq] : cmul(wt[qq], wa.cm[qq][m * (W / 256)]);
+                    twiddle_dfs<R0>(out, pw);
+                    if (m == 0) cluster_wait();  // every CTA is done with the last pass of the previous frame
+#pragma unroll
+                    for (int k0 = 0; k0 < R0; ++k0) {
+                        const int s = k0 / ROWS, r = k0 % ROWS;
+                        const int off = pad_off(r * N2 + m * W);
+                        if (s == c) p0[off] = out[k0];
+                        else st_async_cf(rbase[s] + (uint32_t)off * 8u, out[k0], rbar[s]);
+                    }
                 }
             }
         }
@@ -528,34 +526,50 @@ __global__ void __launch_bounds__(512, 1) sti_wholec_kernel(const WholeArgs wa) 
     }
     cluster_wait();  // consume the last arrive; no peer writes to this CTA any more
 
-    // ---- epilogue: this CTA's bins k = (4 c + r) + R0 k' are every CL-th group of four output bins ----
+    // ---- epilogue: this CTA's bins k = (c ROWS + r) + R0 k' are every CL-th group of ROWS output bins ----
     float* sout = reinterpret_cast<float*>(xch);  // N / CL floats
 #pragma unroll
     for (int i = 0; i < NBT; ++i) {
-        const int klow = PLN::low_freq(t + i * T + c * (N / 16 / CL));
+        const int klow = PLN::low_freq(t + i * T + c * (ROWS * 256));
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
             const int freq = klow + (N / 16) * jj;
             const int idx = (freq + N / 2) & (N - 1);
-            const int li = ((idx / R0) << 2) | (idx & 3);
-            sout[li ^ (((li >> 5) & 7) << 2)] = acc[i * 16 + jj];
+            const int li = (idx / R0) * ROWS + (idx % ROWS);
+            sout[(ROWS == 4) ? (li ^ (((li >> 5) & 7) << 2)) : li] = acc[i * 16 + jj];
         }
     }
     __syncthreads();
-    const float4* sout4 = reinterpret_cast<const float4*>(sout);
-    constexpr int NQL = N / CL / 4;
-    for (int q = t; q < NQL; q += T) {
-        float4 v = sout4[q ^ ((q >> 3) & 7)];
-        const size_t qo = (size_t)q * CL + c;  // float4 index inside the column
-        if (a.nsplit > 1) {
-            reinterpret_cast<float4*>(a.partial + ((size_t)cs * a.nsplit + split) * N)[qo] = v;
-        } else {
-            v.x *= a.scale; v.y *= a.scale; v.z *= a.scale; v.w *= a.scale;
-            const size_t o = (size_t)cs * (N / 4) + qo;
-            if (a.out_lin) reinterpret_cast<float4*>(a.out_lin)[o] = v;
-            if (a.out_db)
-                reinterpret_cast<float4*>(a.out_db)[o] =
-                    make_float4(power_to_db(v.x, a.eps), power_to_db(v.y, a.eps), power_to_db(v.z, a.eps), power_to_db(v.w, a.eps));
+    constexpr int NQL = N / CL / ROWS;  // groups of ROWS bins owned by this CTA
+    if constexpr (ROWS == 4) {
+        const float4* sout4 = reinterpret_cast<const float4*>(sout);
+        for (int q = t; q < NQL; q += T) {
+            float4 v = sout4[q ^ ((q >> 3) & 7)];
+            const size_t qo = (size_t)q * CL + c;  // float4 index inside the column
+            if (a.nsplit > 1) {
+                reinterpret_cast<float4*>(a.partial + ((size_t)cs * a.nsplit + split) * N)[qo] = v;
+            } else {
+                v.x *= a.scale; v.y *= a.scale; v.z *= a.scale; v.w *= a.scale;
+                const size_t o = (size_t)cs * (N / 4) + qo;
+                if (a.out_lin) reinterpret_cast<float4*>(a.out_lin)[o] = v;
+                if (a.out_db)
+                    reinterpret_cast<float4*>(a.out_db)[o] = make_float4(power_to_db(v.x, a.eps), power_to_db(v.y, a.eps),
+                                                                         power_to_db(v.z, a.eps), power_to_db(v.w, a.eps));
+            }
+        }
+    } else {
+        const float2* sout2 = reinterpret_cast<const float2*>(sout);
+        for (int q = t; q < NQL; q += T) {
+            float2 v = sout2[q];
+            const size_t qo = (size_t)q * CL + c;  // float2 index inside the column
+            if (a.nsplit > 1) {
+                reinterpret_cast<float2*>(a.partial + ((size_t)cs * a.nsplit + split) * N)[qo] = v;
+            } else {
+                v.x *= a.scale; v.y *= a.scale;
+                const size_t o = (size_t)cs * (N / 2) + qo;
+                if (a.out_lin) reinterpret_cast<float2*>(a.out_lin)[o] = v;
+                if (a.out_db) reinterpret_cast<float2*>(a.out_db)[o] = make_float2(power_to_db(v.x, a.eps), power_to_db(v.y, a.eps));
+            }
         }
     }
 }

@@ -342,7 +342,17 @@ def test_cluster_path(torch, nfft, nfr, ncol, nsub, kind):
     (65536, 5, 5, 2, "whole"),
     (65536, 160, 2, 1, "whole"),
     (65536, 3, 100, 1, "whole"),
-    (65536, 2, 3, 1, "whole_i8")])
+    (65536, 2, 3, 1, "whole_i8"),
+    (16384, 1, 9, 1, "whole_r2"),    # two rows per CTA, 256 threads, two CTAs per SM: clusters of 2 / 4 / 8
+    (16384, 5, 7, 2, "whole_r2"),
+    (16384, 640, 2, 1, "whole_r2"),
+    (16384, 3, 500, 1, "whole_r2"),
+    (16384, 4, 6, 1, "whole_r2_i16"),
+    (32768, 5, 7, 2, "whole_r2"),
+    (32768, 3, 200, 1, "whole_r2"),
+    (65536, 5, 5, 2, "whole_r2"),
+    (65536, 160, 2, 1, "whole_r2"),
+    (65536, 2, 3, 1, "whole_r2_i8")])
 def test_whole_frame_path(torch, nfft, nfr, ncol, nsub, kind):
     """Whole-frame kernel (sti_whole.cuh: 8192 / 16384 points resident in one SM, first pass fed in
     slabs through a bulk-copy ring refilled by the last reader) against the float64 oracle: modes,
@@ -361,11 +371,12 @@ def test_whole_frame_path(torch, nfft, nfr, ncol, nsub, kind):
         x = ((feed[:, 0].astype(np.float32) + 1j * feed[:, 1].astype(np.float32)) * np.float32(in_scale)).astype(np.complex64)
     plan = engine.StiPlan(nfft)
     try:
-        engine.set_variant(kind if kind in ("whole_s2", "whole_s8") else "whole")
+        engine.set_variant(kind if kind in ("whole_s2", "whole_s8") else "whole_r2" if kind.startswith("whole_r2") else "whole")
         lin, db = plan.run(torch.from_numpy(feed).cuda(), torch.from_numpy(starts).cuda(), nfr, nfft, sub_stride=per_sub,
                            nsub=nsub, in_scale=in_scale, want_lin=True, want_db=True)
         torch.cuda.synchronize()
         assert plan.variant.startswith(f"whole{nfft // 4096}x4096"), plan.variant
+        assert ("r2" in plan.variant) == kind.startswith("whole_r2"), plan.variant
     finally:
         engine.set_variant(None)
     for s in range(nsub):
@@ -397,7 +408,7 @@ def test_large_nfft_defaults_and_fallback(torch):
 
 
 @pytest.mark.parametrize("nfft", [256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536, (16384, "cluster"), (32768, "cluster_dsmem"),
-                                  (65536, "cluster_ldg"), (65536, "cluster_dsmem"), (16384, "whole"), (8192, "whole"), (32768, "whole"), (65536, "whole")])
+                                  (65536, "cluster_ldg"), (65536, "cluster_dsmem"), (16384, "whole"), (8192, "whole"), (32768, "whole"), (65536, "whole"), (16384, "whole_r2"), (65536, "whole_r2")])
 def test_repeated_runs_are_bit_identical(torch, nfft):
     """Race canary (compute-sanitizer is not available on the GPU pool): no atomic touches data (the
     whole-frame kernel counts stage readers with one, which only decides WHO issues the next copy) and
