@@ -182,7 +182,11 @@ int psg_set_force_generic(int on);
 /*
  * Kernel-variant table (tuning / cross-checks).  psg_set_variant(name) makes psg_sti_run prefer the
  * named variant for its FFT length when the layout allows it; NULL or "" restores the automatic
- * choice.  "split" selects the two-phase large-nfft path for nfft = 8192..65536.  Process-wide.
+ * choice.  Path names for the large lengths: "split" (two-phase path, nfft = 8192..65536), "cluster_ldg" /
+ * "cluster" / "cluster_dsmem" (one CTA per 4096-point row, nfft = 8192..65536), "whole" (whole-frame kernels:
+ * 8192 / 16384 in one CTA, 32768 / 65536 on clusters of 2 / 4 CTAs), "whole_r2" (two rows per CTA: clusters
+ * of 2 / 4 / 8 for 16384 / 32768 / 65536), "whole_r4", "whole_s2" / "whole_s8" (ring depth of the single-CTA
+ * kernel); "bluestein_r2" selects the radix-2 kernel for non powers of two.  Process-wide.
  */
 int psg_set_variant(const char* name);
 /* Bytes of the L2-resident scratch the large-nfft split path (nfft >= 16384) works through per
