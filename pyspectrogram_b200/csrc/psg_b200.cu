@@ -247,6 +247,8 @@ struct psg_plan {
     float2* d_bpos = nullptr;
     float2* d_twf = nullptr;
     int bs_npass = 0, bs_radix[4] = {0, 0, 0, 0};
+    // direct mixed-radix transform for nfft = 2^a 3^b 5^c (sti_mixed_kernel): radices, 0 passes = not applicable
+    int mx_npass = 0, mx_radix[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long* d_colb = nullptr;
     size_t colb_bytes = 0;
     std::vector<long long> h_colb;
@@ -328,7 +330,7 @@ extern "C" int psg_set_variant(const char* name) {
         bool ok = g_variant_override == "split" || g_variant_override == "cluster" || g_variant_override == "cluster_ldg" ||
                   g_variant_override == "cluster_dsmem" || g_variant_override == "whole" || g_variant_override == "whole_s2" ||
                   g_variant_override == "whole_s8" || g_variant_override == "whole_r2" || g_variant_override == "whole_r4" ||
-                  g_variant_override == "bluestein_r2";
+                  g_variant_override == "bluestein_r2" || g_variant_override == "bluestein";
         for (int i = 0; i < g_nvariants; ++i) ok = ok || g_variant_override == g_variants[i].name;
         if (!ok) {
             g_variant_override.clear();
@@ -531,6 +533,20 @@ extern "C" int psg_plan_create(psg_plan** out, int nfft, int window_kind, double
     if (logn < 0) {
         rc = build_bluestein(p);
         if (rc) { psg_plan_destroy(p); return rc; }
+        // 2^a 3^b 5^c that fits shared memory: radix plan of the direct transform (power-of-two part first)
+        int rem = nfft, a2 = 0, n3 = 0, n5 = 0;
+        while (rem % 2 == 0) { rem /= 2; ++a2; }
+        while (rem % 3 == 0) { rem /= 3; ++n3; }
+        while (rem % 5 == 0) { rem /= 5; ++n5; }
+        const int np = (a2 % 4 ? 1 : 0) + a2 / 4 + n3 + n5;
+        if (rem == 1 && np <= 10 && (size_t)(psg_pad(nfft) + 4) * 8 + (size_t)(nfft + 4) * 4 <= 200 * 1024) {
+            int k = 0;
+            if (a2 % 4) p->mx_radix[k++] = 1 << (a2 % 4);
+            for (int i = 0; i < a2 / 4; ++i) p->mx_radix[k++] = 16;
+            for (int i = 0; i < n5; ++i) p->mx_radix[k++] = 5;
+            for (int i = 0; i < n3; ++i) p->mx_radix[k++] = 3;
+            p->mx_npass = k;
+        }
     }
     p->variant_name[0] = 0;
     *out = p;
@@ -1208,6 +1224,65 @@ static int run_split(psg_plan* p, StiArgs a, int ncs, int frames_per_col, cudaSt
     return PSG_OK;
 }
 
+// nfft = 2^a 3^b 5^c: direct mixed-radix transform in shared memory (sti_mixed_kernel)
+static int run_mixed(psg_plan* p, StiArgs a, int ncs, int frames_per_col, cudaStream_t st) {
+    const int N = p->nfft;
+    const int tpf = std::min(512, std::max(32, ((N / 8 + 31) / 32) * 32));
+    const size_t group_bytes = (size_t)((psg_pad(N) + 3) & ~1) * 8 + (size_t)((N + 3) & ~3) * 4;
+    int groups = std::max(1, (N >= 4096 ? 512 : 256) / tpf);
+    while (groups > 1 && groups * group_bytes > 100 * 1024) groups /= 2;
+    groups = std::min(groups, std::max(1, floor_pow2(frames_per_col)));
+    const int threads = tpf * groups;
+    const size_t smem = groups * group_bytes;
+    const void* fn = (const void*)sti_mixed_kernel;
+    static thread_local int q_dev = -1;
+    if (q_dev != p->device) {
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        q_dev = p->device;
+    }
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem));
+    if (occ < 1) return fail(PSG_ERR_CUDA, "mixed-radix kernel (nfft=%d) does not fit on an SM", N);
+    const long long slots = (long long)p->sms * occ;
+    int nsplit = std::max(1, (frames_per_col + 1023) / 1024);
+    if ((long long)ncs * nsplit < 2 * slots)
+        nsplit = (int)std::max<long long>(nsplit, std::min<long long>(std::max(1, frames_per_col / (4 * groups)), (2 * slots + ncs - 1) / ncs));
+    const int chunk = (frames_per_col + nsplit - 1) / nsplit;
+    nsplit = (frames_per_col + chunk - 1) / chunk;
+    a.gpc = 1;
+    a.chunk = chunk;
+    a.nsplit = nsplit;
+    if (nsplit > 1) {
+        size_t have_b = p->partial_elems * sizeof(float);
+        int rc = ensure_buffer((void**)&p->d_partial, &have_b, (size_t)ncs * nsplit * N * sizeof(float));
+        p->partial_elems = have_b / sizeof(float);
+        if (rc) return rc;
+        a.partial = p->d_partial;
+    }
+    const long long items = (long long)ncs * nsplit;
+    const long long grid = std::min<long long>(items, slots);
+    MixedArgs b;
+    b.twf = p->d_tw;
+    b.n = N;
+    b.tpf = tpf;
+    b.npass = p->mx_npass;
+    for (int i = 0; i < 10; ++i) b.radix[i] = p->mx_radix[i];
+    void* args[] = {(void*)&a, (void*)&b};
+    CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(threads), args, smem, st));
+    g_launches++;
+    if (nsplit > 1) {
+        const size_t total = (size_t)ncs * N;
+        const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)p->sms * 16);
+        sti_finalize_kernel<<<blocks, 256, 0, st>>>(a.partial, nsplit, N, (size_t)ncs, a.scale, a.eps, a.out_lin, a.out_db);
+        g_launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    std::string name = "mixed" + std::to_string(N) + "_";
+    for (int i = 0; i < p->mx_npass; ++i) name += (i ? "x" : "") + std::to_string(p->mx_radix[i]);
+    snprintf(p->variant_name, sizeof(p->variant_name), "%s", name.c_str());
+    return PSG_OK;
+}
+
 // non power-of-two nfft, M <= 16384: Bluestein with mixed-radix passes in shared memory (sti_bluestein.cuh)
 static int run_bluestein16(psg_plan* p, StiArgs a, int ncs, int frames_per_col, cudaStream_t st) {
     const int N = p->nfft;
@@ -1279,11 +1354,13 @@ static int run_bluestein(psg_plan* p, StiArgs a, int ncs, int frames_per_col, cu
     const int N = p->nfft;
     const size_t M = (size_t)1 << p->logm;
     {
-        bool force_r2 = false;
+        bool force_r2 = false, force_bs = false;
         {
             std::lock_guard<std::mutex> lk(g_variant_mu);
             force_r2 = g_variant_override == "bluestein_r2";
+            force_bs = g_variant_override == "bluestein";
         }
+        if (p->mx_npass && !force_r2 && !force_bs) return run_mixed(p, a, ncs, frames_per_col, st);
         if (p->d_bpos && !force_r2) return run_bluestein16(p, a, ncs, frames_per_col, st);
     }
     snprintf(p->variant_name, sizeof(p->variant_name), "bluestein_m%zu_r2", M);

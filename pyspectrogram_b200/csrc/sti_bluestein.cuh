@@ -184,3 +184,160 @@ __global__ void __launch_bounds__(512) sti_bluestein16_kernel(const StiArgs a, c
         }
     }
 }
+
+// ---- nfft = 2^a 3^b 5^c (1000, 1200, 3000, 5000, 10000, ...): direct mixed-radix transform ------------------
+// The lengths people type into the viewer's spin box are mostly "round" numbers.  They need no chirp-z
+// detour: one N-point transform with radices 16/8/4/2, 5 and 3 in the same in-place pass structure
+//   pass p: n_rest = n_p S_p + n', R_p-point DFT over n_p, output k_p times W_N^{n' k_p N/(R_p S_p)}, stored in
+//   place of n_p; after the last pass position sum_q k_q S_q holds frequency k_0 + R_0 k_1 + R_0 R_1 k_2 + ...
+// instead of two M-point transforms with M >= 2N-1 (a sixth of the butterflies at N = 1000).  Pass 0 reads
+// the samples from global memory and applies the window; the last pass adds |X|^2 to accumulators indexed by
+// position, and the epilogue un-permutes (mixed-radix digit reversal) and fftshifts once per work item.
+struct MixedArgs {
+    const float2* twf;  // [N] exp(-2*pi*j*m/N)
+    int n, tpf;
+    int npass;
+    int radix[10];
+};
+
+PSG_DEV void dft3(cf* a) {
+    const cf t = cadd(a[1], a[2]);
+    const cf u = fma2(t, make_float2(-0.5f, -0.5f), a[0]);
+    const cf d = cscale(csub(a[1], a[2]), 0.86602540378443864676f);
+    a[0] = cadd(a[0], t);
+    a[1] = cadd(u, mul_nj(d));
+    a[2] = csub(u, mul_nj(d));
+}
+PSG_DEV void dft5(cf* a) {
+    constexpr float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
+    constexpr float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
+    const cf t1 = cadd(a[1], a[4]), t2 = cadd(a[2], a[3]), t3 = csub(a[1], a[4]), t4 = csub(a[2], a[3]);
+    const cf m1 = fma2(t2, make_float2(c2, c2), fma2(t1, make_float2(c1, c1), a[0]));
+    const cf m2 = fma2(t2, make_float2(c1, c1), fma2(t1, make_float2(c2, c2), a[0]));
+    const cf n1 = fma2(t4, make_float2(s2, s2), cscale(t3, s1));
+    const cf n2 = fma2(t4, make_float2(-s1, -s1), cscale(t3, s2));
+    a[0] = cadd(a[0], cadd(t1, t2));
+    a[1] = cadd(m1, mul_nj(n1));
+    a[4] = csub(m1, mul_nj(n1));
+    a[2] = cadd(m2, mul_nj(n2));
+    a[3] = csub(m2, mul_nj(n2));
+}
+template <int R>
+PSG_DEV void dft_any(cf* v) {
+    if constexpr (R == 3) dft3(v);
+    else if constexpr (R == 5) dft5(v);
+    else dftR<R>(v);
+}
+
+template <int R>
+PSG_DEV void mixed_pass(float2* __restrict__ buf, int S, int N, int Nv, int tid, int nt, const float2* __restrict__ twf,
+                        bool first, bool last, const StiArgs& a, long long src, float* __restrict__ accs) {
+    const int tstride = N / (R * S);  // W_{R S}^{e} = W_N^{e * tstride}
+    for (int bf = tid; bf < Nv / R; bf += nt) {
+        const int blk = bf / S;
+        const int npr = bf - blk * S;
+        const int base = blk * R * S + npr;
+        cf v[R];
+        if (first) {
+#pragma unroll
+            for (int n = 0; n < R; ++n) {
+                const int i = base + n * S;
+                v[n] = cscale(ldg_iq_rt(a.iq_type, a.iq, src + (long long)i * a.sample_stride), __ldg(a.win + i));
+            }
+        } else {
+#pragma unroll
+            for (int n = 0; n < R; ++n) v[n] = buf[psg_pad(base + n * S)];
+        }
+        dft_any<R>(v);
+        if (last) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const int i = base + k * S;
+                accs[i] = fmaf(v[k].x, v[k].x, fmaf(v[k].y, v[k].y, accs[i]));
+            }
+        } else {
+            if constexpr (R == 16 || R == 8) {
+                constexpr int NPW = psg_npow(R);
+                cf pw[NPW];
+#pragma unroll
+                for (int q = 0; q < NPW; ++q) pw[q] = __ldg(twf + ((npr * tstride) << q));
+                twiddle_dfs<R>(v, pw);
+            } else {
+#pragma unroll
+                for (int k = 1; k < R; ++k) v[k] = cmul(v[k], __ldg(twf + npr * k * tstride));
+            }
+#pragma unroll
+            for (int k = 0; k < R; ++k) buf[psg_pad(base + k * S)] = v[k];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(512) sti_mixed_kernel(const StiArgs a, const MixedArgs b) {
+    const int N = b.n;
+    extern __shared__ __align__(16) float2 bs_smem[];
+    const int T = b.tpf, G = blockDim.x / T;
+    const int g = threadIdx.x / T, t = threadIdx.x - g * T;
+    const int bstride = (psg_pad(N) + 3) & ~1;  // complex per group buffer (even: 16-byte aligned)
+    const int astride = (N + 3) & ~3;           // floats per group accumulator
+    float2* buf = bs_smem + (size_t)g * bstride;
+    float* acc0 = reinterpret_cast<float*>(bs_smem + (size_t)G * bstride);
+    float* accs = acc0 + (size_t)g * astride;
+    const int ncs = a.ncol * a.nsub;
+    const int P = b.npass;
+    for (int item = blockIdx.x; item < ncs * a.nsplit; item += gridDim.x) {
+        const int split = item % a.nsplit;
+        const int cs = item / a.nsplit;
+        const int col = cs % a.ncol, sub = cs / a.ncol;
+        const int k0 = split * a.chunk;
+        const int k1 = min(a.nfr, k0 + a.chunk);
+        const long long src0 = a.col_off[col] + (long long)sub * a.sub_stride;
+        __syncthreads();  // the previous item's epilogue is done with the accumulators
+        for (int i = t; i < N; i += T) accs[i] = 0.f;
+        const int niter = (k1 - k0 + G - 1) / G;
+        for (int j = 0; j < niter; ++j) {
+            const int k = k0 + j * G + g;
+            const int Nv = (k < k1) ? N : 0;  // a group without a frame runs the barriers only
+            const long long src = src0 + (long long)k * a.hop_elems;
+            int S = N;
+            for (int p = 0; p < P; ++p) {
+                const int R = b.radix[p];
+                S /= R;
+                __syncthreads();
+                const bool first = p == 0, last = p == P - 1;
+                switch (R) {
+                    case 2: mixed_pass<2>(buf, S, N, Nv, t, T, b.twf, first, last, a, src, accs); break;
+                    case 3: mixed_pass<3>(buf, S, N, Nv, t, T, b.twf, first, last, a, src, accs); break;
+                    case 4: mixed_pass<4>(buf, S, N, Nv, t, T, b.twf, first, last, a, src, accs); break;
+                    case 5: mixed_pass<5>(buf, S, N, Nv, t, T, b.twf, first, last, a, src, accs); break;
+                    case 8: mixed_pass<8>(buf, S, N, Nv, t, T, b.twf, first, last, a, src, accs); break;
+                    default: mixed_pass<16>(buf, S, N, Nv, t, T, b.twf, first, last, a, src, accs); break;
+                }
+            }
+        }
+        __syncthreads();
+        const int half = N / 2;  // np.fft.fftshift: out[(k + N//2) mod N] = in[k]
+        for (int pos = threadIdx.x; pos < N; pos += blockDim.x) {
+            float sum = acc0[pos];
+            for (int gg = 1; gg < G; ++gg) sum += acc0[(size_t)gg * astride + pos];
+            // frequency held by this position: digits k_q = (pos / S_q) mod R_q, weight R_0 .. R_{q-1}
+            int rem = pos, s = N, mul = 1, freq = 0;
+            for (int p = 0; p < P; ++p) {
+                const int R = b.radix[p];
+                s /= R;
+                const int d = rem / s;
+                rem -= d * s;
+                freq += d * mul;
+                mul *= R;
+            }
+            int idx = freq + half;
+            if (idx >= N) idx -= N;
+            if (a.nsplit > 1) {
+                a.partial[((size_t)cs * a.nsplit + split) * N + idx] = sum;
+            } else {
+                const float pw = sum * a.scale;
+                if (a.out_lin) a.out_lin[(size_t)cs * N + idx] = pw;
+                if (a.out_db) a.out_db[(size_t)cs * N + idx] = power_to_db(pw, a.eps);
+            }
+        }
+    }
+}

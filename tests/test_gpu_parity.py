@@ -85,7 +85,7 @@ def test_non_power_of_two_matches_reference_golden(dp):
     assert_psd_close(med, g["med"], noise_like=False, what="nfft=96 median")
 
 
-@pytest.mark.parametrize("nfft", [3, 5, 7, 33, 100, 1000, 1023, 1025, 4095, 5000, 8191, 12000, 20000, 100000])
+@pytest.mark.parametrize("nfft", [3, 5, 7, 33, 100, 1000, 1023, 1025, 3000, 4095, 5000, 8191, 10000, 12000, 15000, 20000, 100000])
 @pytest.mark.parametrize("mode", ["R", "A"])
 def test_arbitrary_nfft_against_float64_oracle(torch, nfft, mode):
     """Odd, even, prime and large non power-of-two lengths (work buffer in shared memory up to
@@ -99,38 +99,47 @@ def test_arbitrary_nfft_against_float64_oracle(torch, nfft, mode):
     starts = (np.arange(ncol) * nfft * nfr + np.arange(ncol) % 2).astype(np.int64)
     plan = engine.StiPlan(nfft)
     lin, db = plan.run(torch.from_numpy(x).cuda(), torch.from_numpy(starts).cuda(), nfr, nfft, want_lin=True, want_db=True)
-    assert plan.variant.startswith("bluestein")
-    # convolution lengths up to 16384 run the mixed-radix kernel, longer ones the radix-2 kernel
-    assert plan.variant.endswith("_r2") == (2 * nfft - 1 > 16384), plan.variant
+    # 2^a 3^b 5^c that fit shared memory run the direct mixed-radix transform; the rest Bluestein: convolution
+    # lengths up to 16384 with mixed-radix passes, longer ones with the radix-2 kernel
+    smooth = nfft
+    for f in (2, 3, 5):
+        while smooth % f == 0:
+            smooth //= f
+    if smooth == 1 and nfft <= 15000:
+        assert plan.variant.startswith(f"mixed{nfft}_"), plan.variant
+    else:
+        assert plan.variant.startswith("bluestein")
+        assert plan.variant.endswith("_r2") == (2 * nfft - 1 > 16384), plan.variant
     ref = _oracle_columns(x, starts, nfft, nfr, nfft)
     assert_psd_close(lin.cpu().numpy()[0].T, ref.T, noise_like=False, what=f"nfft={nfft} {plan.variant}")
     assert_db_close(db.cpu().numpy()[0].T, 10 * np.log10(ref.T.astype(np.float32) + np.float32(1e-15)),
                     ref_lin=ref.T, what=f"nfft={nfft} dB")
 
 
-@pytest.mark.parametrize("nfft,nfr,ncol", [(1000, 700, 2), (96, 5, 300), (6000, 2, 3)])
-def test_bluestein_kernels_agree(torch, nfft, nfr, ncol):
-    """The mixed-radix Bluestein kernel (default up to M = 16384) against the radix-2 one on the same
-    input, including columns split into frame chunks and more items than resident CTAs."""
+@pytest.mark.parametrize("nfft,nfr,ncol", [(1000, 700, 2), (96, 5, 300), (6000, 2, 3), (45, 9, 40), (7500, 3, 5)])
+def test_arbitrary_nfft_kernels_agree(torch, nfft, nfr, ncol):
+    """The three kernels for non powers of two on the same input: direct mixed-radix transform (default for
+    2^a 3^b 5^c), Bluestein with mixed-radix passes ("bluestein"), Bluestein radix 2 ("bluestein_r2"),
+    including columns split into frame chunks and more items than resident CTAs."""
     from pyspectrogram_b200 import engine
     rng = np.random.default_rng(nfft + nfr)
     x = torch.from_numpy(_recording(rng, nfft * nfr * ncol + 5)).cuda()
     starts = torch.from_numpy((np.arange(ncol) * nfft * nfr + np.arange(ncol) % 2).astype(np.int64)).cuda()
     plan = engine.StiPlan(nfft)
-    lin, _ = plan.run(x, starts, nfr, nfft)
-    torch.cuda.synchronize()
-    assert not plan.variant.endswith("_r2"), plan.variant
+    res = {}
     try:
-        engine.set_variant("bluestein_r2")
-        lin2, _ = plan.run(x, starts, nfr, nfft)
-        torch.cuda.synchronize()
-        assert plan.variant.endswith("_r2"), plan.variant
+        for var, want in ((None, "mixed"), ("bluestein", "bluestein_m"), ("bluestein_r2", "bluestein_m")):
+            engine.set_variant(var)
+            lin, _ = plan.run(x, starts, nfr, nfft)
+            torch.cuda.synchronize()
+            assert plan.variant.startswith(want) and plan.variant.endswith("_r2") == (var == "bluestein_r2"), plan.variant
+            res[var] = lin.cpu().numpy()[0]
     finally:
         engine.set_variant(None)
-    a, b = lin.cpu().numpy()[0], lin2.cpu().numpy()[0]
-    assert_psd_close(a.T, b.T.astype(np.float64), noise_like=False, what=f"bluestein16 vs radix-2 nfft={nfft}")
     ref = _oracle_columns(x.cpu().numpy(), starts.cpu().numpy()[:2], nfft, nfr, nfft)
-    assert_psd_close(a[:2].T, ref.T, noise_like=False, what=f"bluestein16 nfft={nfft}")
+    for var, a in res.items():
+        assert_psd_close(a[:2].T, ref.T, noise_like=False, what=f"{var or 'mixed'} nfft={nfft}")
+        assert_psd_close(a.T, res["bluestein_r2"].T.astype(np.float64), noise_like=False, what=f"{var or 'mixed'} vs radix-2 nfft={nfft}")
 
 
 def test_short_input_raises_value_error(dp):
