@@ -69,7 +69,8 @@ int psg_device_count(void);
  * windows/_windows.py:1318-1320, :2551), computed in float64 on the host, the spectrum scaling
  * 1/sum(w)^2 (scipy _spectral_py.py:2277) folded in, and the float64-accurate twiddle table.
  * nfft: any integer in [PSG_MIN_NFFT, PSG_MAX_NFFT] (the viewer allows any length, drfview.py:474-479).
- * Powers of two run the tuned kernels; other lengths run Bluestein's algorithm on the GPU.
+ * Powers of two run the tuned kernels; 2^a 3^b 5^c up to 15000 a direct mixed-radix transform; every other
+ * length Bluestein's algorithm on the GPU.
  */
 #define PSG_MIN_NFFT 2
 #define PSG_MAX_NFFT 1048576
@@ -186,7 +187,8 @@ int psg_set_force_generic(int on);
  * "cluster" / "cluster_dsmem" (one CTA per 4096-point row, nfft = 8192..65536), "whole" (whole-frame kernels:
  * 8192 / 16384 in one CTA, 32768 / 65536 on clusters of 2 / 4 CTAs), "whole_r2" (two rows per CTA: clusters
  * of 2 / 4 / 8 for 16384 / 32768 / 65536), "whole_r4", "whole_s2" / "whole_s8" (ring depth of the single-CTA
- * kernel); "bluestein_r2" selects the radix-2 kernel for non powers of two.  Process-wide.
+ * kernel); "bluestein" / "bluestein_r2" select the Bluestein kernels (mixed-radix passes / radix 2) for non
+ * powers of two.  Process-wide.
  */
 int psg_set_variant(const char* name);
 /* Bytes of the L2-resident scratch the large-nfft split path (nfft >= 16384) works through per
