@@ -122,6 +122,9 @@ static const Variant g_variants[] = {
     make_variant<11, 16, 8, 16, 16, 1, 1, M, 2, 1, 4, 0, IQ_C64, 2>("tma11_8x16x16_f1_s2x1_tq"),
     make_variant<10, 16, 4, 16, 16, 1, 1, M, 2, 1, 8, 0, IQ_C64, 2>("tma10_4x16x16_f1_s2x1_tq"),
     make_variant<13, 16, 16, 8, 8, 8, 1, M, 2, 1, 1, 0, IQ_C64, 2>("tma13_16x8x8x8_f1_s2x1_tq"),
+    // radix-2 pass in registers on the end of pass 1 (lane pairs exchange by SHFL): three shared-memory passes
+    make_variant<13, 16, 16, 16, 2, 16, 1, M, 2, 1, 1, 0, IQ_C64, 2>("tma13_16x16x2x16_f1_s2x1_tq"),
+    make_variant<13, 16, 16, 16, 2, 16, 1, M, 1, 2, 1, 0, IQ_C64, 2>("tma13_16x16x2x16_f1_s1x2_tq"),
     make_variant<11, 16, 8, 16, 16, 1, 1, M, 2, 1, 4, 0, IQ_C64, 1>("tma11_8x16x16_f1_s2x1_tp"),
     make_variant<10, 16, 4, 16, 16, 1, 1, M, 2, 1, 8, 0, IQ_C64, 1>("tma10_4x16x16_f1_s2x1_tp"),
     make_variant<13, 16, 16, 8, 8, 8, 1, M, 2, 1, 1, 0, IQ_C64, 1>("tma13_16x8x8x8_f1_s2x1_tp"),
@@ -145,6 +148,7 @@ static const Variant g_variants[] = {
     make_variant<11, 16, 8, 16, 16, 1, 1, M, 1, 2, 4, 0, IQ_C64, 2, 1>("tma11_8x16x16_f1_s1x2_tq_m"),
     make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 1, 2, 0, IQ_C64, 2, 1>("tma12_16x16x16_f1_s2x1_tq_m"),
     make_variant<13, 16, 16, 8, 8, 8, 1, M, 2, 1, 1, 0, IQ_C64, 2, 1>("tma13_16x8x8x8_f1_s2x1_tq_m"),
+    make_variant<13, 16, 16, 16, 2, 16, 1, M, 2, 1, 1, 0, IQ_C64, 2, 1>("tma13_16x16x2x16_f1_s2x1_tq_m"),
     // raw integer IQ ingest (complex int16 / int8): the default geometry of every size, both loaders
     make_variant<5, 8, 4, 8, 1, 1, 32, L, 1, 2, 8, 0, IQ_CI16>("ldg5_4x8_f32_i16"),
     make_variant<6, 8, 8, 8, 1, 1, 32, L, 1, 2, 4, 0, IQ_CI16>("ldg6_8x8_f32_i16"),
@@ -158,6 +162,7 @@ static const Variant g_variants[] = {
     make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 1, 2, 0, IQ_CI16, 2>("tma12_16x16x16_f1_s2x1_tq_i16"),
     make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 2, 2, 0, IQ_CI16, 1>("ldg12_16x16x16_f1_tp_i16"),
     make_variant<13, 16, 16, 8, 8, 8, 1, M, 2, 1, 1, 0, IQ_CI16, 2>("tma13_16x8x8x8_f1_s2x1_tq_i16"),
+    make_variant<13, 16, 16, 16, 2, 16, 1, M, 2, 1, 1, 0, IQ_CI16, 2>("tma13_16x16x2x16_f1_s2x1_tq_i16"),
     make_variant<13, 16, 2, 16, 16, 16, 1, L, 1, 1, 1, 0, IQ_CI16, 1>("ldg13_2x16x16x16_f1_tp_i16"),
     make_variant<5, 8, 4, 8, 1, 1, 32, L, 1, 2, 8, 0, IQ_CI8>("ldg5_4x8_f32_i8"),
     make_variant<6, 8, 8, 8, 1, 1, 32, L, 1, 2, 4, 0, IQ_CI8>("ldg6_8x8_f32_i8"),
@@ -171,6 +176,7 @@ static const Variant g_variants[] = {
     make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 1, 2, 0, IQ_CI8, 2>("tma12_16x16x16_f1_s2x1_tq_i8"),
     make_variant<12, 16, 16, 16, 16, 1, 1, L, 1, 2, 2, 0, IQ_CI8, 1>("ldg12_16x16x16_f1_tp_i8"),
     make_variant<13, 16, 16, 8, 8, 8, 1, M, 2, 1, 1, 0, IQ_CI8, 2>("tma13_16x8x8x8_f1_s2x1_tq_i8"),
+    make_variant<13, 16, 16, 16, 2, 16, 1, M, 2, 1, 1, 0, IQ_CI8, 2>("tma13_16x16x2x16_f1_s2x1_tq_i8"),
     make_variant<13, 16, 2, 16, 16, 16, 1, L, 1, 1, 1, 0, IQ_CI8, 1>("ldg13_2x16x16x16_f1_tp_i8"),
 };
 #undef L

@@ -276,6 +276,41 @@ PSG_DEV void smem_pass(float2* __restrict__ buf, const cf* tw, int t, float* acc
     }
 }
 
+// Pass p (radix 16, stride 32) with the following radix-2 pass (stride 16) done in registers: the two
+// inputs of a radix-2 butterfly sit in lanes l and l ^ 16 of one warp (same k, n' and n' + 16), so each
+// lane sends half of its 16 outputs to its partner with SHFL (8 complex = 16 SHFL.32, half the LSU
+// cost of re-reading them) and finishes the butterflies of the other half: lanes 0..15 those of
+// k = 0..7, lanes 16..31 those of k = 8..15.  The pair reads and writes the same 32 positions, so the
+// pass stays in place, and a warp writes exactly the 512 positions its own threads read in the last
+// (radix-16, stride 1) pass.  One shared-memory write + read less than a four-pass plan
+// (8192 = 16*16*2*16: 6.5 instead of 8 accesses per sample).  w2 = W_32^(lane & 15), negated in the
+// upper half-warp (there the difference is taken the other way round).
+template <int E, int T, int R, int S>
+PSG_DEV void smem_pass_fused_r2(float2* __restrict__ buf, const cf* tw, int t, const cf w2) {
+    static_assert(E == 16 && R == 16 && S == 32 && (T % 32) == 0, "pair exchange is laid out for radix 16, stride 32");
+    const int b = t;
+    const int npr = b & 31;
+    const bool hi = (npr & 16) != 0;
+    float2* p = buf + psg_pad((b / S) * (R * S) + npr);
+    cf a[R];
+#pragma unroll
+    for (int n = 0; n < R; ++n) a[n] = p[pad_off(n * S)];
+    dftR<R>(a);
+#pragma unroll
+    for (int k = 1; k < R; ++k) a[k] = cmul(a[k], tw[k - 1]);
+    float2* q = buf + psg_pad((b / S) * (R * S) + (npr & 15)) + (hi ? pad_off(8 * S) : 0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const cf send = hi ? a[i] : a[8 + i];
+        const cf keep = hi ? a[8 + i] : a[i];
+        cf recv;
+        recv.x = __shfl_xor_sync(0xffffffffu, send.x, 16);
+        recv.y = __shfl_xor_sync(0xffffffffu, send.y, 16);
+        q[pad_off(i * S)] = cadd(keep, recv);
+        q[pad_off(i * S) + 18] = cmul(csub(keep, recv), w2);
+    }
+}
+
 // The exchange between pass p (radix Ra, stride Sa) and pass p+1 (radix Rb) stays inside aligned
 // groups of Sa consecutive threads when both passes run one butterfly per thread (Ra == Rb == E):
 // pass p's threads [q*Sa, (q+1)*Sa) write exactly the blocks those same threads read in pass p+1.
@@ -323,8 +358,10 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
     constexpr bool L01 = WarpLocal<E, R0, R1, PL::S0>::value;
     constexpr bool L12 = WarpLocal<E, R1, R2, PL::S1>::value;
     constexpr bool L23 = WarpLocal<E, R2, R3, PL::S2>::value;
+    // 16 x 16 x 2 x 16: the radix-2 pass runs in registers on the end of pass 1 (smem_pass_fused_r2)
+    constexpr bool FUSE2 = (P == 4) && (E == 16) && (R1 == 16) && (R2 == 2) && (R3 == 16) && (PL::S1 == 32);
     // true when no exchange needs a CTA barrier: every frame group then owns its buffers privately
-    constexpr bool ALL_LOCAL = L01 && (P < 3 || L12) && (P < 4 || L23);
+    constexpr bool ALL_LOCAL = L01 && (P < 3 || L12) && (P < 4 || L23) && !FUSE2;
     static_assert(ALL_LOCAL ? (T <= 32) : true, "");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
@@ -418,7 +455,7 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
     }
     // TWP == 2: the power-of-two twiddles of every mid-pass butterfly of this thread stay in registers
     constexpr int NPW1 = psg_npow(R1), NPW2 = psg_npow(R2);
-    cf wb1[(TWP == 2 && P >= 3) ? (E / R1) * NPW1 : 1], wb2[(TWP == 2 && P >= 4) ? (E / R2) * NPW2 : 1];
+    cf wb1[(TWP == 2 && P >= 3) ? (E / R1) * NPW1 : 1], wb2[(TWP == 2 && P >= 4 && !FUSE2) ? (E / R2) * NPW2 : 1];
     if constexpr (TWP == 2 && P >= 3) {
 #pragma unroll
         for (int i = 0; i < E / R1; ++i) {
@@ -427,7 +464,13 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
             for (int q = 0; q < NPW1; ++q) wb1[i * NPW1 + q] = __ldg(a.twp + PL::TW1 + (PL::ROW1 ? npr * 6 + q : q * PL::S1 + npr));
         }
     }
-    if constexpr (TWP == 2 && P >= 4) {
+    cf w2f = make_float2(1.f, 0.f);  // FUSE2: W_32^(lane & 15), sign of the upper half-warp folded in
+    if constexpr (FUSE2) {
+        static_assert(!FUSE2 || TWP == 2, "fused radix-2 plans use the power-layout tables");
+        w2f = __ldg(a.twp + PL::TW2 + (t & 15) * 6);
+        if (t & 16) w2f = make_float2(-w2f.x, -w2f.y);
+    }
+    if constexpr (TWP == 2 && P >= 4 && !FUSE2) {
 #pragma unroll
         for (int i = 0; i < E / R2; ++i) {
             const int npr = (t + i * T) & (PL::S2 - 1);
@@ -549,9 +592,10 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
                 static_assert(LOADER != PSG_LOADER_TMA || STAGES > 1 || !L01, "single stage needs a CTA barrier");
                 if (t == 0 && pj < niter) produce();  // the stage has been read by everyone: refill it
             }
-            smem_pass<E, T, R1, PL::S1, P == 2>(buf, tw1, t, acc);
+            if constexpr (FUSE2) smem_pass_fused_r2<E, T, R1, PL::S1>(buf, tw1, t, w2f);
+            else smem_pass<E, T, R1, PL::S1, P == 2>(buf, tw1, t, acc);
         }
-        if constexpr (P >= 3) {
+        if constexpr (P >= 3 && !FUSE2) {
             cf tw2[(P >= 4) ? (E / R2) * (R2 - 1) : 1];
             if constexpr (P >= 4)
                 load_pass_tw<E, T, R2, PL::S2, PL::ROW2, TWP>(PL::ROW2 ? twsm + (PL::ROW1 ? PL::TW1_LEN : 0) : a.twp + PL::TW2, t, tw2, wb2);
@@ -559,7 +603,7 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
             smem_pass<E, T, R2, PL::S2, P == 3>(buf, tw2, t, acc);
         }
         if constexpr (P >= 4) {
-            exchange_sync<L23>();
+            exchange_sync<L23 || FUSE2>();  // FUSE2: a warp reads back what it wrote (see smem_pass_fused_r2)
             smem_pass<E, T, R3, PL::S3, true>(buf, nullptr, t, acc);
         }
         if constexpr (MULTI) {  // every frame is a finished column

@@ -129,3 +129,74 @@ def test_padding_is_conflict_free_for_default_variants():
         seen.add(key)
         radices = [int(v) for v in name.split("_")[1].split("x")]
         assert conflict_degree(1 << key[0], radices) == [1] * len(radices), name
+
+
+def test_fused_radix2_pair_exchange_8192():
+    """8192 = 16 x 16 x 2 x 16 with the radix-2 pass done in registers (smem_pass_fused_r2): lane l of a
+    warp holds the 16 outputs of pass 1 for n' = l; lanes l and l ^ 16 swap half of them (upper lanes
+    send k = 0..7, lower lanes k = 8..15), finish the radix-2 butterflies of the half they keep with
+    w2 = +-W_32^(l & 15) and store to k*32 + {0, 16} + (l & 15).  Simulated lane by lane and compared
+    with the plain four-pass model and with np.fft."""
+    n, radices = 8192, [16, 16, 2, 16]
+    rng = np.random.default_rng(13)
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    buf = x.astype(np.complex128).copy()
+    tabs = pass_tables(n, radices)
+    # pass 0 (radix 16, stride 512), as in model_fft
+    s0 = 512
+    b = np.arange(s0)
+    idx = b[:, None] + np.arange(16)[None, :] * s0
+    dft16 = np.exp(-2j * np.pi * np.outer(np.arange(16), np.arange(16)) / 16)
+    tw = np.ones((s0, 16), np.complex128)
+    tw[:, 1:] = tabs[0].reshape(15, s0)[:, b].T
+    buf[idx] = (buf[idx] @ dft16.T) * tw
+    # pass 1 + fused radix-2, thread by thread (b = t; lane = t & 31)
+    s1 = 32
+    out = buf.copy()
+    regs = np.empty((s0, 16), np.complex128)
+    for t in range(s0):
+        npr = t & 31
+        pos = (t // s1) * 512 + npr + np.arange(16) * s1
+        a = dft16 @ buf[pos]
+        a[1:] *= tabs[1].reshape(15, s1)[:, npr]
+        regs[t] = a
+    w32 = np.exp(-2j * np.pi * np.arange(16) / 32)
+    for t in range(s0):
+        npr = t & 31
+        hi = bool(npr & 16)
+        partner = t ^ 16
+        w2 = -w32[npr & 15] if hi else w32[npr & 15]
+        q = (t // s1) * 512 + (npr & 15) + (8 * s1 if hi else 0)
+        for i in range(8):
+            keep = regs[t][8 + i] if hi else regs[t][i]
+            # the partner sends (it is hi ? a[i] : a[8 + i]); it sits in the other half-warp
+            recv = regs[partner][8 + i] if hi else regs[partner][i]
+            out[q + i * s1] = keep + recv
+            out[q + i * s1 + 16] = (keep - recv) * w2
+    # reference: the plain pass 1 then pass 2 of the four-pass model
+    ref = buf.copy()
+    for p, (r, s) in ((1, (16, 32)), (2, (2, 16))):
+        m = r * s
+        bb = np.arange(n // r)
+        npr = bb & (s - 1)
+        ii = ((bb // s) * m + npr)[:, None] + np.arange(r)[None, :] * s
+        d = np.exp(-2j * np.pi * np.outer(np.arange(r), np.arange(r)) / r)
+        twp = np.ones((n // r, r), np.complex128)
+        twp[:, 1:] = tabs[p].reshape(r - 1, s)[:, npr].T
+        ref[ii] = (ref[ii] @ d.T) * twp
+    assert np.abs(out - ref).max() <= 1e-12 * np.abs(ref).max()
+    # and the whole plan is an FFT
+    got = model_fft(x, radices)
+    assert np.abs(got - np.fft.fft(x)).max() <= 1e-9 * np.abs(x).sum()
+    # the 512 positions a warp writes are the ones its threads read in the last pass (stride 1):
+    # __syncwarp is enough between them
+    for wq in range(16):
+        ts = np.arange(32 * wq, 32 * wq + 32)
+        written = set()
+        for t in ts:
+            npr = t & 31
+            q = (t // s1) * 512 + (npr & 15) + (8 * s1 if npr & 16 else 0)
+            for i in range(8):
+                written.update((q + i * s1, q + i * s1 + 16))
+        read = set((ts[:, None] * 16 + np.arange(16)[None, :]).reshape(-1).tolist())
+        assert written == read
