@@ -12,7 +12,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "psg_b200.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "sti_kernels.cuh"), os.path.join(HERE, "csrc", "sti_cluster.cuh"), os.path.join(HERE, "csrc", "sti_whole.cuh"), os.path.join(HERE, "csrc", "sti_bluestein.cuh"), os.path.join(HERE, "csrc", "cplx.cuh"),
+DEPS = [SRC, os.path.join(HERE, "csrc", "sti_kernels.cuh"), os.path.join(HERE, "csrc", "sti_cluster.cuh"), os.path.join(HERE, "csrc", "sti_whole.cuh"), os.path.join(HERE, "csrc", "sti_whole16.cuh"), os.path.join(HERE, "csrc", "sti_bluestein.cuh"), os.path.join(HERE, "csrc", "cplx.cuh"),
         os.path.join(HERE, "..", "include", "psg_b200.h")]
 OUT = os.path.join(HERE, "libpsgb200.so")
 

@@ -20,6 +20,7 @@
 #include "sti_kernels.cuh"
 #include "sti_cluster.cuh"
 #include "sti_whole.cuh"
+#include "sti_whole16.cuh"
 #include "sti_bluestein.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -113,6 +114,9 @@ static const Variant g_variants[] = {
     make_variant<8, 16, 16, 16, 1, 1, 2, M, 2, 1, 16>("tma8_16x16_f2_s2x1"),
     make_variant<8, 16, 16, 16, 1, 1, 4, M, 2, 1, 8>("tma8_16x16_f4_s2x1"),
     make_variant<9, 16, 2, 16, 16, 1, 1, M, 1, 2, 16, 0, IQ_C64, 2>("tma9_2x16x16_f1_s1x2_tq"),
+    // 512 points by one warp: radix-2 pass in registers on the end of pass 0, one shared-memory round trip
+    make_variant<9, 16, 16, 2, 16, 1, 1, M, 1, 2, 16, 0, IQ_C64, 2>("tma9_16x2x16_f1_s1x2_tq"),
+    make_variant<9, 16, 16, 2, 16, 1, 1, M, 2, 1, 16, 0, IQ_C64, 2>("tma9_16x2x16_f1_s2x1_tq"),
     make_variant<7, 16, 8, 16, 1, 1, 4, M, 2, 1, 16>("tma7_8x16_f4_s2x1"),
     make_variant<7, 16, 8, 16, 1, 1, 8, M, 2, 1, 8>("tma7_8x16_f8_s2x1"),
     make_variant<6, 8, 8, 8, 1, 1, 8, M, 2, 1, 16>("tma6_8x8_f8_s2x1"),
@@ -144,6 +148,8 @@ static const Variant g_variants[] = {
     make_variant<7, 16, 8, 16, 1, 1, 8, M, 2, 1, 8, 0, IQ_C64, 0, 1>("tma7_8x16_f8_s2x1_m"),
     make_variant<8, 16, 16, 16, 1, 1, 4, M, 2, 1, 8, 0, IQ_C64, 0, 1>("tma8_16x16_f4_s2x1_m"),
     make_variant<9, 16, 2, 16, 16, 1, 1, M, 1, 2, 16, 0, IQ_C64, 2, 1>("tma9_2x16x16_f1_s1x2_tq_m"),
+    make_variant<9, 16, 16, 2, 16, 1, 1, M, 1, 2, 16, 0, IQ_C64, 2, 1>("tma9_16x2x16_f1_s1x2_tq_m"),
+    make_variant<9, 16, 16, 2, 16, 1, 1, M, 2, 1, 16, 0, IQ_C64, 2, 1>("tma9_16x2x16_f1_s2x1_tq_m"),
     make_variant<10, 16, 4, 16, 16, 1, 1, M, 1, 2, 8, 0, IQ_C64, 2, 1>("tma10_4x16x16_f1_s1x2_tq_m"),
     make_variant<11, 16, 8, 16, 16, 1, 1, M, 1, 2, 4, 0, IQ_C64, 2, 1>("tma11_8x16x16_f1_s1x2_tq_m"),
     make_variant<12, 16, 16, 16, 16, 1, 1, M, 2, 1, 2, 0, IQ_C64, 2, 1>("tma12_16x16x16_f1_s2x1_tq_m"),
@@ -195,15 +201,15 @@ static const Variant* variant_by_name(const char* name) {
 // W^1,2,4,8 (_tq) or one row load (_tp) instead of 15 loads win everywhere (the kernels are LSU-bound,
 // not HBM- or FMA-bound).
 static const char* const g_default_tma[] = {"tma5_4x8_f32_s2x1", "tma6_8x8_f16_s2x1", "tma7_8x16_f8_s2x1", "tma8_16x16_f4_s2x1",
-                                            "tma9_2x16x16_f1_s1x2_tq", "tma10_4x16x16_f1_s1x2_tq", "tma11_8x16x16_f1_s1x2_tq",
-                                            "tma12_16x16x16_f1_s2x1_tq", "tma13_16x8x8x8_f1_s2x1_tq"};
+                                            "tma9_16x2x16_f1_s2x1_tq", "tma10_4x16x16_f1_s1x2_tq", "tma11_8x16x16_f1_s1x2_tq",
+                                            "tma12_16x16x16_f1_s2x1_tq", "tma13_16x16x2x16_f1_s2x1_tq"};
 static const char* const g_default_ldg[] = {"ldg5_4x8_f32", "ldg6_8x8_f32", "ldg7_8x16_f16", "ldg8_16x16_f8", "ldg9_8x8x8_f1_tp",
                                             "ldg10_4x16x16_f1_tp", "ldg11_8x16x16_f1_tp", "ldg12_16x16x16_f1_tp",
                                             "ldg13_2x16x16x16_f1_tp"};
 // raw integer IQ (suffix _i16 / _i8 appended): the instantiated subset
 static const char* const g_default_tma_int[] = {"ldg5_4x8_f32", "ldg6_8x8_f32", "ldg7_8x16_f16", "ldg8_16x16_f8", "ldg9_8x8x8_f1_tp",
                                                 "tma10_4x16x16_f1_s2x1_tq", "tma11_8x16x16_f1_s2x1_tq",
-                                                "tma12_16x16x16_f1_s2x1_tq", "tma13_16x8x8x8_f1_s2x1_tq"};
+                                                "tma12_16x16x16_f1_s2x1_tq", "tma13_16x16x2x16_f1_s2x1_tq"};
 
 static const Variant* pick_variant(int logn, bool tma_ok, int iqt) {
     {
@@ -335,7 +341,7 @@ extern "C" int psg_set_variant(const char* name) {
     if (!g_variant_override.empty()) {
         bool ok = g_variant_override == "split" || g_variant_override == "cluster" || g_variant_override == "cluster_ldg" ||
                   g_variant_override == "cluster_dsmem" || g_variant_override == "whole" || g_variant_override == "whole_s2" ||
-                  g_variant_override == "whole_s8" || g_variant_override == "whole_r2" || g_variant_override == "whole_r4" ||
+                  g_variant_override == "whole_s8" || g_variant_override == "whole_f" || g_variant_override == "whole_r2" || g_variant_override == "whole_r4" ||
                   g_variant_override == "bluestein_r2" || g_variant_override == "bluestein";
         for (int i = 0; i < g_nvariants; ++i) ok = ok || g_variant_override == g_variants[i].name;
         if (!ok) {
@@ -1024,6 +1030,57 @@ static int run_whole(psg_plan* p, const StiArgs& a0, int ncs, int frames_per_col
     return PSG_OK;
 }
 
+// ---- whole-frame path with both radix-2 passes in registers (sti_whole16.cuh): nfft = 16384 ---------------
+static int run_whole16(psg_plan* p, const StiArgs& a0, int ncs, int frames_per_col, cudaStream_t st) {
+    const int N = p->nfft;
+    if (N != 16384) return fail(PSG_ERR_UNSUPPORTED, "whole_f path: nfft=%d (16384 only)", N);
+    const void* fn = a0.iq_type == IQ_CI16 ? (const void*)sti_whole16_kernel<IQ_CI16>
+                     : a0.iq_type == IQ_CI8 ? (const void*)sti_whole16_kernel<IQ_CI8>
+                                            : (const void*)sti_whole16_kernel<IQ_C64>;
+    const size_t smem = a0.iq_type == IQ_CI16 ? Whole16Cfg<IQ_CI16>::smem_bytes
+                        : a0.iq_type == IQ_CI8 ? Whole16Cfg<IQ_CI8>::smem_bytes
+                                               : Whole16Cfg<IQ_C64>::smem_bytes;
+    static thread_local const void* q_fn = nullptr;
+    static thread_local int q_dev = -1;
+    if (q_fn != fn || q_dev != p->device) {
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        q_fn = fn;
+        q_dev = p->device;
+    }
+    int nsplit = whole_nsplit(ncs, frames_per_col, p->sms);
+    const int chunk = (frames_per_col + nsplit - 1) / nsplit;
+    nsplit = (frames_per_col + chunk - 1) / chunk;
+    Whole16Args wa;
+    wa.s = a0;
+    wa.s.gpc = 1;
+    wa.s.chunk = chunk;
+    wa.s.nsplit = nsplit;
+    wa.s.nfr = frames_per_col;
+    if (nsplit > 1) {
+        size_t have_b = p->partial_elems * sizeof(float);
+        int rc = ensure_buffer((void**)&p->d_partial, &have_b, (size_t)ncs * nsplit * N * sizeof(float));
+        p->partial_elems = have_b / sizeof(float);
+        if (rc) return rc;
+        wa.s.partial = p->d_partial;
+    }
+    const long long grid = (long long)ncs * nsplit;
+    if (grid > 2147483647ll) return fail(PSG_ERR_ARG, "psg_sti_run: grid too large");
+    void* args[] = {(void*)&wa};
+    CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(512), args, smem, st));
+    g_launches++;
+    if (nsplit > 1) {
+        const size_t total = (size_t)ncs * N;
+        const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)p->sms * 16);
+        sti_finalize_kernel<<<blocks, 256, 0, st>>>(wa.s.partial, nsplit, N, (size_t)ncs, wa.s.scale, wa.s.eps, wa.s.out_lin,
+                                                    wa.s.out_db);
+        g_launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    snprintf(p->variant_name, sizeof(p->variant_name), "whole16x2x16x2x16%s",
+             a0.iq_type == IQ_CI16 ? "_i16" : a0.iq_type == IQ_CI8 ? "_i8" : "");
+    return PSG_OK;
+}
+
 // ---- clustered whole-frame path (sti_whole.cuh): nfft = 32768 / 65536 on clusters of 2 / 4 CTAs ---------
 template <int CL, int ROWS>
 static const void* wholec_fn_iq(int iqt) {
@@ -1493,6 +1550,7 @@ extern "C" int psg_sti_run_typed(psg_plan* p, const void* iq_dev, int iq_type, i
         bool force_split = false, force_cluster = false;
         int whole_nst = 0;   // whole-frame path forced with this many ring stages
         int whole_rows = 0;  // ... and this many rows per CTA (0: the default form of the size)
+        bool whole_f = false;  // 16384: whole-frame kernel with the radix-2 passes in registers (sti_whole16.cuh)
         // Measured defaults (profiles/r01_big_nfft_cluster_vs_split.txt, 4 and 12 GB): the cluster kernel with
         // the exchange in L2 and rows loaded to registers wins at 16384 (31 % vs 26 % of the HBM peak) and
         // 32768 (29 % vs 27 %); at 65536 the 16-CTA clusters fill only 112 of the 148 SMs and the
@@ -1510,7 +1568,9 @@ extern "C" int psg_sti_run_typed(psg_plan* p, const void* iq_dev, int iq_type, i
             if (g_variant_override == "whole_r4") { whole_nst = 4; whole_rows = 4; }
             if (g_variant_override == "whole_s2") whole_nst = 2;
             if (g_variant_override == "whole_s8") whole_nst = 8;
+            whole_f = g_variant_override == "whole_f";
         }
+        if (whole_f && p->logn == 14 && tma_ok) return run_whole16(p, a, ncs, frames_per_col, st);
         // 16384 points: the whole frame in one SM (sti_whole.cuh) is the measured default (39 % of the HBM peak
         // against 30 % for the 4-CTA cluster kernel, profiles/r01_whole_frame_16384.txt)
         // 32768 points: the same kernel on clusters of two CTAs (36 % against 29 %); at 65536 (clusters of four: 24 %)

@@ -285,6 +285,21 @@ PSG_DEV void smem_pass(float2* __restrict__ buf, const cf* tw, int t, float* acc
 // (radix-16, stride 1) pass.  One shared-memory write + read less than a four-pass plan
 // (8192 = 16*16*2*16: 6.5 instead of 8 accesses per sample).  w2 = W_32^(lane & 15), negated in the
 // upper half-warp (there the difference is taken the other way round).
+// the exchange itself: a[k] = this lane's 16 outputs (n' = lane), q = padded address of position
+// (block base + (n' & 15)); stores the finished radix-2 outputs of the eight k this lane keeps
+PSG_DEV void pair_exchange_store(const cf* a, float2* q, const bool hi, const cf w2) {
+    if (hi) q += pad_off(8 * 32);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const cf send = hi ? a[i] : a[8 + i];
+        const cf keep = hi ? a[8 + i] : a[i];
+        cf recv;
+        recv.x = __shfl_xor_sync(0xffffffffu, send.x, 16);
+        recv.y = __shfl_xor_sync(0xffffffffu, send.y, 16);
+        q[pad_off(i * 32)] = cadd(keep, recv);
+        q[pad_off(i * 32) + 18] = cmul(csub(keep, recv), w2);
+    }
+}
 template <int E, int T, int R, int S>
 PSG_DEV void smem_pass_fused_r2(float2* __restrict__ buf, const cf* tw, int t, const cf w2) {
     static_assert(E == 16 && R == 16 && S == 32 && (T % 32) == 0, "pair exchange is laid out for radix 16, stride 32");
@@ -298,17 +313,7 @@ PSG_DEV void smem_pass_fused_r2(float2* __restrict__ buf, const cf* tw, int t, c
     dftR<R>(a);
 #pragma unroll
     for (int k = 1; k < R; ++k) a[k] = cmul(a[k], tw[k - 1]);
-    float2* q = buf + psg_pad((b / S) * (R * S) + (npr & 15)) + (hi ? pad_off(8 * S) : 0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const cf send = hi ? a[i] : a[8 + i];
-        const cf keep = hi ? a[8 + i] : a[i];
-        cf recv;
-        recv.x = __shfl_xor_sync(0xffffffffu, send.x, 16);
-        recv.y = __shfl_xor_sync(0xffffffffu, send.y, 16);
-        q[pad_off(i * S)] = cadd(keep, recv);
-        q[pad_off(i * S) + 18] = cmul(csub(keep, recv), w2);
-    }
+    pair_exchange_store(a, buf + psg_pad((b / S) * (R * S) + (npr & 15)), hi, w2);
 }
 
 // The exchange between pass p (radix Ra, stride Sa) and pass p+1 (radix Rb) stays inside aligned
@@ -360,8 +365,11 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
     constexpr bool L23 = WarpLocal<E, R2, R3, PL::S2>::value;
     // 16 x 16 x 2 x 16: the radix-2 pass runs in registers on the end of pass 1 (smem_pass_fused_r2)
     constexpr bool FUSE2 = (P == 4) && (E == 16) && (R1 == 16) && (R2 == 2) && (R3 == 16) && (PL::S1 == 32);
+    // 16 x 2 x 16 (512 points, one warp per frame): the same exchange on the end of pass 0 -- one
+    // shared-memory round trip per frame, no CTA barrier
+    constexpr bool FUSE0 = (P == 3) && (E == 16) && (R0 == 16) && (R1 == 2) && (R2 == 16) && (PL::S0 == 32) && (T == 32);
     // true when no exchange needs a CTA barrier: every frame group then owns its buffers privately
-    constexpr bool ALL_LOCAL = L01 && (P < 3 || L12) && (P < 4 || L23) && !FUSE2;
+    constexpr bool ALL_LOCAL = FUSE0 || (L01 && (P < 3 || L12) && (P < 4 || L23) && !FUSE2);
     static_assert(ALL_LOCAL ? (T <= 32) : true, "");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
@@ -455,8 +463,8 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
     }
     // TWP == 2: the power-of-two twiddles of every mid-pass butterfly of this thread stay in registers
     constexpr int NPW1 = psg_npow(R1), NPW2 = psg_npow(R2);
-    cf wb1[(TWP == 2 && P >= 3) ? (E / R1) * NPW1 : 1], wb2[(TWP == 2 && P >= 4 && !FUSE2) ? (E / R2) * NPW2 : 1];
-    if constexpr (TWP == 2 && P >= 3) {
+    cf wb1[(TWP == 2 && P >= 3 && !FUSE0) ? (E / R1) * NPW1 : 1], wb2[(TWP == 2 && P >= 4 && !FUSE2) ? (E / R2) * NPW2 : 1];
+    if constexpr (TWP == 2 && P >= 3 && !FUSE0) {
 #pragma unroll
         for (int i = 0; i < E / R1; ++i) {
             const int npr = (t + i * T) & (PL::S1 - 1);
@@ -465,9 +473,9 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
         }
     }
     cf w2f = make_float2(1.f, 0.f);  // FUSE2: W_32^(lane & 15), sign of the upper half-warp folded in
-    if constexpr (FUSE2) {
-        static_assert(!FUSE2 || TWP == 2, "fused radix-2 plans use the power-layout tables");
-        w2f = __ldg(a.twp + PL::TW2 + (t & 15) * 6);
+    if constexpr (FUSE2 || FUSE0) {
+        static_assert(!(FUSE2 || FUSE0) || TWP == 2, "fused radix-2 plans use the power-layout tables");
+        w2f = __ldg(a.twp + (FUSE2 ? PL::TW2 : PL::TW1) + (t & 15) * 6);
         if (t & 16) w2f = make_float2(-w2f.x, -w2f.y);
     }
     if constexpr (TWP == 2 && P >= 4 && !FUSE2) {
@@ -581,10 +589,20 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
             float2* p0 = buf + psg_pad(t + i * T);
 #pragma unroll
             for (int kk = 1; kk < R0; ++kk) x[i * R0 + kk] = cmul(x[i * R0 + kk], tw0[i * (R0 - 1) + kk - 1]);
+            if constexpr (FUSE0) {
+                pair_exchange_store(&x[0], buf + psg_pad(t & 15), (t & 16) != 0, w2f);
+            } else {
 #pragma unroll
-            for (int kk = 0; kk < R0; ++kk) p0[pad_off(kk * PL::S0)] = x[i * R0 + kk];
+                for (int kk = 0; kk < R0; ++kk) p0[pad_off(kk * PL::S0)] = x[i * R0 + kk];
+            }
         }
-        {
+        if constexpr (FUSE0) {
+            __syncwarp();
+            if constexpr (LOADER == PSG_LOADER_TMA && STAGES == 1) {
+                if (t == 0 && pj < niter) produce();  // the group's slot has been read by its one warp
+            }
+            smem_pass<E, T, R2, PL::S2, true>(buf, nullptr, t, acc);
+        } else {
             cf tw1[(P >= 3) ? (E / R1) * (R1 - 1) : 1];
             if constexpr (P >= 3) load_pass_tw<E, T, R1, PL::S1, PL::ROW1, TWP>(PL::ROW1 ? twsm : a.twp + PL::TW1, t, tw1, wb1);
             exchange_sync<L01>();
@@ -595,7 +613,7 @@ __global__ void __launch_bounds__(F*((1 << LOGN) / E), MINB) sti_fused_kernel(co
             if constexpr (FUSE2) smem_pass_fused_r2<E, T, R1, PL::S1>(buf, tw1, t, w2f);
             else smem_pass<E, T, R1, PL::S1, P == 2>(buf, tw1, t, acc);
         }
-        if constexpr (P >= 3 && !FUSE2) {
+        if constexpr (P >= 3 && !FUSE2 && !FUSE0) {
             cf tw2[(P >= 4) ? (E / R2) * (R2 - 1) : 1];
             if constexpr (P >= 4)
                 load_pass_tw<E, T, R2, PL::S2, PL::ROW2, TWP>(PL::ROW2 ? twsm + (PL::ROW1 ? PL::TW1_LEN : 0) : a.twp + PL::TW2, t, tw2, wb2);

@@ -200,3 +200,26 @@ def test_fused_radix2_pair_exchange_8192():
                 written.update((q + i * s1, q + i * s1 + 16))
         read = set((ts[:, None] * 16 + np.arange(16)[None, :]).reshape(-1).tolist())
         assert written == read
+
+
+def test_whole16_plan_16x2x16x2x16():
+    """The 16384-point whole-frame kernel with both radix-2 passes in registers (sti_whole16.cuh): the
+    five-pass plan is an FFT, and the kernel's closed-form frequency map of the last pass
+    (butterfly b = k0*64 + k1*32 + k2*2 + k3 -> k0 + 16 k1 + 32 k2 + 512 k3 + 1024 j) is low_freq."""
+    n, radices = 16384, [16, 2, 16, 2, 16]
+    rng = np.random.default_rng(16)
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    got = model_fft(x, radices)
+    ref = np.fft.fft(x)
+    assert np.abs(got - ref).max() <= 1e-9 * np.abs(ref).max()
+    b = np.arange(n // 16)
+    klow = (b >> 6) + 16 * ((b >> 5) & 1) + 32 * ((b >> 1) & 15) + 512 * (b & 1)
+    assert np.array_equal(klow, low_freq(b, n, radices))
+    # slab geometry of the first pass: the four slabs of 256 threads cover every n' exactly once
+    seen = np.zeros(1024, int)
+    for m in range(4):
+        for u in range(256):
+            lane = u & 31
+            npp = 128 * m + 16 * (u >> 5) + (lane & 15)
+            seen[npp + 512 * (lane >> 4)] += 1
+    assert (seen == 1).all()

@@ -352,6 +352,12 @@ def test_cluster_path(torch, nfft, nfr, ncol, nsub, kind):
     (65536, 160, 2, 1, "whole"),
     (65536, 3, 100, 1, "whole"),
     (65536, 2, 3, 1, "whole_i8"),
+    (16384, 1, 9, 1, "whole_f"),     # 16 x 2 x 16 x 2 x 16 with both radix-2 passes in registers (sti_whole16.cuh)
+    (16384, 5, 7, 2, "whole_f"),
+    (16384, 640, 2, 1, "whole_f"),
+    (16384, 3, 500, 1, "whole_f"),
+    (16384, 4, 6, 1, "whole_f_i16"),
+    (16384, 2, 3, 1, "whole_f_i8"),
     (16384, 1, 9, 1, "whole_r2"),    # two rows per CTA, 256 threads, two CTAs per SM: clusters of 2 / 4 / 8
     (16384, 5, 7, 2, "whole_r2"),
     (16384, 640, 2, 1, "whole_r2"),
@@ -380,12 +386,16 @@ def test_whole_frame_path(torch, nfft, nfr, ncol, nsub, kind):
         x = ((feed[:, 0].astype(np.float32) + 1j * feed[:, 1].astype(np.float32)) * np.float32(in_scale)).astype(np.complex64)
     plan = engine.StiPlan(nfft)
     try:
-        engine.set_variant(kind if kind in ("whole_s2", "whole_s8") else "whole_r2" if kind.startswith("whole_r2") else "whole")
+        engine.set_variant(kind if kind in ("whole_s2", "whole_s8") else "whole_r2" if kind.startswith("whole_r2")
+                           else "whole_f" if kind.startswith("whole_f") else "whole")
         lin, db = plan.run(torch.from_numpy(feed).cuda(), torch.from_numpy(starts).cuda(), nfr, nfft, sub_stride=per_sub,
                            nsub=nsub, in_scale=in_scale, want_lin=True, want_db=True)
         torch.cuda.synchronize()
-        assert plan.variant.startswith(f"whole{nfft // 4096}x4096"), plan.variant
-        assert ("r2" in plan.variant) == kind.startswith("whole_r2"), plan.variant
+        if kind.startswith("whole_f"):
+            assert plan.variant.startswith("whole16x2x16x2x16"), plan.variant
+        else:
+            assert plan.variant.startswith(f"whole{nfft // 4096}x4096"), plan.variant
+            assert ("r2" in plan.variant) == kind.startswith("whole_r2"), plan.variant
     finally:
         engine.set_variant(None)
     for s in range(nsub):
