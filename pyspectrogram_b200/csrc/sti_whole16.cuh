@@ -18,8 +18,8 @@
 //             exactly the 512-point blocks it wrote in pass 2+3: __syncwarp.
 // 7 shared-memory accesses per sample (bulk-copy write, stage read, 2 x (write + read), last read, 2 x half an
 // access worth of SHFL) against 8, and two CTA barriers per frame against three.  512 threads, one CTA per SM.
-// The stage of a half is refilled by whichever of its eight warps reads it last (the relaxed shared-memory
-// counter of sti_whole.cuh), so the first slab of frame f+1 streams in under passes 2-4 of frame f.
+// The stage of a half is refilled right after the CTA barrier that follows its reads, every warp issuing four
+// of the 32 copies, so the first slab of frame f+1 streams in under passes 2-4 of frame f.
 #pragma once
 #include "sti_whole.cuh"
 
@@ -60,7 +60,6 @@ __global__ void __launch_bounds__(512, 1) sti_whole16_kernel(const Whole16Args w
     const StiArgs& a = wa.s;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);      // [2] stage of half h full
-    unsigned* cnt = reinterpret_cast<unsigned*>(smem_raw + 64);  // [2] warps of half h that have read its stage (running total)
     unsigned char* stage = smem_raw + CF::HDR;
     float2* xch = reinterpret_cast<float2*>(smem_raw + CF::HDR + 2 * (size_t)CF::STAGE);
 
@@ -79,27 +78,32 @@ __global__ void __launch_bounds__(512, 1) sti_whole16_kernel(const Whole16Args w
     const int nsteps = 2 * nfr;  // per half: step q = (frame q >> 1, slab h + 2 (q & 1))
     unsigned char* const myst = stage + (size_t)h * CF::STAGE;
 
-    auto issue = [&](int q) {  // one thread of half h
+    // Refill of this half's stage for step q, spread over the half's eight warps: lane 0 of warp w8 issues
+    // copies 4 w8 .. 4 w8 + 3, warp 0 also posts the byte count.  (One thread issuing all 32 copies is a
+    // ~450-instruction serial section in front of a CTA barrier: 14 % of all stall samples.)  Called right
+    // after a CTA barrier that follows every warp's reads of the stage, so no "stage free" signal is needed;
+    // a copy that completes before the count is posted only makes the pending byte count negative for a while.
+    const int w8 = (t & 255) >> 5;
+    auto issue = [&](int q) {  // lane 0 of every warp
         const int f = q >> 1, m = h + 2 * (q & 1);
         const uintptr_t src0 =
             reinterpret_cast<uintptr_t>(a.iq) + (uintptr_t)((fbase + (long long)f * a.hop_elems + m * CF::WS) * IQB);
         const uint32_t bytes = CF::WS * IQB + ((src0 & 15) ? 16 : 0);
         uint64_t* bar = bars + h;
-        mbar_expect_tx(bar, bytes * 32);
-        const uintptr_t s16 = src0 & ~(uintptr_t)15;
-#pragma unroll 4
-        for (int c = 0; c < 32; ++c)  // c = 2 n0 + hi: element offset 512 c
-            bulk_g2s(myst + c * SEG, reinterpret_cast<const void*>(s16 + (uintptr_t)c * 512 * IQB), bytes, bar);
+        if (w8 == 0) mbar_expect_tx(bar, bytes * 32);
+        const uintptr_t s16 = (src0 & ~(uintptr_t)15) + (uintptr_t)(4 * w8) * 512 * IQB;
+        unsigned char* dst = myst + 4 * w8 * SEG;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)  // copy 2 n0 + hi: element offset 512 (2 n0 + hi)
+            bulk_g2s(dst + c * SEG, reinterpret_cast<const void*>(s16 + (uintptr_t)c * 512 * IQB), bytes, bar);
     };
     if (t == 0) {
         mbar_init(bars + 0, 1);
         mbar_init(bars + 1, 1);
-        cnt[0] = 0;
-        cnt[1] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();  // barriers and counters initialised
-    if ((t & 255) == 0) issue(0);
+    if (lane == 0) issue(0);
 
     // (twiddles are re-read from L1/L2 right before the wait or barrier that precedes their use: as
     // loop-invariant registers they push the accumulators into local memory)
@@ -136,14 +140,13 @@ __global__ void __launch_bounds__(512, 1) sti_whole16_kernel(const Whole16Args w
             for (int n0 = 0; n0 < 16; ++n0) x[n0] = lds_iq<IQT>(myst + (2 * n0 + (hi ? 1 : 0)) * SEG, skew + nt);
             dftRw<16>(x, wq);
             if (j == 0) load_window(1);
-            // the butterflies have consumed every load of this warp: the warp that reads the stage last refills it
-            __syncwarp();
-            if (lane == 0) {
-                const unsigned old = count_reader(cnt + h);
-                if ((old & 7) == 7 && q + 1 < nsteps) issue(q + 1);
-            }
             twiddle_dfs<16>(x, pw);
-            if (j == 0) __syncthreads();  // the last pass of the previous frame is done with the exchange buffer
+            if (j == 0) {
+                // the last pass of the previous frame is done with the exchange buffer, and every warp's
+                // butterflies have consumed its loads from the stage: refill it with the second slab
+                __syncthreads();
+                if (lane == 0) issue(q + 1);
+            }
             pair_exchange_store_1024(x, q0 + pad_off(256 * j), hi, w1);
         }
         cf w2 = __ldg(a.tw + 512 * (lane & 15));  // W_32^{lane & 15}
@@ -152,6 +155,7 @@ __global__ void __launch_bounds__(512, 1) sti_whole16_kernel(const Whole16Args w
 #pragma unroll
         for (int q = 0; q < 4; ++q) pwA[q] = __ldg(a.tw + ((32 * lane) << q));  // W_512^{lane 2^q}
         __syncthreads();
+        if (lane == 0 && 2 * f + 2 < nsteps) issue(2 * f + 2);  // next frame's first slab streams in under passes 2-4
         // ---- pass 2+3: radix 16 at stride 32 + radix 2 at stride 16, inside each 512-point block ----
 #pragma unroll 1
         for (int i = 0; i < 2; ++i) {
