@@ -187,7 +187,7 @@ int psg_set_force_generic(int on);
  * "cluster" / "cluster_dsmem" (one CTA per 4096-point row, nfft = 8192..65536), "whole" (whole-frame kernels:
  * 8192 / 16384 in one CTA, 32768 / 65536 on clusters of 2 / 4 CTAs), "whole_r2" (two rows per CTA: clusters
  * of 2 / 4 / 8 for 16384 / 32768 / 65536), "whole_r4", "whole_s2" / "whole_s8" (ring depth of the single-CTA
- * kernel); "bluestein" / "bluestein_r2" select the Bluestein kernels (mixed-radix passes / radix 2) for non
+ * kernel), "whole_f" (16384 as 16 x 2 x 16 x 2 x 16 with both radix-2 passes in registers, sti_whole16.cuh); "bluestein" / "bluestein_r2" select the Bluestein kernels (mixed-radix passes / radix 2) for non
  * powers of two.  Process-wide.
  */
 int psg_set_variant(const char* name);

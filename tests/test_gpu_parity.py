@@ -427,7 +427,7 @@ def test_large_nfft_defaults_and_fallback(torch):
 
 
 @pytest.mark.parametrize("nfft", [256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536, (16384, "cluster"), (32768, "cluster_dsmem"),
-                                  (65536, "cluster_ldg"), (65536, "cluster_dsmem"), (16384, "whole"), (8192, "whole"), (32768, "whole"), (65536, "whole"), (16384, "whole_r2"), (65536, "whole_r2")])
+                                  (65536, "cluster_ldg"), (65536, "cluster_dsmem"), (16384, "whole"), (8192, "whole"), (32768, "whole"), (65536, "whole"), (16384, "whole_r2"), (65536, "whole_r2"), (16384, "whole_f")])
 def test_repeated_runs_are_bit_identical(torch, nfft):
     """Race canary (compute-sanitizer is not available on the GPU pool): no atomic touches data (the
     whole-frame kernel counts stage readers with one, which only decides WHO issues the next copy) and

@@ -1,10 +1,10 @@
 mkdir -p gpurun_out
-(timeout 300 python -m pytest tests/test_gpu_parity.py -k "whole_f" -x -q 2>&1 | tail -12) > gpurun_out/whole_f_tests.log 2>&1
-cat gpurun_out/whole_f_tests.log
-for v in whole whole_f; do
-  timeout 120 python tools/default_sweep.py --gb 4 --nffts 16384 --variant $v > gpurun_out/w16_${v}_4gb.log 2>&1; cat gpurun_out/w16_${v}_4gb.log
-  timeout 120 python tools/default_sweep.py --gb 12 --nffts 16384 --variant $v > gpurun_out/w16_${v}_12gb.log 2>&1; cat gpurun_out/w16_${v}_12gb.log
-done
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:sti_whole16 --launch-skip 2 -c 1 -f -o gpurun_out/whole16 \
-  python tools/default_sweep.py --gb 4 --nffts 16384 --variant whole_f > gpurun_out/whole16_ncu.log 2>&1
-tail -2 gpurun_out/whole16_ncu.log
+(timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -6) > gpurun_out/gpu_tests.log 2>&1
+cat gpurun_out/gpu_tests.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 600 gpurun_out/bench_ref.json
+timeout 600 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; cat gpurun_out/bench_n1.json
+timeout 400 python tools/default_sweep.py --gb 12 > gpurun_out/default_sweep_12gb.log 2>&1; cat gpurun_out/default_sweep_12gb.log
+timeout 400 python tools/default_sweep.py --gb 4 > gpurun_out/default_sweep_4gb.log 2>&1; cat gpurun_out/default_sweep_4gb.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_bench.log 2>&1
+tail -1 gpurun_out/ncu_bench.log | cut -c1-200
