@@ -3,9 +3,11 @@
 Every STI column depends only on its own samples (drfProc.py:161-166), so the flat list of
 columns ``(channel, sub-channel, time bin)`` is block-partitioned across ranks -- whole channels
 when there are at least as many channels as ranks, contiguous time-bin ranges otherwise -- and
-each rank computes its slab with no data-path collective.  The only exchange is one gather of
-``[ncol_local][nfft]`` float32 slabs when the image is returned to the host; the time-median
-(drfProc.py:401) needs every column of a row and therefore runs after the gather.
+each rank computes its slab with no data-path collective.  The image is assembled by one gather of
+``[ncol_local][nfft]`` float32 slabs when it is returned to the host.  The time-median (drfProc.py:401)
+needs every column of a row: per channel it stays on the channel's rank; with time-bin shards it is the
+one real exchange of the path -- the image is re-sharded by frequency and every rank takes the median of
+its slab (``median_over_time_sharded``).
 
 One process per GPU; ``torch.distributed`` (NCCL over NVLink on the GPU box, gloo in CPU tests)
 is plumbing only.
@@ -76,3 +78,63 @@ def gather_columns(local, ncols_per_rank, dst=0, group=None):
         return torch.cat([recv[r, : ncols_per_rank[r]] for r in range(world)], dim=0)
     dist.gather(send, None, dst=dst, group=group)
     return None
+
+
+def median_over_time_sharded(local, ncols_per_rank, median_fn, dst=0, group=None):
+    """Time-median of an image whose COLUMNS (time bins) are sharded over the ranks (BASELINE config 4).
+
+    ``np.median(sxx, axis=1)`` (drfProc.py:401) needs every time bin of a frequency row.  Gathering the
+    image on one rank and taking the median there leaves that rank with the whole ``[ntime][nfft]``
+    selection while the others idle -- at nfft = 65536, ntime = 3600 that is as long as the transform
+    of a two-GPU shard.  Here the image is re-sharded by FREQUENCY instead: rank ``s`` receives bins
+    ``shard_range(nfft, s, world)`` of every rank's columns (the one exchange of the path: pairwise
+    sends of ``[ncol_r][nfft / world]`` blocks over NVLink), stacks them in rank order -- which is time
+    order -- runs ``median_fn`` on its ``[ntime][nfft / world]`` slab, and the median slabs are
+    gathered on ``dst``.  A median is an order statistic of one frequency row, so the result is
+    bit-identical to the median of the assembled image.
+
+    ``local``: this rank's ``[ncol_local][nfft]`` linear slab.  ``median_fn(img)`` maps a contiguous
+    ``[1][ntime][w]`` tensor to a tuple of ``[1][w]`` tensors (e.g. ``StiPlan.median`` returning the
+    linear and / or dB median; ``None`` entries are passed through).  Returns the tuple of ``[nfft]``
+    tensors on ``dst``, ``None`` elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    nfft = int(local.shape[1])
+    assert len(ncols_per_rank) == world and local.shape[0] == ncols_per_rank[rank]
+    if world == 1:
+        return tuple(None if m is None else m[0] for m in median_fn(local.reshape(1, -1, nfft)))
+    f_lo, f_hi = shard_range(nfft, rank, world)
+    width = f_hi - f_lo
+    ntime = sum(ncols_per_rank)
+    slab = torch.empty((ntime, width), dtype=local.dtype, device=local.device)
+    ops, keep = [], []
+    off = 0
+    for r in range(world):
+        rows = slab[off:off + ncols_per_rank[r]]
+        off += ncols_per_rank[r]
+        if r == rank:
+            rows.copy_(local[:, f_lo:f_hi])
+            continue
+        lo, hi = shard_range(nfft, r, world)
+        if ncols_per_rank[rank] and hi > lo:
+            send = local[:, lo:hi].contiguous()
+            keep.append(send)
+            ops.append(dist.P2POp(dist.isend, send, r, group))
+        if ncols_per_rank[r] and width:
+            ops.append(dist.P2POp(dist.irecv, rows, r, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    meds = median_fn(slab.reshape(1, ntime, width))
+    widths = [shard_range(nfft, r, world)[1] - shard_range(nfft, r, world)[0] for r in range(world)]
+    out = []
+    for m in meds:
+        if m is None:
+            out.append(None)
+            continue
+        full = gather_columns(m.reshape(width, 1), widths, dst=dst, group=group)
+        out.append(full.reshape(nfft) if rank == dst else None)
+    return tuple(out) if rank == dst else None

@@ -88,3 +88,45 @@ def test_sharded_starts_concatenate_to_the_single_gpu_table():
     for world in (2, 4, 8):
         parts = [full[slice(*pdist.shard_range(ntime, r, world))] for r in range(world)]
         assert np.array_equal(np.concatenate(parts), full)
+
+
+def _median_worker(rank, world, port, ncols, nfft, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(5)
+        full = rng.random((sum(ncols), nfft)).astype(np.float32)
+        lo = sum(ncols[:rank])
+        local = torch.from_numpy(full[lo:lo + ncols[rank]].copy())
+
+        def median_fn(img):  # [1][ntime][w] -> ([1][w] linear, None)
+            return torch.from_numpy(np.median(img.numpy(), axis=1)), None
+
+        res = pdist.median_over_time_sharded(local, ncols, median_fn, dst=0)
+        if rank == 0:
+            q.put(bool(np.array_equal(res[0].numpy(), np.median(full, axis=0)) and res[1] is None))
+        else:
+            q.put(res is None)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ncols,nfft", [([5, 5], 16), ([4, 3], 10), ([6, 1], 7)])
+def test_median_over_time_sharded_two_gloo_ranks(ncols, nfft):
+    """Time-bin shards re-sharded by frequency (the one exchange of BASELINE config 4): the median of
+    the slabs, gathered, is bit-identical to np.median of the assembled image -- equal and ragged
+    shards, nfft not divisible by the number of ranks."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_median_worker, args=(r, 2, port, ncols, nfft, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(results)

@@ -1,10 +1,4 @@
 mkdir -p gpurun_out
-(timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -6) > gpurun_out/gpu_tests.log 2>&1
-cat gpurun_out/gpu_tests.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 600 gpurun_out/bench_ref.json
-timeout 600 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; cat gpurun_out/bench_n1.json
-timeout 400 python tools/default_sweep.py --gb 12 > gpurun_out/default_sweep_12gb.log 2>&1; cat gpurun_out/default_sweep_12gb.log
-timeout 400 python tools/default_sweep.py --gb 4 > gpurun_out/default_sweep_4gb.log 2>&1; cat gpurun_out/default_sweep_4gb.log
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_bench.log 2>&1
-tail -1 gpurun_out/ncu_bench.log | cut -c1-200
+N=${NGPU:-2}
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tools/dist_configs_probe.py --out gpurun_out/dist_configs_n$N.json > gpurun_out/dist_configs_n$N.log 2>&1
+grep '^{' gpurun_out/dist_configs_n$N.log | cut -c1-900
