@@ -618,6 +618,23 @@ def test_median_is_exact_order_statistic(torch):
         ref = np.median(img, axis=1)
         assert np.array_equal(lin.cpu().numpy(), ref), (nsub, ncol, nfft)
         assert np.abs(db.cpu().numpy() - 10 * np.log10(ref + np.float32(1e-15))).max() <= 1e-4
+    # the bisection starts below the leading bits all keys of a tile share: narrow value ranges (long
+    # common prefix), a constant image (no differing bit at all), mixed signs (no common prefix), one
+    # outlier per row, with column counts around the 4-column vector loads
+    for ncol in (4, 5, 7, 8, 64, 99, 3600):
+        for kind in ("narrow", "const", "signed", "outlier"):
+            img = rng.random((2, ncol, 72), dtype=np.float32)
+            if kind == "narrow":
+                img = np.float32(1.0) + img * np.float32(1e-6)
+            elif kind == "const":
+                img[:] = np.float32(0.3)
+            elif kind == "signed":
+                img = img - np.float32(0.5)
+            else:
+                img = np.float32(2.0) + img * np.float32(1e-3)
+                img[:, 0, :] = np.float32(1e-30)
+            lin, _ = plan.median(torch.from_numpy(np.ascontiguousarray(img)).cuda(), want_lin=True, want_db=False)
+            assert np.array_equal(lin.cpu().numpy(), np.median(img, axis=1)), (ncol, kind)
 
 
 def test_epoch_sized_frame_starts_are_reproduced(torch):
