@@ -1,2 +1,5 @@
 mkdir -p gpurun_out
-timeout 300 python tools/mode_r_ab.py > gpurun_out/mode_r_ab.log 2>&1; cat gpurun_out/mode_r_ab.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
+grep '^{' gpurun_out/bench_n2.json | cut -c1-1500
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/bench_n2_ref.json 2> gpurun_out/bench_n2_ref.err
+grep '^{' gpurun_out/bench_n2_ref.json | cut -c1-300
