@@ -1,5 +1,6 @@
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
-grep '^{' gpurun_out/bench_n2.json | cut -c1-1500
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/bench_n2_ref.json 2> gpurun_out/bench_n2_ref.err
-grep '^{' gpurun_out/bench_n2_ref.json | cut -c1-300
+(timeout 600 python -m pytest tests/test_gpu_parity.py -k "median or minmax or proc_data or drop_in or golden" -x -q 2>&1 | tail -6) > gpurun_out/median_tests.log 2>&1
+cat gpurun_out/median_tests.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 1 --master-addr 127.0.0.1 --master-port 29511 tools/dist_configs_probe.py --out gpurun_out/dist_configs_n1_newmedian.json > gpurun_out/dist_configs_n1_newmedian.log 2>&1
+grep '^{' gpurun_out/dist_configs_n1_newmedian.log | cut -c1-420
+timeout 300 python bench.py --no-e2e --no-cpu > gpurun_out/bench_newmedian.json 2>gpurun_out/bench_newmedian.err; cut -c1-330 gpurun_out/bench_newmedian.json
