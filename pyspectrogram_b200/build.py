@@ -11,13 +11,17 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "csrc", "psg_b200.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "sti_kernels.cuh"), os.path.join(HERE, "csrc", "sti_cluster.cuh"), os.path.join(HERE, "csrc", "sti_whole.cuh"), os.path.join(HERE, "csrc", "sti_whole16.cuh"), os.path.join(HERE, "csrc", "sti_bluestein.cuh"), os.path.join(HERE, "csrc", "cplx.cuh"),
-        os.path.join(HERE, "..", "include", "psg_b200.h")]
+CSRC = os.path.join(HERE, "csrc")
+# translation units (compiled in parallel, linked into one library); every header is a dependency of both
+UNITS = ["psg_b200.cu", "psg_r32.cu"]
+DEPS = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))] + [
+    os.path.join(HERE, "..", "include", "psg_b200.h")]
 OUT = os.path.join(HERE, "libpsgb200.so")
+OBJ_DIR = os.path.join(HERE, "build")
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC", "-cudart", "static"]
+ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMPILE_FLAGS = [*ARCH_FLAGS, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
+LINK_FLAGS = [*ARCH_FLAGS, "-shared", "-Xcompiler", "-fPIC", "-cudart", "static"]
 
 
 def find_nvcc() -> str:
@@ -34,19 +38,42 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in DEPS if os.path.exists(d))
 
 
+def _unit_stale(src: str, obj: str) -> bool:
+    if not os.path.exists(obj):
+        return True
+    t = os.path.getmtime(obj)
+    hdrs = [d for d in DEPS if not d.endswith(".cu")]
+    return any(os.path.getmtime(d) > t for d in [src, *hdrs] if os.path.exists(d))
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return OUT
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-o", OUT, SRC]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd))
+    nvcc = find_nvcc()
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    procs = []
+    objs = []
+    for unit in UNITS:
+        src = os.path.join(CSRC, unit)
+        obj = os.path.join(OBJ_DIR, unit[:-3] + ".o")
+        objs.append(obj)
+        if not force and not _unit_stale(src, obj):
+            continue
+        cmd = [nvcc, *COMPILE_FLAGS, "-c", "-o", obj, src]
+        if verbose:
+            cmd[1:1] = ["-Xptxas", "-v"]
+            print(" ".join(cmd))
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cmd, pr in procs:
+        out, _ = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd) + "\n" + out)
+        if verbose:
+            print(out)
+    cmd = [nvcc, *LINK_FLAGS, "-o", OUT, *objs]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     return OUT
 
 

@@ -22,6 +22,7 @@
 #include "sti_whole.cuh"
 #include "sti_whole16.cuh"
 #include "sti_bluestein.cuh"
+#include "psg_r32.h"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -342,7 +343,7 @@ extern "C" int psg_set_variant(const char* name) {
         bool ok = g_variant_override == "split" || g_variant_override == "cluster" || g_variant_override == "cluster_ldg" ||
                   g_variant_override == "cluster_dsmem" || g_variant_override == "whole" || g_variant_override == "whole_s2" ||
                   g_variant_override == "whole_s8" || g_variant_override == "whole_f" || g_variant_override == "whole_r2" || g_variant_override == "whole_r4" ||
-                  g_variant_override == "bluestein_r2" || g_variant_override == "bluestein";
+                  g_variant_override == "bluestein_r2" || g_variant_override == "bluestein" || g_variant_override == "r32";
         for (int i = 0; i < g_nvariants; ++i) ok = ok || g_variant_override == g_variants[i].name;
         if (!ok) {
             g_variant_override.clear();
@@ -1176,6 +1177,59 @@ static int run_wholec(psg_plan* p, const StiArgs& a0, int ncs, int frames_per_co
     return PSG_OK;
 }
 
+// ---- radix-32 whole-frame path (sti_r32.cuh, psg_r32.cu): nfft = 16384 / 32768 / 65536, three shared-memory passes ----
+// Persistent CTAs (clusters of 2 / 4 for 32768 / 65536) walk the work items; *ran = false when the device cannot
+// co-schedule the cluster (caller falls back).
+static int run_r32(psg_plan* p, const StiArgs& a0, int ncs, int frames_per_col, cudaStream_t st, bool* ran) {
+    const int N = p->nfft;
+    *ran = false;
+    static thread_local int q_key = -1, q_groups = 0;
+    const int key = (p->device << 8) | (p->logn << 2) | a0.iq_type;
+    if (q_key != key) {
+        int ng = 0;
+        const cudaError_t e = (cudaError_t)psg_r32_max_groups(p->logn, a0.iq_type, p->device, p->sms, &ng);
+        if (e != cudaSuccess) return fail(PSG_ERR_CUDA, "radix-32 path: %s", cudaGetErrorString(e));
+        q_key = key;
+        q_groups = ng;
+    }
+    if (q_groups < 1) return PSG_OK;
+    int nsplit = whole_nsplit(ncs, frames_per_col, q_groups);
+    const int chunk = (frames_per_col + nsplit - 1) / nsplit;
+    nsplit = (frames_per_col + chunk - 1) / chunk;
+    StiArgs a = a0;
+    a.gpc = 1;
+    a.chunk = chunk;
+    a.nsplit = nsplit;
+    a.nfr = frames_per_col;
+    if (nsplit > 1) {
+        size_t have_b = p->partial_elems * sizeof(float);
+        const int rc = ensure_buffer((void**)&p->d_partial, &have_b, (size_t)ncs * nsplit * N * sizeof(float));
+        p->partial_elems = have_b / sizeof(float);
+        if (rc) return rc;
+        a.partial = p->d_partial;
+    }
+    const long long nitems = (long long)ncs * nsplit;
+    if (nitems > 2147483647ll) return fail(PSG_ERR_ARG, "psg_sti_run: too many work items");
+    const int ngroups = (int)std::min<long long>(nitems, q_groups);
+    if (getenv("PSG_DEBUG"))
+        fprintf(stderr, "[psg] radix-32 path nfft=%d groups=%d (resident %d) items=%lld (nsplit=%d, chunk=%d)\n", N, ngroups, q_groups,
+                nitems, nsplit, chunk);
+    const cudaError_t e = (cudaError_t)psg_r32_launch(p->logn, a0.iq_type, a, (int)nitems, ngroups, st);
+    if (e != cudaSuccess) return fail(PSG_ERR_CUDA, "radix-32 kernel launch: %s", cudaGetErrorString(e));
+    g_launches++;
+    if (nsplit > 1) {
+        const size_t total = (size_t)ncs * N;
+        const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)p->sms * 16);
+        sti_finalize_kernel<<<blocks, 256, 0, st>>>(a.partial, nsplit, N, (size_t)ncs, a.scale, a.eps, a.out_lin, a.out_db);
+        g_launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    snprintf(p->variant_name, sizeof(p->variant_name), "r32_%s%s%s", N == 16384 ? "32x32x16" : N == 32768 ? "32x32x32_c2" : "32x32x2x32_c4",
+             "", a0.iq_type == IQ_CI16 ? "_i16" : a0.iq_type == IQ_CI8 ? "_i8" : "");
+    *ran = true;
+    return PSG_OK;
+}
+
 // nfft = r0 * 4096 (r0 = 2..16): streaming first pass -> L2-resident scratch -> tuned 4096-point
 // fused kernel over the r0 sub-sequences -> interleave.  See sti_kernels.cuh.
 static int run_split(psg_plan* p, StiArgs a, int ncs, int frames_per_col, cudaStream_t st) {
@@ -1569,6 +1623,18 @@ extern "C" int psg_sti_run_typed(psg_plan* p, const void* iq_dev, int iq_type, i
             if (g_variant_override == "whole_s2") whole_nst = 2;
             if (g_variant_override == "whole_s8") whole_nst = 8;
             whole_f = g_variant_override == "whole_f";
+        }
+        bool force_r32 = false, other_path = false;
+        {
+            std::lock_guard<std::mutex> lk(g_variant_mu);
+            force_r32 = g_variant_override == "r32";
+            other_path = !g_variant_override.empty() && !force_r32;
+        }
+        // 16384 / 32768 / 65536 points: three-pass radix-32 kernels (sti_r32.cuh), the measured default
+        if (p->logn >= 14 && p->logn <= 16 && tma_ok && !v && (force_r32 || !other_path)) {
+            bool ran = false;
+            const int rcr = run_r32(p, a, ncs, frames_per_col, st, &ran);
+            if (rcr || ran) return rcr;
         }
         if (whole_f && p->logn == 14 && tma_ok) return run_whole16(p, a, ncs, frames_per_col, st);
         // 16384 points: the whole frame in one SM (sti_whole.cuh) is the measured default (39 % of the HBM peak

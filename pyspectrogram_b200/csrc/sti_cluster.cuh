@@ -40,13 +40,6 @@ struct ClusterArgs {
     float* tmp;                // [ncs*nsplit][R0][4096] raw sums, natural k'
 };
 
-PSG_DEV unsigned cluster_ctarank() {
-    unsigned r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-PSG_DEV void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-PSG_DEV void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 // exchange-slot read: written by other CTAs of the cluster during this kernel -> not the .nc path;
 // .cg keeps it out of L1 (the acquire of the cluster barrier orders it after the writers' release)
 PSG_DEV float2 ld_xchg(const float2* p) {
@@ -323,34 +316,8 @@ __global__ void __launch_bounds__(256, 2) sti_cluster_kernel(const ClusterArgs a
 //                                                frame r, so frame r+2 may be sent
 // Pre-pass of frame r+1 runs before the row transform of frame r: the data of a frame has a whole row
 // phase to cross the cluster, only the small "free" signal is waited for with no slack.
-PSG_DEV uint32_t map_cluster(uint32_t local_addr, unsigned rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
-    return r;
-}
-PSG_DEV void st_async_cf(uint32_t raddr, cf v, uint32_t rbar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(raddr),
-                 "f"(v.x), "f"(v.y), "r"(rbar)
-                 : "memory");
-}
 PSG_DEV void mbar_arrive_cluster(uint32_t rbar) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
-}
-// a wait that cannot hang the device: a protocol error traps instead of spinning forever
-PSG_DEV void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    for (int spins = 0;; ++spins) {
-        uint32_t done;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (done) return;
-        if (spins > (1 << 22)) asm volatile("trap;");
-    }
 }
 
 struct DsmemStep {  // ClusterStep + the address its slab is fetched from

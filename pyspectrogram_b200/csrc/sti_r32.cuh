@@ -1,0 +1,443 @@
+// nfft = 16384 / 32768 / 65536 in THREE shared-memory passes: 32 points per thread, frame in place.
+//
+// The four-pass whole-frame kernels (sti_whole.cuh) spend eight shared-memory accesses per sample and
+// stop at 36-40 % of the HBM peak with the LSU data pipe 64 % busy (profiles/r01_whole_frame_16384.txt).
+// This family needs 5.5:
+//   plan      N = 32 x L, L = 512 CL the row length, CL = N / 16384 CTAs of one cluster per frame.
+//             pass 0  radix 32 over n0 (elements n' + n0 L), thread <-> n' = 512 c + t of CTA c
+//             pass 1  radix 32 inside every row (stride L/32)
+//             pass 2  L/32-point DFTs on consecutive positions: radix 16 (L = 512), radix 32 (L = 1024),
+//                     radix 32 at stride 2 plus a radix-2 butterfly between lane pairs (SHFL) for L = 2048
+//   in place  every pass overwrites its own inputs; the buffer M (one CTA's rows, 128 KB) is not padded
+//             but XOR-swizzled -- the 16-byte chunk index inside a 128-byte line is XORed with three bits
+//             of the line index chosen so that the one pass whose lanes stride over lines (the last) is
+//             conflict-free with LDS.128 (LDS.64 for the stride-2 form); the 64-bit accesses of passes 0
+//             and 1 always cover whole lines per half-warp.
+//   loader    the CTA's 32 segments of 512 samples: 24 arrive by bulk copies (UBLKCP) in a staging area
+//             S (96 KB, one frame ahead, refilled by whichever warp reads it last), the other 8 straight
+//             into registers with LDG issued a pass ahead (their lines are pulled into L2 when the bulk
+//             copies are issued).  Integer IQ fits S whole.  128 KB + 96 KB fill the SM: one CTA of
+//             512 threads per SM.
+//   TMEM      the tensor memory (256 KB, unused by a kernel without MMAs) is this kernel's second
+//             register file: per thread 32 |X|^2 accumulators, its 32 window values and the twiddle
+//             powers W^{1,2,4,8,16} of passes 0 and 1 live there (tcgen05.st once, tcgen05.ld per frame:
+//             ~19 clk, no LSU wavefronts -- tools/ubench/tmem_probe.cu), so 32 complex points fit the
+//             128 registers a 512-thread CTA leaves per thread.
+//   cluster   CL > 1: CTA c owns rows k0 in [c 32/CL, (c+1) 32/CL); pass-0 outputs go to the owners with
+//             st.async (DSMEM, counted in bytes on the owner's mbarrier); passes 1 and 2 are local.
+//   sync per frame: mbarrier "S full", split "M free" (mbarrier of 16 warp arrivals, or the hardware
+//             cluster barrier: arrive after the last pass, wait before the first store of the next
+//             frame), one CTA barrier after pass 0; pass 1 -> 2 stays inside a warp (a pair of warps for
+//             L = 2048: named barrier).
+//   CTAs are persistent and walk work items (a column's chunk of frames) as one continuous frame
+//   pipeline, so Mode R (one frame per column) runs at the same rate as long integrations.
+// Index algebra restated in numpy and checked on the CPU by tests/test_fft_plan.py.
+#pragma once
+#include "sti_common.cuh"
+#include "r32_math.cuh"
+
+struct R32Args {
+    StiArgs s;    // tw = full table W_N^m; chunk / nsplit as in the other kernels
+    int nitems;   // ncol * nsub * nsplit
+    int ngroups;  // clusters (CTAs for CL = 1) in the grid
+};
+
+// ---- tensor memory as a scratch file ----------------------------------------------------------------------
+// .32x32b: thread i of warp w owns TMEM lane 32 (w % 4) + i; the address is warp-uniform (lane base << 16 | column)
+PSG_DEV void tmem_ld8(uint32_t taddr, float* r) {
+    uint32_t u[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(u[i]);
+}
+PSG_DEV void tmem_ld16(uint32_t taddr, float* r) {
+    uint32_t u[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+          "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
+}
+PSG_DEV void tmem_st8(uint32_t taddr, const float* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
+                 "r"(__float_as_uint(r[0])), "r"(__float_as_uint(r[1])), "r"(__float_as_uint(r[2])), "r"(__float_as_uint(r[3])),
+                 "r"(__float_as_uint(r[4])), "r"(__float_as_uint(r[5])), "r"(__float_as_uint(r[6])), "r"(__float_as_uint(r[7]))
+                 : "memory");
+}
+PSG_DEV void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---- geometry -------------------------------------------------------------------------------------------------
+template <int CL, int IQT>
+struct R32Cfg {
+    static constexpr int T = 512, NW = 16;
+    using G = R32Geo<CL>;
+    static constexpr int N = G::N, L = G::L, NR = G::NR, S1 = G::S1, SWSH = G::SWSH;
+    static constexpr int IQB = IqBytes<IQT>::value;
+    static constexpr int NSEG_S = (IQB == 8) ? 24 : 32;  // segments staged in S; the rest by LDG
+    static constexpr int NLDG = 32 - NSEG_S;
+    static constexpr int SEG = 512 * IQB + 16;  // staged segment + alignment slack
+    static constexpr int HDR = 128;
+    static constexpr int MBYTES = 16384 * 8;
+    static constexpr int RS = G::RS;
+    static constexpr size_t smem_bytes = HDR + (size_t)NSEG_S * SEG + MBYTES;
+    static_assert((size_t)NR * RS * 4 <= MBYTES, "epilogue staging fits M");
+    // TMEM columns of a warp's slot (128 per slot, slot = warp / 4)
+    static constexpr int C_ACC = 0, C_WIN = 32, C_PW0 = 64, C_PW1 = 80;
+};
+
+PSG_DEV cf lds_cf(uint32_t saddr) {
+    cf v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr));
+    return v;
+}
+PSG_DEV void sts_cf(uint32_t saddr, cf v) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(saddr), "f"(v.x), "f"(v.y) : "memory"); }
+PSG_DEV void lds_cf2(uint32_t saddr, cf& a, cf& b) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(b.x), "=f"(b.y) : "r"(saddr));
+}
+PSG_DEV void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+PSG_DEV void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+template <int CL, int IQT>
+__global__ void __launch_bounds__(512, 1) sti_r32_kernel(const R32Args ra) {
+    using CF = R32Cfg<CL, IQT>;
+    constexpr int T = CF::T, N = CF::N, L = CF::L, NR = CF::NR, S1 = CF::S1, SWSH = CF::SWSH, IQB = CF::IQB, NSEG_S = CF::NSEG_S,
+                  NLDG = CF::NLDG, SEG = CF::SEG, RS = CF::RS;
+    const StiArgs& a = ra.s;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* const bar_full = reinterpret_cast<uint64_t*>(smem_raw);        // S holds the next frame
+    uint64_t* const bar_mfree = reinterpret_cast<uint64_t*>(smem_raw + 8);   // CL == 1: the 16 warps are done with M
+    uint64_t* const bar_landed = reinterpret_cast<uint64_t*>(smem_raw + 16);  // CL > 1: the peers' pass-0 outputs (bytes)
+    unsigned* const cnt = reinterpret_cast<unsigned*>(smem_raw + 24);        // warps that have read S (running total)
+    uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 32);
+    unsigned char* const stage = smem_raw + CF::HDR;
+    const uint32_t m_base = smem_u32(smem_raw + CF::HDR + (size_t)NSEG_S * SEG);
+
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int c = (CL > 1) ? (int)cluster_ctarank() : 0;
+    const int group = blockIdx.x / CL;
+    const int np = c * 512 + t;  // this thread's n' in pass 0
+
+    // ---- work items: group g walks items g, g + ngroups, ...; one continuous sequence of frames ----
+    struct Cursor {
+        long long base;  // element offset of the frame's first sample
+        int item, f, nfr;
+        bool valid;
+    };
+    auto open_item = [&](Cursor& cu, int item) {
+        cu.item = item;
+        cu.valid = item < ra.nitems;
+        cu.f = 0;
+        cu.nfr = 0;
+        cu.base = 0;
+        if (cu.valid) {
+            const int split = item % a.nsplit, cs = item / a.nsplit;
+            const int col = cs % a.ncol, sub = cs / a.ncol;
+            const int kf0 = split * a.chunk;
+            cu.nfr = min(a.nfr, kf0 + a.chunk) - kf0;
+            cu.base = __ldg(a.col_off + col) + (long long)sub * a.sub_stride + (long long)kf0 * a.hop_elems;
+        }
+    };
+    auto advance = [&](const Cursor& cu) {
+        Cursor n = cu;
+        if (cu.f + 1 < cu.nfr) {
+            n.f = cu.f + 1;
+            n.base = cu.base + a.hop_elems;
+        } else {
+            open_item(n, cu.item + ra.ngroups);
+        }
+        return n;
+    };
+    // bulk copies of a frame's staged segments + L2 prefetch of the segments that go through registers (one thread)
+    auto issue = [&](long long base) {
+        const uintptr_t src0 = reinterpret_cast<uintptr_t>(a.iq) + (uintptr_t)((base + c * 512) * IQB);
+        const uint32_t bytes = 512 * IQB + ((src0 & 15) ? 16 : 0);
+        const uintptr_t al = src0 & ~(uintptr_t)15;
+        mbar_expect_tx(bar_full, bytes * NSEG_S);
+#pragma unroll 4
+        for (int s = 0; s < NSEG_S; ++s)
+            bulk_g2s(stage + s * SEG, reinterpret_cast<const void*>(al + (uintptr_t)s * L * IQB), bytes, bar_full);
+#pragma unroll
+        for (int s = NSEG_S; s < 32; ++s)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(al + (uintptr_t)s * L * IQB), "r"(bytes) : "memory");
+    };
+    cf pre[NLDG > 0 ? NLDG : 1];  // the frame's last NLDG segments, loaded a pass ahead
+    auto load_pre = [&](const Cursor& cu) {
+        if constexpr (NLDG > 0) {
+#pragma unroll
+            for (int i = 0; i < NLDG; ++i)
+                pre[i] = cu.valid ? ldg_iq<IQT>(a.iq, cu.base + np + (long long)(NSEG_S + i) * L) : make_float2(0.f, 0.f);
+        }
+    };
+
+    Cursor cur;
+    open_item(cur, group);
+    if (!cur.valid) return;  // uniform over the cluster; nothing allocated yet
+
+    // ---- setup: barriers, tensor memory, per-thread tables -> TMEM ----
+    if (t == 0) {
+        mbar_init(bar_full, 1);
+        mbar_init(bar_mfree, CF::NW);
+        mbar_init(bar_landed, 1);
+        *cnt = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (w == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = *tmem_slot + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(128 * (w >> 2));
+    constexpr uint32_t PEER_BYTES = (uint32_t)(CL - 1) * 512u * NR * 8u;  // (CL-1) peers x 512 columns x NR rows
+    if (t == 0) {
+        if constexpr (CL > 1) mbar_expect_tx(bar_landed, PEER_BYTES);  // frame 0
+        issue(cur.base);
+    }
+    load_pre(cur);
+    {
+        // window of this thread's samples n' + a L, a < 32: column 2 j = element j, column 2 j + 1 = element j + 16
+        float wv[8];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int j = 4 * m + (i >> 1), aa = j + 16 * (i & 1);
+                wv[i] = __ldg(a.win + np + aa * L);
+            }
+            tmem_st8(tmem + CF::C_WIN + 8 * m, wv);
+        }
+        // twiddle powers: pass 0  W_N^{n' 2^q},  pass 1  W_L^{c1 2^q} with c1 = t mod S1
+        const int c1 = t & (S1 - 1);
+        float p0[16], p1[16];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const float2 v0 = __ldg(a.tw + (((unsigned)np << q) & (N - 1)));
+            const float2 v1 = __ldg(a.tw + ((((unsigned)c1 << q) * 32u) & (N - 1)));
+            p0[2 * q] = v0.x; p0[2 * q + 1] = v0.y;
+            p1[2 * q] = v1.x; p1[2 * q + 1] = v1.y;
+        }
+#pragma unroll
+        for (int i = 10; i < 16; ++i) p0[i] = p1[i] = 0.f;
+        tmem_st8(tmem + CF::C_PW0, p0);
+        tmem_st8(tmem + CF::C_PW0 + 8, p0 + 8);
+        tmem_st8(tmem + CF::C_PW1, p1);
+        tmem_st8(tmem + CF::C_PW1 + 8, p1 + 8);
+        tmem_wait_st();
+    }
+    // pass-0 destinations: this thread's column n' of every row; the peers' copies of M and of "landed"
+    const uint32_t np_off = r32_p0_col<CL>(np);  // row r adds r * L * 8 (a multiple of 1024: the swizzle bits of n' stay)
+    uint32_t rbase[CL], rbar[CL];
+#pragma unroll
+    for (int s = 0; s < CL; ++s) {
+        rbase[s] = (CL > 1) ? map_cluster(m_base + np_off, (unsigned)s) : m_base + np_off;
+        rbar[s] = (CL > 1) ? map_cluster(smem_u32(bar_landed), (unsigned)s) : 0u;
+    }
+    if constexpr (CL > 1) {
+        __syncthreads();   // "landed" armed before the peers are released
+        cluster_arrive();  // matches the wait before the first store of frame 0
+    }
+
+    uint32_t q = 0;  // frames done by this CTA
+    for (;; ++q) {
+        const Cursor nxt = advance(cur);
+        const int skew = (int)(((reinterpret_cast<uintptr_t>(a.iq) + (uintptr_t)((cur.base + c * 512) * IQB)) & 15) / IQB);
+        cf x[32];
+        // ---- pass 0: samples -> registers, window folded into the first butterfly layer ----
+        mbar_wait_bounded(bar_full, q & 1);
+#pragma unroll
+        for (int s = 0; s < NSEG_S; ++s) x[s] = lds_iq<IQT>(stage + s * SEG, skew + t);
+        if constexpr (NLDG > 0) {
+#pragma unroll
+            for (int i = 0; i < NLDG; ++i) x[NSEG_S + i] = pre[i];
+        }
+        {
+            cf u[16], v[16];
+            float wv[16];
+            tmem_ld16(tmem + CF::C_WIN, wv);
+            dft32_layer8<0, true>(x, wv, u, v);
+            tmem_ld16(tmem + CF::C_WIN + 16, wv);
+            dft32_layer8<8, true>(x, wv, u, v);
+            // every load of S by this warp has been consumed: the warp that reads S last refills it
+            __syncwarp();
+            if (lane == 0) {
+                const unsigned old = count_reader(cnt);
+                if ((old & (CF::NW - 1)) == CF::NW - 1 && nxt.valid) issue(nxt.base);
+            }
+            dft32_finish(x, u, v);
+        }
+        {
+            float pf[16];
+            tmem_ld16(tmem + CF::C_PW0, pf);
+            cf pw[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) pw[i] = make_float2(pf[2 * i], pf[2 * i + 1]);
+            twiddle_dfs32(x, pw);
+        }
+        // M free: every warp (every CTA of the cluster) is past the last pass of the previous frame
+        if constexpr (CL > 1) {
+            cluster_wait();
+        } else {
+            if (q > 0) mbar_wait_bounded(bar_mfree, (q - 1) & 1);
+        }
+#pragma unroll
+        for (int k0 = 0; k0 < 32; ++k0) {
+            const int s = k0 / NR, r = k0 % NR;
+            const uint32_t off = (uint32_t)r * (L * 8);
+            if (CL == 1 || s == c) sts_cf(rbase[CL == 1 ? 0 : s] + off, x[k0]);
+            else st_async_cf(rbase[s] + off, x[k0], rbar[s]);
+        }
+        __syncthreads();  // this CTA's own pass-0 stores
+        if constexpr (CL > 1) {
+            mbar_wait_bounded(bar_landed, q & 1);  // the peers' (st.async, counted in bytes)
+            if (t == 0 && nxt.valid) mbar_expect_tx(bar_landed, PEER_BYTES);  // next frame: sent only after the cluster barrier
+        }
+        // ---- pass 1: radix 32 at stride S1 inside row r1 ----
+        {
+            const uint32_t base1 = m_base + r32_p1_base<CL>(t);
+#pragma unroll
+            for (int b = 0; b < 32; ++b) x[b] = lds_cf(base1 + r32_p1_off<CL>(t, b));
+            dft32(x);
+            {
+                float pf[16];
+                tmem_ld16(tmem + CF::C_PW1, pf);
+                cf pw[5];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) pw[i] = make_float2(pf[2 * i], pf[2 * i + 1]);
+                twiddle_dfs32(x, pw);
+            }
+#pragma unroll
+            for (int b = 0; b < 32; ++b) sts_cf(base1 + r32_p1_off<CL>(t, b), x[b]);
+        }
+        if constexpr (CL == 4) named_bar_sync(1 + (t >> 6), 64);  // a row is two warps
+        else __syncwarp();                                       // a warp owns whole rows
+        // next frame's register segments: in flight under pass 2
+        load_pre(nxt);
+        // ---- pass 2: the L/32-point DFTs on consecutive positions, |X|^2 into the accumulators (TMEM) ----
+        const bool first = cur.f == 0;
+        tmem_wait_st();  // the accumulator columns written by the previous frame
+        auto accumulate8 = [&](int m, const float* p) {  // acc[8 m .. 8 m + 7] += p
+            float acc[8];
+            if (first) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = p[i];
+            } else {
+                tmem_ld8(tmem + CF::C_ACC + 8 * m, acc);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] += p[i];
+            }
+            tmem_st8(tmem + CF::C_ACC + 8 * m, acc);
+        };
+        if constexpr (CL == 1) {
+            // rows 2 w and 2 w + 1, block k1 = lane of each: 16 consecutive elements = one line, chunk q ^ (lane & 7)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                cf y[16];
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) lds_cf2(m_base + r32_p2_addr<CL>(t, i, ch), y[2 * ch], y[2 * ch + 1]);
+                dft16(y);
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    float p[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) p[j] = fmaf(y[8 * m + j].x, y[8 * m + j].x, y[8 * m + j].y * y[8 * m + j].y);
+                    accumulate8(2 * i + m, p);
+                }
+            }
+        } else if constexpr (CL == 2) {
+            // row w, block k1 = lane: 32 consecutive elements = lines 2 lane, 2 lane + 1, chunk (j & 7) ^ (lane & 7)
+#pragma unroll
+            for (int ch = 0; ch < 16; ++ch) lds_cf2(m_base + r32_p2_addr<CL>(t, 0, ch), x[2 * ch], x[2 * ch + 1]);
+            dft32(x);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                float p[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) p[j] = fmaf(x[8 * m + j].x, x[8 * m + j].x, x[8 * m + j].y * x[8 * m + j].y);
+                accumulate8(m, p);
+            }
+        } else {
+            // row r2 = t / 64, k1 = (t % 64) / 2, e = t & 1: elements 64 k1 + 2 d + e, d < 32; then the radix-2
+            // butterfly over e between lanes l and l ^ 1: lane e = 0 finishes outputs q2 = i and i + 32, i < 16,
+            // lane e = 1 outputs 16 + i and 48 + i (W_64^{16 + i} = -j W_64^i)
+            const int e = t & 1;
+#pragma unroll
+            for (int d = 0; d < 32; ++d) x[d] = lds_cf(m_base + r32_p2_addr<CL>(t, 0, d));
+            dft32(x);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                float p[8];
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) {
+                    const int i = 4 * m + ii;
+                    const cf send = e ? x[i] : x[16 + i];
+                    const cf keep = e ? x[16 + i] : x[i];
+                    cf recv;
+                    recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+                    recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+                    r32_pair_finish(e, i, keep, recv, p[2 * ii], p[2 * ii + 1]);
+                }
+                accumulate8(m, p);
+            }
+        }
+        // ---- the item's last frame: accumulators -> fftshifted column, coalesced 128-bit stores ----
+        if (cur.f + 1 == cur.nfr) {
+            tmem_wait_st();
+            __syncthreads();  // every warp is done reading M (peers write to it only after the cluster barrier)
+            float* const sout = reinterpret_cast<float*>(smem_raw + CF::HDR + (size_t)NSEG_S * SEG);
+            // this CTA's bins: freq = k0 + 32 m, k0 = c NR + r; fftshift moves m by N/64; staged as sout[r RS + m']
+            constexpr int MM = N / 32, MSH = N / 64;
+#pragma unroll
+            for (int m8 = 0; m8 < 4; ++m8) {
+                float acc[8];
+                tmem_ld8(tmem + CF::C_ACC + 8 * m8, acc);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int ai = 8 * m8 + j;  // accumulator index -> (row r, m)
+                    int r, m;
+                    r32_acc_bin<CL>(t, ai, r, m);
+                    sout[r * RS + ((m + MSH) & (MM - 1))] = acc[j];
+                }
+            }
+            __syncthreads();
+            const int cs = cur.item / a.nsplit, split = cur.item % a.nsplit;
+            constexpr int QPM = NR / 4;  // float4 per m'
+            for (int e4 = t; e4 < MM * QPM; e4 += T) {
+                const int mp = e4 / QPM, r0 = 4 * (e4 % QPM);
+                float4 v4 = make_float4(sout[(r0 + 0) * RS + mp], sout[(r0 + 1) * RS + mp], sout[(r0 + 2) * RS + mp],
+                                        sout[(r0 + 3) * RS + mp]);
+                const size_t o4 = (size_t)(32 * mp + c * NR + r0) / 4;  // float4 index inside the column
+                if (a.nsplit > 1) {
+                    reinterpret_cast<float4*>(a.partial + ((size_t)cs * a.nsplit + split) * N)[o4] = v4;
+                } else {
+                    v4.x *= a.scale; v4.y *= a.scale; v4.z *= a.scale; v4.w *= a.scale;
+                    const size_t o = (size_t)cs * (N / 4) + o4;
+                    if (a.out_lin) reinterpret_cast<float4*>(a.out_lin)[o] = v4;
+                    if (a.out_db)
+                        reinterpret_cast<float4*>(a.out_db)[o] = make_float4(power_to_db(v4.x, a.eps), power_to_db(v4.y, a.eps),
+                                                                             power_to_db(v4.z, a.eps), power_to_db(v4.w, a.eps));
+                }
+            }
+        }
+        // ---- done with M ----
+        if constexpr (CL > 1) {
+            cluster_arrive_relaxed();
+        } else {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_mfree);
+        }
+        if (!nxt.valid) break;
+        cur = nxt;
+    }
+    if constexpr (CL > 1) cluster_wait();  // consume the last arrive; no peer writes to this CTA any more
+    tmem_wait_st();
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "n"(512));
+}

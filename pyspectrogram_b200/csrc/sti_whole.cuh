@@ -44,16 +44,6 @@ struct WholeCfg {
     static_assert(NSLAB % NST == 0 && NST <= 8, "the stage of a slab is a compile-time constant");
 };
 
-// Reader count of a stage.  Relaxed on purpose: an acq_rel atomic compiles to MEMBAR.ALL.CTA, which makes
-// the lane wait for every load it has in flight -- including the window loads issued ~700 clk ahead.
-// Ordering comes from the data flow: a warp's reads of the stage have been consumed by its butterflies
-// (and __syncwarp() has gathered the lanes) before lane 0 counts the warp, so the bulk copy the last
-// counter issues cannot overtake a read.
-PSG_DEV unsigned count_reader(unsigned* p) {
-    unsigned old;
-    asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(p)) : "memory");
-    return old;
-}
 
 template <int R0, int IQT, int NST>
 __global__ void __launch_bounds__(512, 1) sti_whole_kernel(const WholeArgs wa) {
@@ -285,7 +275,6 @@ struct WholeClCfg {
     static_assert((NPC / W) * NB == NSTEP, "eight steps per frame");
 };
 
-PSG_DEV void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 // W_16^K = exp(-2 pi j K / 16)
 template <int K>
 PSG_DEV cf w16_const() {
