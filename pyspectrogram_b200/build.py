@@ -38,11 +38,20 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in DEPS if os.path.exists(d))
 
 
+# headers only psg_r32.cu includes (editing them does not rebuild the big unit)
+R32_ONLY = ("sti_r32.cuh", "r32_math.cuh")
+R32_HDRS = ("psg_r32.h", "sti_r32.cuh", "r32_math.cuh", "sti_common.cuh", "cplx.cuh")
+
+
 def _unit_stale(src: str, obj: str) -> bool:
     if not os.path.exists(obj):
         return True
     t = os.path.getmtime(obj)
     hdrs = [d for d in DEPS if not d.endswith(".cu")]
+    if os.path.basename(src) == "psg_r32.cu":
+        hdrs = [d for d in hdrs if os.path.basename(d) in R32_HDRS]
+    else:
+        hdrs = [d for d in hdrs if os.path.basename(d) not in R32_ONLY]
     return any(os.path.getmtime(d) > t for d in [src, *hdrs] if os.path.exists(d))
 
 

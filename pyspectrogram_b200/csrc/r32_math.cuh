@@ -67,23 +67,32 @@ PSG_HD void dft32(cf* a) {
     dft32_finish(a, u, v);
 }
 
-// x[k] *= W^k, k = 1..31, from pw[q] = W^(2^q), q < 5, depth first (see tw_visit)
-template <int K, int QMIN>
-PSG_HD void tw32_visit(cf* x, const cf* pw, const cf tk) {
+// x[k] *= W^k, k = 1..31, from pw[q] = W^(2^q), q < 5, depth first (see tw_visit); every finished output is
+// handed to emit(k, x[k]) at once, so the stores of a pass interleave with its twiddle arithmetic instead of
+// forming a pure load/store phase behind it (the LSU phases are what the FMA pipe idles on, tools/r32_trace.py)
+template <int K, int QMIN, class F>
+PSG_HD void tw32_visit(cf* x, const cf* pw, const cf tk, F& emit) {
     x[K] = cmul(x[K], tk);
-    if constexpr (QMIN <= 0 && K + 1 < 32) tw32_visit<K + 1, 1>(x, pw, cmul(tk, pw[0]));
-    if constexpr (QMIN <= 1 && K + 2 < 32) tw32_visit<K + 2, 2>(x, pw, cmul(tk, pw[1]));
-    if constexpr (QMIN <= 2 && K + 4 < 32) tw32_visit<K + 4, 3>(x, pw, cmul(tk, pw[2]));
-    if constexpr (QMIN <= 3 && K + 8 < 32) tw32_visit<K + 8, 4>(x, pw, cmul(tk, pw[3]));
-    if constexpr (QMIN <= 4 && K + 16 < 32) tw32_visit<K + 16, 5>(x, pw, cmul(tk, pw[4]));
+    emit(K, x[K]);
+    if constexpr (QMIN <= 0 && K + 1 < 32) tw32_visit<K + 1, 1>(x, pw, cmul(tk, pw[0]), emit);
+    if constexpr (QMIN <= 1 && K + 2 < 32) tw32_visit<K + 2, 2>(x, pw, cmul(tk, pw[1]), emit);
+    if constexpr (QMIN <= 2 && K + 4 < 32) tw32_visit<K + 4, 3>(x, pw, cmul(tk, pw[2]), emit);
+    if constexpr (QMIN <= 3 && K + 8 < 32) tw32_visit<K + 8, 4>(x, pw, cmul(tk, pw[3]), emit);
+    if constexpr (QMIN <= 4 && K + 16 < 32) tw32_visit<K + 16, 5>(x, pw, cmul(tk, pw[4]), emit);
 }
-PSG_HD void twiddle_dfs32(cf* x, const cf* pw) {
-    tw32_visit<1, 1>(x, pw, pw[0]);
-    tw32_visit<2, 2>(x, pw, pw[1]);
-    tw32_visit<4, 3>(x, pw, pw[2]);
-    tw32_visit<8, 4>(x, pw, pw[3]);
-    tw32_visit<16, 5>(x, pw, pw[4]);
+template <class F>
+PSG_HD void twiddle_dfs32(cf* x, const cf* pw, F&& emit) {
+    emit(0, x[0]);
+    tw32_visit<1, 1>(x, pw, pw[0], emit);
+    tw32_visit<2, 2>(x, pw, pw[1], emit);
+    tw32_visit<4, 3>(x, pw, pw[2], emit);
+    tw32_visit<8, 4>(x, pw, pw[3], emit);
+    tw32_visit<16, 5>(x, pw, pw[4], emit);
 }
+struct R32NoEmit {
+    PSG_HD void operator()(int, cf) const {}
+};
+PSG_HD void twiddle_dfs32(cf* x, const cf* pw) { twiddle_dfs32(x, pw, R32NoEmit{}); }
 
 // W_64^i, i < 16 (the radix-2 butterfly of the L = 2048 rows); i is a compile-time constant after unrolling
 PSG_HD cf w64_table(int i) {
@@ -155,12 +164,11 @@ PSG_HD void r32_acc_bin(int t, int ai, int& r, int& m) {
     else { r = t >> 6; m = ((t & 63) >> 1) + 32 * (((t & 1) ? 16 : 0) + (ai >> 1) + 32 * (ai & 1)); }
 }
 // the radix-2 butterfly between the lanes of a pair (CL = 4): from this lane's 32 outputs y of the stride-2
-// DFT and the partner's (recv = the partner's y[e ? i : 16 + i]), powers of the two bins lane e finishes for i
-PSG_HD void r32_pair_finish(int e, int i, cf keep, cf recv, float& p0, float& p1) {
+// DFT and the partner's (recv = the partner's y[e ? i : 16 + i]), the two outputs lane e finishes for i
+PSG_HD void r32_pair_finish(int e, int i, cf keep, cf recv, cf& s0, cf& s1) {
     const cf y0 = e ? recv : keep;
     cf z = cmul(e ? keep : recv, w64_table(i));
     if (e) z = mul_nj(z);
-    const cf s0 = cadd(y0, z), s1 = csub(y0, z);
-    p0 = fmaf(s0.x, s0.x, s0.y * s0.y);
-    p1 = fmaf(s1.x, s1.x, s1.y * s1.y);
+    s0 = cadd(y0, z);
+    s1 = csub(y0, z);
 }

@@ -152,6 +152,19 @@ PSG_DEV void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// one probe of the barrier (no spin): issued early, its latency hides behind independent arithmetic
+PSG_DEV bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+
 // Reader count of a stage.  Relaxed on purpose: an acq_rel atomic compiles to MEMBAR.ALL.CTA, which makes
 // the lane wait for every load it has in flight -- including the window loads issued ~700 clk ahead.
 // Ordering comes from the data flow: a warp's reads of the stage have been consumed by its butterflies

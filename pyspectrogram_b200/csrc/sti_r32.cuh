@@ -35,11 +35,13 @@
 #pragma once
 #include "sti_common.cuh"
 #include "r32_math.cuh"
+#include <type_traits>
 
 struct R32Args {
     StiArgs s;    // tw = full table W_N^m; chunk / nsplit as in the other kernels
     int nitems;   // ncol * nsub * nsplit
     int ngroups;  // clusters (CTAs for CL = 1) in the grid
+    long long* trace;  // R32_TRACE: [frames][16 warps][events] clock64 of CTA 0, else unused
 };
 
 // ---- tensor memory as a scratch file ----------------------------------------------------------------------
@@ -73,7 +75,12 @@ PSG_DEV void tmem_st8(uint32_t taddr, const float* r) {
 PSG_DEV void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- geometry -------------------------------------------------------------------------------------------------
-template <int CL, int IQT>
+// OPT bit 0: the warps issue their pass-1 loads in groups of four (one warp per scheduler) behind the CTA barrier;
+//     bit 1: accumulators as (sum re^2, sum im^2) pairs: one FFMA2 per bin instead of FMUL + FFMA + FADD
+//     bit 2: TRACE -- CTA 0 records clock64 at the phase boundaries of frames 8..11 (tools/r32_trace.py)
+enum { R32_ORDER = 1, R32_ACC2 = 2, R32_TRACE = 4 };
+enum { R32_TRACE_EVENTS = 12, R32_TRACE_FRAME0 = 8, R32_TRACE_FRAMES = 4 };
+template <int CL, int IQT, int OPT = 0>
 struct R32Cfg {
     static constexpr int T = 512, NW = 16;
     using G = R32Geo<CL>;
@@ -81,14 +88,16 @@ struct R32Cfg {
     static constexpr int IQB = IqBytes<IQT>::value;
     static constexpr int NSEG_S = (IQB == 8) ? 24 : 32;  // segments staged in S; the rest by LDG
     static constexpr int NLDG = 32 - NSEG_S;
-    static constexpr int SEG = 512 * IQB + 16;  // staged segment + alignment slack
+    static constexpr int SEG = 512 * IQB + (CL == 1 ? 0 : 16);  // staged segment (+ alignment slack; CL = 1: one contiguous copy)
     static constexpr int HDR = 128;
     static constexpr int MBYTES = 16384 * 8;
     static constexpr int RS = G::RS;
-    static constexpr size_t smem_bytes = HDR + (size_t)NSEG_S * SEG + MBYTES;
+    static constexpr int SBYTES = NSEG_S * SEG + (CL == 1 ? 128 : 0);  // CL = 1: slack once, rounded so that M stays 128-byte aligned
+    static constexpr size_t smem_bytes = HDR + (size_t)SBYTES + MBYTES;
     static_assert((size_t)NR * RS * 4 <= MBYTES, "epilogue staging fits M");
     // TMEM columns of a warp's slot (128 per slot, slot = warp / 4)
-    static constexpr int C_ACC = 0, C_WIN = 32, C_PW0 = 64, C_PW1 = 80;
+    static constexpr int ACCW = (OPT & R32_ACC2) ? 64 : 32;
+    static constexpr int C_ACC = 0, C_WIN = ACCW, C_PW0 = ACCW + 32, C_PW1 = ACCW + 48;
 };
 
 PSG_DEV cf lds_cf(uint32_t saddr) {
@@ -101,11 +110,13 @@ PSG_DEV void lds_cf2(uint32_t saddr, cf& a, cf& b) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(b.x), "=f"(b.y) : "r"(saddr));
 }
 PSG_DEV void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+PSG_DEV void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 PSG_DEV void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-template <int CL, int IQT>
+template <int CL, int IQT, int OPT = 0>
 __global__ void __launch_bounds__(512, 1) sti_r32_kernel(const R32Args ra) {
-    using CF = R32Cfg<CL, IQT>;
+    using CF = R32Cfg<CL, IQT, OPT>;
+    constexpr bool ORDER = (OPT & R32_ORDER) != 0, ACC2 = (OPT & R32_ACC2) != 0, TRACE = (OPT & R32_TRACE) != 0;
     constexpr int T = CF::T, N = CF::N, L = CF::L, NR = CF::NR, S1 = CF::S1, SWSH = CF::SWSH, IQB = CF::IQB, NSEG_S = CF::NSEG_S,
                   NLDG = CF::NLDG, SEG = CF::SEG, RS = CF::RS;
     const StiArgs& a = ra.s;
@@ -116,7 +127,7 @@ __global__ void __launch_bounds__(512, 1) sti_r32_kernel(const R32Args ra) {
     unsigned* const cnt = reinterpret_cast<unsigned*>(smem_raw + 24);        // warps that have read S (running total)
     uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 32);
     unsigned char* const stage = smem_raw + CF::HDR;
-    const uint32_t m_base = smem_u32(smem_raw + CF::HDR + (size_t)NSEG_S * SEG);
+    const uint32_t m_base = smem_u32(smem_raw + CF::HDR + (size_t)CF::SBYTES);
 
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const int c = (CL > 1) ? (int)cluster_ctarank() : 0;
@@ -153,18 +164,35 @@ __global__ void __launch_bounds__(512, 1) sti_r32_kernel(const R32Args ra) {
         }
         return n;
     };
-    // bulk copies of a frame's staged segments + L2 prefetch of the segments that go through registers (one thread)
+    // bulk copies of a frame's staged segments + L2 prefetch of the segments that go through registers.
+    // CL = 1: the CTA's segments are the frame itself, contiguous: one bulk copy and one prefetch by thread 0.
+    // CL > 1: segments of 512 samples every L; issuing a bulk copy costs the issuing warp ~70 clk (tools/r32_trace.py:
+    // one thread issuing all 32 delayed its warp by 2000 clk a frame), so lane 0 of warp w issues segments w and
+    // w + 16; warp 0 also arms the barrier.
     auto issue = [&](long long base) {
         const uintptr_t src0 = reinterpret_cast<uintptr_t>(a.iq) + (uintptr_t)((base + c * 512) * IQB);
-        const uint32_t bytes = 512 * IQB + ((src0 & 15) ? 16 : 0);
+        const uint32_t slack = (src0 & 15) ? 16 : 0;
         const uintptr_t al = src0 & ~(uintptr_t)15;
-        mbar_expect_tx(bar_full, bytes * NSEG_S);
-#pragma unroll 4
-        for (int s = 0; s < NSEG_S; ++s)
-            bulk_g2s(stage + s * SEG, reinterpret_cast<const void*>(al + (uintptr_t)s * L * IQB), bytes, bar_full);
+        if constexpr (CL == 1) {
+            if (t == 0) {
+                const uint32_t bytes = NSEG_S * 512 * IQB + slack;
+                mbar_expect_tx(bar_full, bytes);
+                bulk_g2s(stage, reinterpret_cast<const void*>(al), bytes, bar_full);
+                if constexpr (NLDG > 0)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(al + (uintptr_t)NSEG_S * 512 * IQB),
+                                 "r"((uint32_t)(NLDG * 512 * IQB) + slack)
+                                 : "memory");
+            }
+        } else if (lane == 0) {
+            const uint32_t bytes = 512 * IQB + slack;
+            if (w == 0) mbar_expect_tx(bar_full, bytes * NSEG_S);
 #pragma unroll
-        for (int s = NSEG_S; s < 32; ++s)
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(al + (uintptr_t)s * L * IQB), "r"(bytes) : "memory");
+            for (int h = 0; h < 2; ++h) {
+                const int s = w + 16 * h;
+                if (s < NSEG_S) bulk_g2s(stage + s * SEG, reinterpret_cast<const void*>(al + (uintptr_t)s * L * IQB), bytes, bar_full);
+                else asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(al + (uintptr_t)s * L * IQB), "r"(bytes) : "memory");
+            }
+        }
     };
     cf pre[NLDG > 0 ? NLDG : 1];  // the frame's last NLDG segments, loaded a pass ahead
     auto load_pre = [&](const Cursor& cu) {
@@ -198,8 +226,8 @@ __global__ void __launch_bounds__(512, 1) sti_r32_kernel(const R32Args ra) {
     constexpr uint32_t PEER_BYTES = (uint32_t)(CL - 1) * 512u * NR * 8u;  // (CL-1) peers x 512 columns x NR rows
     if (t == 0) {
         if constexpr (CL > 1) mbar_expect_tx(bar_landed, PEER_BYTES);  // frame 0
-        issue(cur.base);
     }
+    issue(cur.base);
     load_pre(cur);
     {
         // window of this thread's samples n' + a L, a < 32: column 2 j = element j, column 2 j + 1 = element j + 16
@@ -245,17 +273,29 @@ __global__ void __launch_bounds__(512, 1) sti_r32_kernel(const R32Args ra) {
     }
 
     uint32_t q = 0;  // frames done by this CTA
+    // TRACE: x0 / x1 make the clock read depend on the arithmetic before it (the packed-math asm is not volatile)
+    auto mark = [&](int ev, float x0, float x1) {
+        if constexpr (TRACE) {
+            asm volatile("" ::"f"(x0), "f"(x1) : "memory");
+            if (blockIdx.x == 0 && lane == 0 && q >= R32_TRACE_FRAME0 && q < R32_TRACE_FRAME0 + R32_TRACE_FRAMES)
+                ra.trace[((q - R32_TRACE_FRAME0) * 16 + w) * R32_TRACE_EVENTS + ev] = clock64();
+        }
+    };
     for (;; ++q) {
         const Cursor nxt = advance(cur);
+        mark(0, 0.f, 0.f);
         const int skew = (int)(((reinterpret_cast<uintptr_t>(a.iq) + (uintptr_t)((cur.base + c * 512) * IQB)) & 15) / IQB);
         cf x[32];
+        bool mfree_ok = true;
         // ---- pass 0: samples -> registers, window folded into the first butterfly layer ----
         mbar_wait_bounded(bar_full, q & 1);
+        mark(1, 0.f, 0.f);
+        // in the order the first butterfly layer consumes them: (j, j + 16)
 #pragma unroll
-        for (int s = 0; s < NSEG_S; ++s) x[s] = lds_iq<IQT>(stage + s * SEG, skew + t);
-        if constexpr (NLDG > 0) {
-#pragma unroll
-            for (int i = 0; i < NLDG; ++i) x[NSEG_S + i] = pre[i];
+        for (int j = 0; j < 16; ++j) {
+            x[j] = lds_iq<IQT>(stage + j * SEG, skew + t);
+            if (j + 16 < NSEG_S) x[j + 16] = lds_iq<IQT>(stage + (j + 16) * SEG, skew + t);
+            else x[j + 16] = pre[j + 16 - NSEG_S];
         }
         {
             cf u[16], v[16];
@@ -264,45 +304,62 @@ __global__ void __launch_bounds__(512, 1) sti_r32_kernel(const R32Args ra) {
             dft32_layer8<0, true>(x, wv, u, v);
             tmem_ld16(tmem + CF::C_WIN + 16, wv);
             dft32_layer8<8, true>(x, wv, u, v);
-            // every load of S by this warp has been consumed: the warp that reads S last refills it
-            __syncwarp();
-            if (lane == 0) {
-                const unsigned old = count_reader(cnt);
-                if ((old & (CF::NW - 1)) == CF::NW - 1 && nxt.valid) issue(nxt.base);
-            }
+            mark(2, u[0].x, v[15].y);
+            // probe "M free" now: the answer arrives under the sixteen-point butterflies
+            if constexpr (CL == 1) mfree_ok = q == 0 || mbar_test(bar_mfree, (q - 1) & 1);
             dft32_finish(x, u, v);
         }
+        mark(3, x[1].x, x[31].y);
+        // M free: every warp (every CTA of the cluster) is past the last pass of the previous frame
+        if constexpr (CL > 1) {
+            cluster_wait();
+        } else {
+            if (!mfree_ok) mbar_wait_bounded(bar_mfree, (q - 1) & 1);
+        }
+        mark(4, 0.f, 0.f);
         {
+            // twiddle W_N^{n' k0} and store, output by output: row k0 % NR of CTA k0 / NR
             float pf[16];
             tmem_ld16(tmem + CF::C_PW0, pf);
             cf pw[5];
 #pragma unroll
             for (int i = 0; i < 5; ++i) pw[i] = make_float2(pf[2 * i], pf[2 * i + 1]);
-            twiddle_dfs32(x, pw);
+            twiddle_dfs32(x, pw, [&](int k0, cf v) {
+                const int s = k0 / NR, r = k0 % NR;
+                const uint32_t off = (uint32_t)r * (L * 8);
+                if (CL == 1 || s == c) sts_cf(rbase[CL == 1 ? 0 : s] + off, v);
+                else st_async_cf(rbase[s] + off, v, rbar[s]);
+            });
         }
-        // M free: every warp (every CTA of the cluster) is past the last pass of the previous frame
-        if constexpr (CL > 1) {
-            cluster_wait();
-        } else {
-            if (q > 0) mbar_wait_bounded(bar_mfree, (q - 1) & 1);
-        }
-#pragma unroll
-        for (int k0 = 0; k0 < 32; ++k0) {
-            const int s = k0 / NR, r = k0 % NR;
-            const uint32_t off = (uint32_t)r * (L * 8);
-            if (CL == 1 || s == c) sts_cf(rbase[CL == 1 ? 0 : s] + off, x[k0]);
-            else st_async_cf(rbase[s] + off, x[k0], rbar[s]);
-        }
+        mark(5, 0.f, 0.f);
         __syncthreads();  // this CTA's own pass-0 stores
         if constexpr (CL > 1) {
             mbar_wait_bounded(bar_landed, q & 1);  // the peers' (st.async, counted in bytes)
             if (t == 0 && nxt.valid) mbar_expect_tx(bar_landed, PEER_BYTES);  // next frame: sent only after the cluster barrier
         }
+        mark(6, 0.f, 0.f);
         // ---- pass 1: radix 32 at stride S1 inside row r1 ----
         {
             const uint32_t base1 = m_base + r32_p1_base<CL>(t);
+            // ORDER: behind the CTA barrier every warp wants the LSU at once and all of them get their data
+            // last; chained named barriers let warps 4 g .. 4 g + 3 (one per scheduler) issue their loads
+            // before group g + 1 does, so group 0 computes while the others still load
+            if constexpr (ORDER) {
+                if ((w >> 2) > 0) named_bar_sync(8 + (w >> 2), 256);
+            }
 #pragma unroll
-            for (int b = 0; b < 32; ++b) x[b] = lds_cf(base1 + r32_p1_off<CL>(t, b));
+            for (int j = 0; j < 16; ++j) {  // pair order of the first butterfly layer
+                x[j] = lds_cf(base1 + r32_p1_off<CL>(t, j));
+                x[j + 16] = lds_cf(base1 + r32_p1_off<CL>(t, j + 16));
+            }
+            if constexpr (ORDER) {
+                if ((w >> 2) < 3) named_bar_arrive(9 + (w >> 2), 256);
+            }
+            // S was consumed by every warp before the barrier.  It is refilled from here, not right after its last
+            // read: the bulk copies then land under the arithmetic of passes 1 and 2 instead of competing with the
+            // pass-0 stores and pass-1 loads, the one stretch of the frame that is bound by the shared-memory pipe
+            if (nxt.valid) issue(nxt.base);
+            mark(7, x[0].x, x[31].y);
             dft32(x);
             {
                 float pf[16];
@@ -310,29 +367,61 @@ __global__ void __launch_bounds__(512, 1) sti_r32_kernel(const R32Args ra) {
                 cf pw[5];
 #pragma unroll
                 for (int i = 0; i < 5; ++i) pw[i] = make_float2(pf[2 * i], pf[2 * i + 1]);
-                twiddle_dfs32(x, pw);
+                twiddle_dfs32(x, pw, [&](int k1, cf v) { sts_cf(base1 + r32_p1_off<CL>(t, k1), v); });
             }
-#pragma unroll
-            for (int b = 0; b < 32; ++b) sts_cf(base1 + r32_p1_off<CL>(t, b), x[b]);
+            mark(8, 0.f, 0.f);
         }
         if constexpr (CL == 4) named_bar_sync(1 + (t >> 6), 64);  // a row is two warps
         else __syncwarp();                                       // a warp owns whole rows
+        mark(9, 0.f, 0.f);
         // next frame's register segments: in flight under pass 2
         load_pre(nxt);
         // ---- pass 2: the L/32-point DFTs on consecutive positions, |X|^2 into the accumulators (TMEM) ----
         const bool first = cur.f == 0;
         tmem_wait_st();  // the accumulator columns written by the previous frame
-        auto accumulate8 = [&](int m, const float* p) {  // acc[8 m .. 8 m + 7] += p
-            float acc[8];
-            if (first) {
+        // bins bin0 .. bin0 + NB - 1 of this thread += |y|^2
+        auto accumulate = [&](int bin0, const cf* y, auto nb_tag) {
+            constexpr int NB = decltype(nb_tag)::value;
+            if constexpr (ACC2) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] = p[i];
+                for (int g = 0; g < NB / 4; ++g) {
+                    float acc[8];
+                    const uint32_t col = tmem + CF::C_ACC + 2 * bin0 + 8 * g;
+                    if (first) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const cf sq = mul2(y[4 * g + i], y[4 * g + i]);
+                            acc[2 * i] = sq.x;
+                            acc[2 * i + 1] = sq.y;
+                        }
+                    } else {
+                        tmem_ld8(col, acc);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const cf sq = fma2(y[4 * g + i], y[4 * g + i], make_float2(acc[2 * i], acc[2 * i + 1]));
+                            acc[2 * i] = sq.x;
+                            acc[2 * i + 1] = sq.y;
+                        }
+                    }
+                    tmem_st8(col, acc);
+                }
             } else {
-                tmem_ld8(tmem + CF::C_ACC + 8 * m, acc);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] += p[i];
+                for (int g = 0; g < NB / 8; ++g) {
+                    float acc[8];
+                    const uint32_t col = tmem + CF::C_ACC + bin0 + 8 * g;
+                    if (first) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[i] = fmaf(y[8 * g + i].x, y[8 * g + i].x, y[8 * g + i].y * y[8 * g + i].y);
+                    } else {
+                        tmem_ld8(col, acc);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            acc[i] += fmaf(y[8 * g + i].x, y[8 * g + i].x, y[8 * g + i].y * y[8 * g + i].y);
+                    }
+                    tmem_st8(col, acc);
+                }
             }
-            tmem_st8(tmem + CF::C_ACC + 8 * m, acc);
         };
         if constexpr (CL == 1) {
             // rows 2 w and 2 w + 1, block k1 = lane of each: 16 consecutive elements = one line, chunk q ^ (lane & 7)
@@ -342,26 +431,15 @@ __global__ void __launch_bounds__(512, 1) sti_r32_kernel(const R32Args ra) {
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch) lds_cf2(m_base + r32_p2_addr<CL>(t, i, ch), y[2 * ch], y[2 * ch + 1]);
                 dft16(y);
-#pragma unroll
-                for (int m = 0; m < 2; ++m) {
-                    float p[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) p[j] = fmaf(y[8 * m + j].x, y[8 * m + j].x, y[8 * m + j].y * y[8 * m + j].y);
-                    accumulate8(2 * i + m, p);
-                }
+                if (i == 0) mark(10, y[0].x, y[15].y);
+                accumulate(16 * i, y, std::integral_constant<int, 16>{});
             }
         } else if constexpr (CL == 2) {
             // row w, block k1 = lane: 32 consecutive elements = lines 2 lane, 2 lane + 1, chunk (j & 7) ^ (lane & 7)
 #pragma unroll
             for (int ch = 0; ch < 16; ++ch) lds_cf2(m_base + r32_p2_addr<CL>(t, 0, ch), x[2 * ch], x[2 * ch + 1]);
             dft32(x);
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                float p[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) p[j] = fmaf(x[8 * m + j].x, x[8 * m + j].x, x[8 * m + j].y * x[8 * m + j].y);
-                accumulate8(m, p);
-            }
+            accumulate(0, x, std::integral_constant<int, 32>{});
         } else {
             // row r2 = t / 64, k1 = (t % 64) / 2, e = t & 1: elements 64 k1 + 2 d + e, d < 32; then the radix-2
             // butterfly over e between lanes l and l ^ 1: lane e = 0 finishes outputs q2 = i and i + 32, i < 16,
@@ -372,7 +450,7 @@ __global__ void __launch_bounds__(512, 1) sti_r32_kernel(const R32Args ra) {
             dft32(x);
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
-                float p[8];
+                cf s[8];
 #pragma unroll
                 for (int ii = 0; ii < 4; ++ii) {
                     const int i = 4 * m + ii;
@@ -381,28 +459,30 @@ __global__ void __launch_bounds__(512, 1) sti_r32_kernel(const R32Args ra) {
                     cf recv;
                     recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
                     recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
-                    r32_pair_finish(e, i, keep, recv, p[2 * ii], p[2 * ii + 1]);
+                    r32_pair_finish(e, i, keep, recv, s[2 * ii], s[2 * ii + 1]);
                 }
-                accumulate8(m, p);
+                accumulate(8 * m, s, std::integral_constant<int, 8>{});
             }
         }
+        tmem_wait_st();
+        mark(11, 0.f, 0.f);
         // ---- the item's last frame: accumulators -> fftshifted column, coalesced 128-bit stores ----
         if (cur.f + 1 == cur.nfr) {
             tmem_wait_st();
             __syncthreads();  // every warp is done reading M (peers write to it only after the cluster barrier)
-            float* const sout = reinterpret_cast<float*>(smem_raw + CF::HDR + (size_t)NSEG_S * SEG);
+            float* const sout = reinterpret_cast<float*>(smem_raw + CF::HDR + (size_t)CF::SBYTES);
             // this CTA's bins: freq = k0 + 32 m, k0 = c NR + r; fftshift moves m by N/64; staged as sout[r RS + m']
             constexpr int MM = N / 32, MSH = N / 64;
 #pragma unroll
-            for (int m8 = 0; m8 < 4; ++m8) {
+            for (int m8 = 0; m8 < CF::ACCW / 8; ++m8) {
                 float acc[8];
                 tmem_ld8(tmem + CF::C_ACC + 8 * m8, acc);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int ai = 8 * m8 + j;  // accumulator index -> (row r, m)
+                for (int j = 0; j < (ACC2 ? 4 : 8); ++j) {
+                    const int ai = (ACC2 ? 4 : 8) * m8 + j;  // accumulator index -> (row r, m)
                     int r, m;
                     r32_acc_bin<CL>(t, ai, r, m);
-                    sout[r * RS + ((m + MSH) & (MM - 1))] = acc[j];
+                    sout[r * RS + ((m + MSH) & (MM - 1))] = ACC2 ? acc[2 * j] + acc[2 * j + 1] : acc[j];
                 }
             }
             __syncthreads();

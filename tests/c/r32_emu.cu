@@ -190,7 +190,10 @@ static void run(unsigned seed) {
                 for (int i = 0; i < 16; ++i) {
                     const cf keep = e ? y[t][16 + i] : y[t][i];
                     const cf recv = e ? y[t ^ 1][16 + i] : y[t ^ 1][i];  // what the partner (e' = 1 - e) sends: its y[e' ? i : 16 + i]
-                    r32_pair_finish(e, i, keep, recv, acc[t][2 * i], acc[t][2 * i + 1]);
+                    cf s0, s1;
+                    r32_pair_finish(e, i, keep, recv, s0, s1);
+                    acc[t][2 * i] = fmaf(s0.x, s0.x, s0.y * s0.y);
+                    acc[t][2 * i + 1] = fmaf(s1.x, s1.x, s1.y * s1.y);
                 }
             }
         }
