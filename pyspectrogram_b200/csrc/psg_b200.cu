@@ -1224,8 +1224,11 @@ static int run_r32(psg_plan* p, const StiArgs& a0, int ncs, int frames_per_col, 
         g_launches++;
     }
     CUDA_TRY(cudaGetLastError());
-    snprintf(p->variant_name, sizeof(p->variant_name), "r32_%s%s%s", N == 16384 ? "32x32x16" : N == 32768 ? "32x32x32_c2" : "32x32x2x32_c4",
-             "", a0.iq_type == IQ_CI16 ? "_i16" : a0.iq_type == IQ_CI8 ? "_i8" : "");
+    int thr = 0, cl = 0;
+    psg_r32_describe(p->logn, &thr, &cl);
+    snprintf(p->variant_name, sizeof(p->variant_name), "r32_%s_t%dc%d%s",
+             N == 8192 ? "32x16x16" : N == 16384 ? "32x32x16" : N == 32768 ? "32x32x32" : "32x32x2x32", thr, cl,
+             a0.iq_type == IQ_CI16 ? "_i16" : a0.iq_type == IQ_CI8 ? "_i8" : "");
     *ran = true;
     return PSG_OK;
 }
@@ -1630,8 +1633,12 @@ extern "C" int psg_sti_run_typed(psg_plan* p, const void* iq_dev, int iq_type, i
             force_r32 = g_variant_override == "r32";
             other_path = !g_variant_override.empty() && !force_r32;
         }
-        // 16384 / 32768 / 65536 points: three-pass radix-32 kernels (sti_r32.cuh), the measured default
-        if (p->logn >= 14 && p->logn <= 16 && tma_ok && !v && (force_r32 || !other_path)) {
+        // 16384 / 32768 / 65536 points: three-pass radix-32 kernels (sti_r32.cuh), the measured default;
+        // 8192 points: the same kernel with 256 threads, two CTAs per SM (selectable: "r32")
+        // (default there for one frame per column: 333 against 250 Gsamples/s; with integration the 16x16x2x16
+        // kernel stays ahead, 61 % against 55 % of the HBM peak)
+        const bool r32_8192 = p->logn == 13 && frames_per_col == 1 && !other_path && g_use_multi.load();
+        if (((p->logn >= 14 && p->logn <= 16 && !v && !other_path) || r32_8192 || (force_r32 && p->logn >= 13 && p->logn <= 16)) && tma_ok) {
             bool ran = false;
             const int rcr = run_r32(p, a, ncs, frames_per_col, st, &ran);
             if (rcr || ran) return rcr;

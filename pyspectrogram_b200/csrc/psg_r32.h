@@ -10,3 +10,5 @@
 int psg_r32_max_groups(int logn, int iq_type, int device, int sms, int* ngroups);
 // enqueue the kernel: `a` complete (chunk / nsplit / partial set), nitems = ncol * nsub * nsplit
 int psg_r32_launch(int logn, int iq_type, const StiArgs& a, int nitems, int ngroups, cudaStream_t st);
+// threads per CTA and cluster size of the kernel psg_r32_launch would run for this size
+void psg_r32_describe(int logn, int* threads, int* cl);

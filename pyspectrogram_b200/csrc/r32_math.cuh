@@ -89,6 +89,24 @@ PSG_HD void twiddle_dfs32(cf* x, const cf* pw, F&& emit) {
     tw32_visit<8, 4>(x, pw, pw[3], emit);
     tw32_visit<16, 5>(x, pw, pw[4], emit);
 }
+// the same for a 16-point butterfly (pw[q], q < 4)
+template <int K, int QMIN, class F>
+PSG_HD void tw16_visit(cf* x, const cf* pw, const cf tk, F& emit) {
+    x[K] = cmul(x[K], tk);
+    emit(K, x[K]);
+    if constexpr (QMIN <= 0 && K + 1 < 16) tw16_visit<K + 1, 1>(x, pw, cmul(tk, pw[0]), emit);
+    if constexpr (QMIN <= 1 && K + 2 < 16) tw16_visit<K + 2, 2>(x, pw, cmul(tk, pw[1]), emit);
+    if constexpr (QMIN <= 2 && K + 4 < 16) tw16_visit<K + 4, 3>(x, pw, cmul(tk, pw[2]), emit);
+    if constexpr (QMIN <= 3 && K + 8 < 16) tw16_visit<K + 8, 4>(x, pw, cmul(tk, pw[3]), emit);
+}
+template <class F>
+PSG_HD void twiddle_dfs16(cf* x, const cf* pw, F&& emit) {
+    emit(0, x[0]);
+    tw16_visit<1, 1>(x, pw, pw[0], emit);
+    tw16_visit<2, 2>(x, pw, pw[1], emit);
+    tw16_visit<4, 3>(x, pw, pw[2], emit);
+    tw16_visit<8, 4>(x, pw, pw[3], emit);
+}
 struct R32NoEmit {
     PSG_HD void operator()(int, cf) const {}
 };
@@ -111,43 +129,61 @@ PSG_HD constexpr uint32_t r32_swz(uint32_t pos) {
 }
 
 // ---- geometry (independent of the sample type) ------------------------------------------------------------------
-template <int CL>
+// N = 2^LOGN = 32 L; a CTA of T threads owns T columns n' of pass 0 and NR = 32 T / L rows of length L afterwards;
+// CL = L / T CTAs (one cluster) share a frame.  Rows: L = R1 S1, pass 1 radix R1 at stride S1, pass 2 the S1-point
+// DFTs on consecutive positions (S1 = 16: radix 16; 32: radix 32; 64: radix 32 at stride 2 + a lane-pair butterfly).
+//   8192  = 32 x 256 (T = 256, two CTAs per SM)      rows 16 x 16
+//   16384 = 32 x 512 (T = 512; or T = 256 on pairs)   rows 32 x 16
+//   32768 = 32 x 1024 (T = 512 on pairs)              rows 32 x 32
+//   65536 = 32 x 2048 (T = 512 on clusters of four)   rows 32 x 32 x 2
+template <int LOGN, int T_>
 struct R32Geo {
-    static constexpr int N = 16384 * CL, L = 512 * CL, NR = 32 / CL, S1 = L / 32;
-    static constexpr int SWSH = (CL == 1) ? 0 : (CL == 2) ? 1 : 2;  // line-index bits XORed into the chunk index
+    static constexpr int N = 1 << LOGN, T = T_, L = N / 32, CL = L / T, NR = 32 / CL;
+    static constexpr int R1 = (L >= 512) ? 32 : 16, S1 = L / R1, NB1 = 32 / R1;
+    static constexpr int SWSH = (S1 == 16) ? 0 : (S1 == 32) ? 1 : 2;  // line-index bits XORed into the chunk index
     static constexpr int RS = L + CL;  // row stride of the epilogue's staging, in floats
-    static_assert(CL == 1 || CL == 2 || CL == 4, "16384, 32768 or 65536 points");
+    static_assert(L % T == 0 && (CL == 1 || CL == 2 || CL == 4 || CL == 8) && NR * CL == 32, "cluster shape");
+    static_assert(S1 == 16 || S1 == 32 || S1 == 64, "row plan");
+    static_assert(T % 32 == 0 && NR * S1 == T * NB1, "NB1 pass-1 butterflies per thread");
 };
 
 // Byte offsets inside M.  Each is r32_swz(pos) of the element it names, written so that everything but the
 // thread-dependent part folds into an immediate once the loops are unrolled (checked against r32_swz on the CPU).
-// pass 0: output k0 of column n' (n' = 512 c + t) -> row r = k0 % NR of CTA k0 / NR, element r L + n'
-template <int CL>
-PSG_HD uint32_t r32_p0_col(int np) { return r32_swz<R32Geo<CL>::SWSH>((uint32_t)np); }  // + r * L * 8
-// pass 1: thread t <-> (row r1 = t / S1, c1 = t % S1), element r1 L + b S1 + c1; the swizzle bits are b & 7
-template <int CL>
-PSG_HD uint32_t r32_p1_base(int t) {
-    constexpr int L = R32Geo<CL>::L, S1 = R32Geo<CL>::S1;
-    const int r1 = t / S1, c1 = t & (S1 - 1);
-    return (uint32_t)r1 * (L * 8) + (uint32_t)(c1 >> 4) * 128u + (uint32_t)(c1 & 1) * 8u;
+// pass 0: output k0 of column n' (n' = T c + t) -> row r = k0 % NR of CTA k0 / NR, element r L + n'
+template <class G>
+PSG_HD uint32_t r32_p0_col(int np) { return r32_swz<G::SWSH>((uint32_t)np); }  // + r * L * 8
+// pass 1: butterfly i of thread t is (row r1, c1) = divmod(t + i T, S1), element r1 L + b S1 + c1; swizzle bits b & 7
+template <class G>
+PSG_HD uint32_t r32_p1_base(int t, int i) {
+    const int id = t + i * G::T, r1 = id / G::S1, c1 = id & (G::S1 - 1);
+    return (uint32_t)r1 * (G::L * 8) + (uint32_t)(c1 >> 4) * 128u + (uint32_t)(c1 & 1) * 8u;
 }
-template <int CL>
+template <class G>
 PSG_HD uint32_t r32_p1_off(int t, int b) {
-    constexpr int S1 = R32Geo<CL>::S1;
-    const uint32_t cc = (uint32_t)(((t & (S1 - 1)) & 15) >> 1);
-    return (uint32_t)b * (S1 * 8) + ((cc ^ (uint32_t)(b & 7)) << 4);
+    const uint32_t cc = (uint32_t)(((t & (G::S1 - 1)) & 15) >> 1);  // c1 does not depend on i: T is a multiple of S1
+    return (uint32_t)b * (G::S1 * 8) + ((cc ^ (uint32_t)(b & 7)) << 4);
 }
 // pass 2
-//   CL = 1: rows 2 w + i (i < 2), block k1 = lane of each: 16 consecutive elements = one line; j = 16-byte chunk (elements 2 j, 2 j + 1)
-//   CL = 2: row w, block k1 = lane: 32 consecutive elements = two lines; j = chunk < 16
-//   CL = 4: row t / 64, k1 = (t % 64) / 2, e = t & 1: elements 64 k1 + 2 j + e, j < 32 (64-bit accesses)
-template <int CL>
+//   S1 = 16: a warp's pass-1 rows hold 64 blocks of 16 consecutive elements (one line each); lane takes blocks
+//            jj = lane + 32 i (i < 2): row 2 w + (jj / R1 >> 1) T / 16 + (jj / R1 & 1), block k1 = jj % R1;
+//            j = 16-byte chunk (elements 2 j, 2 j + 1)
+//   S1 = 32: row w, block k1 = lane: 32 consecutive elements = two lines; j = chunk < 16
+//   S1 = 64: row t / 64, k1 = (t % 64) / 2, e = t & 1: elements 64 k1 + 2 j + e, j < 32 (64-bit accesses)
+template <class G>
+PSG_HD void r32_p2_block(int t, int i, int& row, int& k1) {  // S1 = 16
+    const int lane = t & 31, w = t >> 5, jj = lane + 32 * i, sel = jj / G::R1;
+    row = 2 * w + (sel >> 1) * (G::T / 16) + (sel & 1);
+    k1 = jj % G::R1;
+}
+template <class G>
 PSG_HD uint32_t r32_p2_addr(int t, int i, int j) {
-    constexpr int L = R32Geo<CL>::L;
+    constexpr int L = G::L;
     const int lane = t & 31, w = t >> 5;
-    if constexpr (CL == 1) {
-        return (uint32_t)(2 * w + i) * (L * 8) + (uint32_t)lane * 128u + (((uint32_t)j ^ (uint32_t)(lane & 7)) << 4);
-    } else if constexpr (CL == 2) {
+    if constexpr (G::S1 == 16) {
+        int row, k1;
+        r32_p2_block<G>(t, i, row, k1);
+        return (uint32_t)row * (L * 8) + (uint32_t)k1 * 128u + (((uint32_t)j ^ (uint32_t)(k1 & 7)) << 4);
+    } else if constexpr (G::S1 == 32) {
         return (uint32_t)w * (L * 8) + (uint32_t)lane * 256u + (uint32_t)(j >> 3) * 128u + (((uint32_t)(j & 7) ^ (uint32_t)(lane & 7)) << 4);
     } else {
         const int r2 = t >> 6, k1 = (t & 63) >> 1, e = t & 1;
@@ -156,14 +192,22 @@ PSG_HD uint32_t r32_p2_addr(int t, int i, int j) {
     }
 }
 // accumulator ai of thread t holds the bin  freq = (c NR + r) + 32 m  of the frame
-template <int CL>
+template <class G>
 PSG_HD void r32_acc_bin(int t, int ai, int& r, int& m) {
     const int lane = t & 31, w = t >> 5;
-    if constexpr (CL == 1) { r = 2 * w + (ai >> 4); m = lane + 32 * (ai & 15); }
-    else if constexpr (CL == 2) { r = w; m = lane + 32 * ai; }
-    else { r = t >> 6; m = ((t & 63) >> 1) + 32 * (((t & 1) ? 16 : 0) + (ai >> 1) + 32 * (ai & 1)); }
+    if constexpr (G::S1 == 16) {
+        int k1;
+        r32_p2_block<G>(t, ai >> 4, r, k1);
+        m = k1 + G::R1 * (ai & 15);
+    } else if constexpr (G::S1 == 32) {
+        r = w;
+        m = lane + 32 * ai;
+    } else {
+        r = t >> 6;
+        m = ((t & 63) >> 1) + 32 * (((t & 1) ? 16 : 0) + (ai >> 1) + 32 * (ai & 1));
+    }
 }
-// the radix-2 butterfly between the lanes of a pair (CL = 4): from this lane's 32 outputs y of the stride-2
+// the radix-2 butterfly between the lanes of a pair (S1 = 64): from this lane's 32 outputs y of the stride-2
 // DFT and the partner's (recv = the partner's y[e ? i : 16 + i]), the two outputs lane e finishes for i
 PSG_HD void r32_pair_finish(int e, int i, cf keep, cf recv, cf& s0, cf& s1) {
     const cf y0 = e ? recv : keep;

@@ -1,13 +1,14 @@
-// nfft = 16384 / 32768 / 65536 in THREE shared-memory passes: 32 points per thread, frame in place.
+// nfft = 8192 / 16384 / 32768 / 65536 in THREE shared-memory passes: 32 points per thread, frame in place.
 //
 // The four-pass whole-frame kernels (sti_whole.cuh) spend eight shared-memory accesses per sample and
 // stop at 36-40 % of the HBM peak with the LSU data pipe 64 % busy (profiles/r01_whole_frame_16384.txt).
 // This family needs 5.5:
-//   plan      N = 32 x L, L = 512 CL the row length, CL = N / 16384 CTAs of one cluster per frame.
-//             pass 0  radix 32 over n0 (elements n' + n0 L), thread <-> n' = 512 c + t of CTA c
-//             pass 1  radix 32 inside every row (stride L/32)
-//             pass 2  L/32-point DFTs on consecutive positions: radix 16 (L = 512), radix 32 (L = 1024),
-//                     radix 32 at stride 2 plus a radix-2 butterfly between lane pairs (SHFL) for L = 2048
+//   plan      N = 32 x L, L the row length; a CTA of T threads owns T columns, CL = L / T CTAs (one cluster)
+//             share a frame (geometries: R32Geo in r32_math.cuh).
+//             pass 0  radix 32 over n0 (elements n' + n0 L), thread <-> n' = T c + t of CTA c
+//             pass 1  radix R1 = 32 (16 for L = 256) inside every row, stride S1 = L / R1
+//             pass 2  S1-point DFTs on consecutive positions: radix 16 (S1 = 16), radix 32 (S1 = 32),
+//                     radix 32 at stride 2 plus a radix-2 butterfly between lane pairs (SHFL) for S1 = 64
 //   in place  every pass overwrites its own inputs; the buffer M (one CTA's rows, 128 KB) is not padded
 //             but XOR-swizzled -- the 16-byte chunk index inside a 128-byte line is XORed with three bits
 //             of the line index chosen so that the one pass whose lanes stride over lines (the last) is
@@ -16,8 +17,9 @@
 //   loader    the CTA's 32 segments of 512 samples: 24 arrive by bulk copies (UBLKCP) in a staging area
 //             S (96 KB, one frame ahead, refilled by whichever warp reads it last), the other 8 straight
 //             into registers with LDG issued a pass ahead (their lines are pulled into L2 when the bulk
-//             copies are issued).  Integer IQ fits S whole.  128 KB + 96 KB fill the SM: one CTA of
-//             512 threads per SM.
+//             copies are issued).  Integer IQ fits S whole.  T = 512: 128 KB + 96 KB fill the SM, one CTA
+//             per SM; T = 256 (8192 points): 64 KB + 48 KB, two independent CTAs per SM whose phases
+//             interleave (one computes while the other moves data).
 //   TMEM      the tensor memory (256 KB, unused by a kernel without MMAs) is this kernel's second
 //             register file: per thread 32 |X|^2 accumulators, its 32 window values and the twiddle
 //             powers W^{1,2,4,8,16} of passes 0 and 1 live there (tcgen05.st once, tcgen05.ld per frame:
@@ -80,21 +82,20 @@ PSG_DEV void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: 
 //     bit 2: TRACE -- CTA 0 records clock64 at the phase boundaries of frames 8..11 (tools/r32_trace.py)
 enum { R32_ORDER = 1, R32_ACC2 = 2, R32_TRACE = 4 };
 enum { R32_TRACE_EVENTS = 12, R32_TRACE_FRAME0 = 8, R32_TRACE_FRAMES = 4 };
-template <int CL, int IQT, int OPT = 0>
+template <int LOGN, int T_, int IQT, int OPT = 0>
 struct R32Cfg {
-    static constexpr int T = 512, NW = 16;
-    using G = R32Geo<CL>;
-    static constexpr int N = G::N, L = G::L, NR = G::NR, S1 = G::S1, SWSH = G::SWSH;
+    using G = R32Geo<LOGN, T_>;
+    static constexpr int T = T_, NW = T / 32;
     static constexpr int IQB = IqBytes<IQT>::value;
     static constexpr int NSEG_S = (IQB == 8) ? 24 : 32;  // segments staged in S; the rest by LDG
     static constexpr int NLDG = 32 - NSEG_S;
-    static constexpr int SEG = 512 * IQB + (CL == 1 ? 0 : 16);  // staged segment (+ alignment slack; CL = 1: one contiguous copy)
+    static constexpr int SEG = T * IQB + (G::CL == 1 ? 0 : 16);  // staged segment (+ alignment slack; CL = 1: one contiguous copy)
     static constexpr int HDR = 128;
-    static constexpr int MBYTES = 16384 * 8;
-    static constexpr int RS = G::RS;
-    static constexpr int SBYTES = NSEG_S * SEG + (CL == 1 ? 128 : 0);  // CL = 1: slack once, rounded so that M stays 128-byte aligned
+    static constexpr int MBYTES = T * 32 * 8;
+    static constexpr int SBYTES = NSEG_S * SEG + (G::CL == 1 ? 128 : 0);  // CL = 1: slack once, rounded so that M stays 128-byte aligned
     static constexpr size_t smem_bytes = HDR + (size_t)SBYTES + MBYTES;
-    static_assert((size_t)NR * RS * 4 <= MBYTES, "epilogue staging fits M");
+    static_assert(SBYTES % 128 == 0, "M is 128-byte aligned");
+    static_assert((size_t)G::NR * G::RS * 4 <= MBYTES, "epilogue staging fits M");
     // TMEM columns of a warp's slot (128 per slot, slot = warp / 4)
     static constexpr int ACCW = (OPT & R32_ACC2) ? 64 : 32;
     static constexpr int C_ACC = 0, C_WIN = ACCW, C_PW0 = ACCW + 32, C_PW1 = ACCW + 48;
@@ -110,21 +111,26 @@ PSG_DEV void lds_cf2(uint32_t saddr, cf& a, cf& b) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(b.x), "=f"(b.y) : "r"(saddr));
 }
 PSG_DEV void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
-PSG_DEV void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+// barrier ids as immediates: with an id in a register ptxas reserves all 16 barriers for the CTA, and two CTAs do
+// not fit one SM any more (measured: the 8192-point form ran one CTA per SM)
+template <int ID, int NTHREADS>
+PSG_DEV void named_bar_arrive_c() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(NTHREADS) : "memory"); }
+template <int ID, int NTHREADS>
+PSG_DEV void named_bar_sync_c() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(NTHREADS) : "memory"); }
 PSG_DEV void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-template <int CL, int IQT, int OPT = 0>
-__global__ void __launch_bounds__(512, 1) sti_r32_kernel(const R32Args ra) {
-    using CF = R32Cfg<CL, IQT, OPT>;
+template <int LOGN, int T_, int IQT, int OPT = 0>
+__global__ void __launch_bounds__(T_, 512 / T_) sti_r32_kernel(const R32Args ra) {
+    using CF = R32Cfg<LOGN, T_, IQT, OPT>;
+    using G = typename CF::G;
     constexpr bool ORDER = (OPT & R32_ORDER) != 0, ACC2 = (OPT & R32_ACC2) != 0, TRACE = (OPT & R32_TRACE) != 0;
-    constexpr int T = CF::T, N = CF::N, L = CF::L, NR = CF::NR, S1 = CF::S1, SWSH = CF::SWSH, IQB = CF::IQB, NSEG_S = CF::NSEG_S,
-                  NLDG = CF::NLDG, SEG = CF::SEG, RS = CF::RS;
+    constexpr int T = CF::T, NW = CF::NW, N = G::N, L = G::L, CL = G::CL, NR = G::NR, R1 = G::R1, S1 = G::S1, NB1 = G::NB1,
+                  IQB = CF::IQB, NSEG_S = CF::NSEG_S, NLDG = CF::NLDG, SEG = CF::SEG, RS = G::RS;
     const StiArgs& a = ra.s;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* const bar_full = reinterpret_cast<uint64_t*>(smem_raw);        // S holds the next frame
-    uint64_t* const bar_mfree = reinterpret_cast<uint64_t*>(smem_raw + 8);   // CL == 1: the 16 warps are done with M
+    uint64_t* const bar_mfree = reinterpret_cast<uint64_t*>(smem_raw + 8);   // CL == 1: every warp is done with M
     uint64_t* const bar_landed = reinterpret_cast<uint64_t*>(smem_raw + 16);  // CL > 1: the peers' pass-0 outputs (bytes)
-    unsigned* const cnt = reinterpret_cast<unsigned*>(smem_raw + 24);        // warps that have read S (running total)
     uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 32);
     unsigned char* const stage = smem_raw + CF::HDR;
     const uint32_t m_base = smem_u32(smem_raw + CF::HDR + (size_t)CF::SBYTES);
@@ -132,7 +138,7 @@ __global__ void __launch_bounds__(512, 1) sti_r32_kernel(const R32Args ra) {
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const int c = (CL > 1) ? (int)cluster_ctarank() : 0;
     const int group = blockIdx.x / CL;
-    const int np = c * 512 + t;  // this thread's n' in pass 0
+    const int np = c * T + t;  // this thread's n' in pass 0
 
     // ---- work items: group g walks items g, g + ngroups, ...; one continuous sequence of frames ----
     struct Cursor {
@@ -166,29 +172,29 @@ __global__ void __launch_bounds__(512, 1) sti_r32_kernel(const R32Args ra) {
     };
     // bulk copies of a frame's staged segments + L2 prefetch of the segments that go through registers.
     // CL = 1: the CTA's segments are the frame itself, contiguous: one bulk copy and one prefetch by thread 0.
-    // CL > 1: segments of 512 samples every L; issuing a bulk copy costs the issuing warp ~70 clk (tools/r32_trace.py:
-    // one thread issuing all 32 delayed its warp by 2000 clk a frame), so lane 0 of warp w issues segments w and
-    // w + 16; warp 0 also arms the barrier.
+    // CL > 1: segments of T samples every L; issuing a bulk copy costs the issuing warp ~70 clk (tools/r32_trace.py:
+    // one thread issuing all 32 delayed its warp by 2000 clk a frame), so lane 0 of warp w issues segments w,
+    // w + NW, ..; warp 0 also arms the barrier.
     auto issue = [&](long long base) {
-        const uintptr_t src0 = reinterpret_cast<uintptr_t>(a.iq) + (uintptr_t)((base + c * 512) * IQB);
+        const uintptr_t src0 = reinterpret_cast<uintptr_t>(a.iq) + (uintptr_t)((base + c * T) * IQB);
         const uint32_t slack = (src0 & 15) ? 16 : 0;
         const uintptr_t al = src0 & ~(uintptr_t)15;
         if constexpr (CL == 1) {
             if (t == 0) {
-                const uint32_t bytes = NSEG_S * 512 * IQB + slack;
+                const uint32_t bytes = NSEG_S * T * IQB + slack;
                 mbar_expect_tx(bar_full, bytes);
                 bulk_g2s(stage, reinterpret_cast<const void*>(al), bytes, bar_full);
                 if constexpr (NLDG > 0)
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(al + (uintptr_t)NSEG_S * 512 * IQB),
-                                 "r"((uint32_t)(NLDG * 512 * IQB) + slack)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(al + (uintptr_t)NSEG_S * T * IQB),
+                                 "r"((uint32_t)(NLDG * T * IQB) + slack)
                                  : "memory");
             }
         } else if (lane == 0) {
-            const uint32_t bytes = 512 * IQB + slack;
+            const uint32_t bytes = T * IQB + slack;
             if (w == 0) mbar_expect_tx(bar_full, bytes * NSEG_S);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int s = w + 16 * h;
+            for (int h = 0; h < 32 / NW; ++h) {
+                const int s = w + NW * h;
                 if (s < NSEG_S) bulk_g2s(stage + s * SEG, reinterpret_cast<const void*>(al + (uintptr_t)s * L * IQB), bytes, bar_full);
                 else asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(al + (uintptr_t)s * L * IQB), "r"(bytes) : "memory");
             }
@@ -210,20 +216,19 @@ __global__ void __launch_bounds__(512, 1) sti_r32_kernel(const R32Args ra) {
     // ---- setup: barriers, tensor memory, per-thread tables -> TMEM ----
     if (t == 0) {
         mbar_init(bar_full, 1);
-        mbar_init(bar_mfree, CF::NW);
+        mbar_init(bar_mfree, NW);
         mbar_init(bar_landed, 1);
-        *cnt = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (w == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(T));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = *tmem_slot + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(128 * (w >> 2));
-    constexpr uint32_t PEER_BYTES = (uint32_t)(CL - 1) * 512u * NR * 8u;  // (CL-1) peers x 512 columns x NR rows
+    constexpr uint32_t PEER_BYTES = (uint32_t)(CL - 1) * (uint32_t)T * NR * 8u;  // (CL-1) peers x T columns x NR rows
     if (t == 0) {
         if constexpr (CL > 1) mbar_expect_tx(bar_landed, PEER_BYTES);  // frame 0
     }
@@ -241,7 +246,7 @@ __global__ void __launch_bounds__(512, 1) sti_r32_kernel(const R32Args ra) {
             }
             tmem_st8(tmem + CF::C_WIN + 8 * m, wv);
         }
-        // twiddle powers: pass 0  W_N^{n' 2^q},  pass 1  W_L^{c1 2^q} with c1 = t mod S1
+        // twiddle powers: pass 0  W_N^{n' 2^q},  pass 1  W_L^{c1 2^q} with c1 = t mod S1 (the same for every butterfly of the thread)
         const int c1 = t & (S1 - 1);
         float p0[16], p1[16];
 #pragma unroll
@@ -260,7 +265,7 @@ __global__ void __launch_bounds__(512, 1) sti_r32_kernel(const R32Args ra) {
         tmem_wait_st();
     }
     // pass-0 destinations: this thread's column n' of every row; the peers' copies of M and of "landed"
-    const uint32_t np_off = r32_p0_col<CL>(np);  // row r adds r * L * 8 (a multiple of 1024: the swizzle bits of n' stay)
+    const uint32_t np_off = r32_p0_col<G>(np);  // row r adds r * L * 8 (a multiple of 1024: the swizzle bits of n' stay)
     uint32_t rbase[CL], rbar[CL];
 #pragma unroll
     for (int s = 0; s < CL; ++s) {
@@ -272,7 +277,8 @@ __global__ void __launch_bounds__(512, 1) sti_r32_kernel(const R32Args ra) {
         cluster_arrive();  // matches the wait before the first store of frame 0
     }
 
-    uint32_t q = 0;  // frames done by this CTA
+    uint32_t q = 0;        // frames done by this CTA
+    bool full_ok = false;  // "S full" of the coming frame already observed (probed under the previous frame's last pass)
     // TRACE: x0 / x1 make the clock read depend on the arithmetic before it (the packed-math asm is not volatile)
     auto mark = [&](int ev, float x0, float x1) {
         if constexpr (TRACE) {
@@ -284,11 +290,11 @@ __global__ void __launch_bounds__(512, 1) sti_r32_kernel(const R32Args ra) {
     for (;; ++q) {
         const Cursor nxt = advance(cur);
         mark(0, 0.f, 0.f);
-        const int skew = (int)(((reinterpret_cast<uintptr_t>(a.iq) + (uintptr_t)((cur.base + c * 512) * IQB)) & 15) / IQB);
+        const int skew = (int)(((reinterpret_cast<uintptr_t>(a.iq) + (uintptr_t)((cur.base + c * T) * IQB)) & 15) / IQB);
         cf x[32];
         bool mfree_ok = true;
         // ---- pass 0: samples -> registers, window folded into the first butterfly layer ----
-        mbar_wait_bounded(bar_full, q & 1);
+        if (!full_ok) mbar_wait_bounded(bar_full, q & 1);
         mark(1, 0.f, 0.f);
         // in the order the first butterfly layer consumes them: (j, j + 16)
 #pragma unroll
@@ -338,45 +344,71 @@ __global__ void __launch_bounds__(512, 1) sti_r32_kernel(const R32Args ra) {
             if (t == 0 && nxt.valid) mbar_expect_tx(bar_landed, PEER_BYTES);  // next frame: sent only after the cluster barrier
         }
         mark(6, 0.f, 0.f);
-        // ---- pass 1: radix 32 at stride S1 inside row r1 ----
+        // ---- pass 1: NB1 radix-R1 butterflies at stride S1, in place ----
         {
-            const uint32_t base1 = m_base + r32_p1_base<CL>(t);
             // ORDER: behind the CTA barrier every warp wants the LSU at once and all of them get their data
             // last; chained named barriers let warps 4 g .. 4 g + 3 (one per scheduler) issue their loads
             // before group g + 1 does, so group 0 computes while the others still load
             if constexpr (ORDER) {
-                if ((w >> 2) > 0) named_bar_sync(8 + (w >> 2), 256);
+                const int g = w >> 2;
+                if (g == 1) named_bar_sync_c<1, 256>();
+                if (NW > 8 && g == 2) named_bar_sync_c<2, 256>();
+                if (NW > 8 && g == 3) named_bar_sync_c<3, 256>();
             }
+            if constexpr (R1 == 32) {
+                const uint32_t base1 = m_base + r32_p1_base<G>(t, 0);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {  // pair order of the first butterfly layer
-                x[j] = lds_cf(base1 + r32_p1_off<CL>(t, j));
-                x[j + 16] = lds_cf(base1 + r32_p1_off<CL>(t, j + 16));
+                for (int j = 0; j < 16; ++j) {  // pair order of the first butterfly layer
+                    x[j] = lds_cf(base1 + r32_p1_off<G>(t, j));
+                    x[j + 16] = lds_cf(base1 + r32_p1_off<G>(t, j + 16));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < NB1; ++i) {
+                    const uint32_t base1 = m_base + r32_p1_base<G>(t, i);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)  // the order of the first layer of 4-point butterflies
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) x[16 * i + j + 4 * h] = lds_cf(base1 + r32_p1_off<G>(t, j + 4 * h));
+                }
             }
             if constexpr (ORDER) {
-                if ((w >> 2) < 3) named_bar_arrive(9 + (w >> 2), 256);
+                const int g = w >> 2;
+                if (g == 0) named_bar_arrive_c<1, 256>();
+                if (NW > 8 && g == 1) named_bar_arrive_c<2, 256>();
+                if (NW > 8 && g == 2) named_bar_arrive_c<3, 256>();
             }
             // S was consumed by every warp before the barrier.  It is refilled from here, not right after its last
             // read: the bulk copies then land under the arithmetic of passes 1 and 2 instead of competing with the
             // pass-0 stores and pass-1 loads, the one stretch of the frame that is bound by the shared-memory pipe
             if (nxt.valid) issue(nxt.base);
             mark(7, x[0].x, x[31].y);
-            dft32(x);
-            {
-                float pf[16];
-                tmem_ld16(tmem + CF::C_PW1, pf);
-                cf pw[5];
+            float pf[16];
+            tmem_ld16(tmem + CF::C_PW1, pf);
+            cf pw[5];
 #pragma unroll
-                for (int i = 0; i < 5; ++i) pw[i] = make_float2(pf[2 * i], pf[2 * i + 1]);
-                twiddle_dfs32(x, pw, [&](int k1, cf v) { sts_cf(base1 + r32_p1_off<CL>(t, k1), v); });
+            for (int i = 0; i < 5; ++i) pw[i] = make_float2(pf[2 * i], pf[2 * i + 1]);
+            if constexpr (R1 == 32) {
+                const uint32_t base1 = m_base + r32_p1_base<G>(t, 0);
+                dft32(x);
+                twiddle_dfs32(x, pw, [&](int k1, cf v) { sts_cf(base1 + r32_p1_off<G>(t, k1), v); });
+            } else {
+#pragma unroll
+                for (int i = 0; i < NB1; ++i) {
+                    const uint32_t base1 = m_base + r32_p1_base<G>(t, i);
+                    dft16(&x[16 * i]);
+                    twiddle_dfs16(&x[16 * i], pw, [&](int k1, cf v) { sts_cf(base1 + r32_p1_off<G>(t, k1), v); });
+                }
             }
             mark(8, 0.f, 0.f);
         }
-        if constexpr (CL == 4) named_bar_sync(1 + (t >> 6), 64);  // a row is two warps
-        else __syncwarp();                                       // a warp owns whole rows
+        if constexpr (S1 == 64) named_bar_sync(4 + (t >> 6), 64);  // a row is two warps (ids 4..11; one CTA per SM here)
+        else __syncwarp();                                        // a warp owns whole rows
         mark(9, 0.f, 0.f);
         // next frame's register segments: in flight under pass 2
         load_pre(nxt);
-        // ---- pass 2: the L/32-point DFTs on consecutive positions, |X|^2 into the accumulators (TMEM) ----
+        full_ok = nxt.valid && mbar_test(bar_full, (q + 1) & 1);
+        // ---- pass 2: the S1-point DFTs on consecutive positions, |X|^2 into the accumulators (TMEM) ----
         const bool first = cur.f == 0;
         tmem_wait_st();  // the accumulator columns written by the previous frame
         // bins bin0 .. bin0 + NB - 1 of this thread += |y|^2
@@ -423,22 +455,23 @@ __global__ void __launch_bounds__(512, 1) sti_r32_kernel(const R32Args ra) {
                 }
             }
         };
-        if constexpr (CL == 1) {
-            // rows 2 w and 2 w + 1, block k1 = lane of each: 16 consecutive elements = one line, chunk q ^ (lane & 7)
+        if constexpr (S1 == 16) {
+            // two blocks of 16 consecutive elements (one line each) out of the rows this warp wrote in pass 1
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 cf y[16];
 #pragma unroll
-                for (int ch = 0; ch < 8; ++ch) lds_cf2(m_base + r32_p2_addr<CL>(t, i, ch), y[2 * ch], y[2 * ch + 1]);
+                for (int ch = 0; ch < 8; ++ch) lds_cf2(m_base + r32_p2_addr<G>(t, i, ch), y[2 * ch], y[2 * ch + 1]);
                 dft16(y);
                 if (i == 0) mark(10, y[0].x, y[15].y);
                 accumulate(16 * i, y, std::integral_constant<int, 16>{});
             }
-        } else if constexpr (CL == 2) {
+        } else if constexpr (S1 == 32) {
             // row w, block k1 = lane: 32 consecutive elements = lines 2 lane, 2 lane + 1, chunk (j & 7) ^ (lane & 7)
 #pragma unroll
-            for (int ch = 0; ch < 16; ++ch) lds_cf2(m_base + r32_p2_addr<CL>(t, 0, ch), x[2 * ch], x[2 * ch + 1]);
+            for (int ch = 0; ch < 16; ++ch) lds_cf2(m_base + r32_p2_addr<G>(t, 0, ch), x[2 * ch], x[2 * ch + 1]);
             dft32(x);
+            mark(10, x[0].x, x[31].y);
             accumulate(0, x, std::integral_constant<int, 32>{});
         } else {
             // row r2 = t / 64, k1 = (t % 64) / 2, e = t & 1: elements 64 k1 + 2 d + e, d < 32; then the radix-2
@@ -446,8 +479,9 @@ __global__ void __launch_bounds__(512, 1) sti_r32_kernel(const R32Args ra) {
             // lane e = 1 outputs 16 + i and 48 + i (W_64^{16 + i} = -j W_64^i)
             const int e = t & 1;
 #pragma unroll
-            for (int d = 0; d < 32; ++d) x[d] = lds_cf(m_base + r32_p2_addr<CL>(t, 0, d));
+            for (int d = 0; d < 32; ++d) x[d] = lds_cf(m_base + r32_p2_addr<G>(t, 0, d));
             dft32(x);
+            mark(10, x[0].x, x[31].y);
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
                 cf s[8];
@@ -468,7 +502,6 @@ __global__ void __launch_bounds__(512, 1) sti_r32_kernel(const R32Args ra) {
         mark(11, 0.f, 0.f);
         // ---- the item's last frame: accumulators -> fftshifted column, coalesced 128-bit stores ----
         if (cur.f + 1 == cur.nfr) {
-            tmem_wait_st();
             __syncthreads();  // every warp is done reading M (peers write to it only after the cluster barrier)
             float* const sout = reinterpret_cast<float*>(smem_raw + CF::HDR + (size_t)CF::SBYTES);
             // this CTA's bins: freq = k0 + 32 m, k0 = c NR + r; fftshift moves m by N/64; staged as sout[r RS + m']
@@ -481,7 +514,7 @@ __global__ void __launch_bounds__(512, 1) sti_r32_kernel(const R32Args ra) {
                 for (int j = 0; j < (ACC2 ? 4 : 8); ++j) {
                     const int ai = (ACC2 ? 4 : 8) * m8 + j;  // accumulator index -> (row r, m)
                     int r, m;
-                    r32_acc_bin<CL>(t, ai, r, m);
+                    r32_acc_bin<G>(t, ai, r, m);
                     sout[r * RS + ((m + MSH) & (MM - 1))] = ACC2 ? acc[2 * j] + acc[2 * j + 1] : acc[j];
                 }
             }
@@ -519,5 +552,5 @@ __global__ void __launch_bounds__(512, 1) sti_r32_kernel(const R32Args ra) {
     tmem_wait_st();
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
-    if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "n"(512));
+    if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "n"(T));
 }

@@ -63,10 +63,10 @@ static void check_banks(const uint32_t* addr, int width, const char* what) {
     }
 }
 
-template <int CL>
+template <int LOGN, int T>
 static void run(unsigned seed) {
-    using G = R32Geo<CL>;
-    constexpr int N = G::N, L = G::L, NR = G::NR, S1 = G::S1, SWSH = G::SWSH, T = 512;
+    using G = R32Geo<LOGN, T>;
+    constexpr int N = G::N, L = G::L, CL = G::CL, NR = G::NR, R1 = G::R1, S1 = G::S1, NB1 = G::NB1, SWSH = G::SWSH;
     srand(seed);
     std::vector<float2> x(N), tw(N);
     std::vector<float> win(N);
@@ -76,8 +76,8 @@ static void run(unsigned seed) {
         const double ang = -2.0 * M_PI * (double)n / (double)N;
         tw[n] = make_float2((float)cos(ang), (float)sin(ang));
     }
-    std::vector<std::vector<unsigned char>> M(CL, std::vector<unsigned char>(16384 * 8, 0xff));
-    std::vector<std::vector<int>> written(CL, std::vector<int>(16384, 0));
+    std::vector<std::vector<unsigned char>> M(CL, std::vector<unsigned char>(T * 32 * 8, 0xff));
+    std::vector<std::vector<int>> written(CL, std::vector<int>(T * 32, 0));
     auto ld = [&](int cta, uint32_t off) { float2 v; memcpy(&v, &M[cta][off], 8); return v; };
     auto st = [&](int cta, uint32_t off, float2 v) { memcpy(&M[cta][off], &v, 8); };
 
@@ -86,7 +86,7 @@ static void run(unsigned seed) {
         for (int w0 = 0; w0 < T; w0 += 32) {
             uint32_t addr[32][32];  // [k0][lane]
             for (int lane = 0; lane < 32; ++lane) {
-                const int t = w0 + lane, np = c * 512 + t;
+                const int t = w0 + lane, np = c * T + t;
                 cf xr[32], u[16], v[16];
                 float wv[32];
                 for (int a = 0; a < 32; ++a) xr[a] = x[np + a * L];
@@ -97,11 +97,11 @@ static void run(unsigned seed) {
                 cf pw[5];
                 for (int q = 0; q < 5; ++q) pw[q] = tw[((unsigned)np << q) & (N - 1)];
                 twiddle_dfs32(xr, pw);
-                const uint32_t col = r32_p0_col<CL>(np);
+                const uint32_t col = r32_p0_col<G>(np);
                 for (int k0 = 0; k0 < 32; ++k0) {
                     const int s = k0 / NR, r = k0 % NR;
                     const uint32_t off = col + (uint32_t)r * (L * 8);
-                    CHECK(off == r32_swz<SWSH>((uint32_t)(r * L + np)), "pass 0 address CL=%d np=%d k0=%d", CL, np, k0);
+                    CHECK(off == r32_swz<SWSH>((uint32_t)(r * L + np)), "pass 0 address N=%d np=%d k0=%d", N, np, k0);
                     st(s, off, xr[k0]);
                     written[s][off / 8]++;
                     addr[k0][lane] = off;
@@ -111,29 +111,37 @@ static void run(unsigned seed) {
         }
     }
     for (int c = 0; c < CL; ++c)
-        for (int i = 0; i < 16384; ++i) CHECK(written[c][i] == 1, "pass 0: slot %d of CTA %d written %d times", i, c, written[c][i]);
+        for (int i = 0; i < T * 32; ++i) CHECK(written[c][i] == 1, "pass 0: slot %d of CTA %d written %d times", i, c, written[c][i]);
 
     // ---- pass 1 ----
     for (int c = 0; c < CL; ++c) {
         for (int w0 = 0; w0 < T; w0 += 32) {
-            uint32_t addr[32][32];
+            uint32_t addr[NB1][32][32];
             for (int lane = 0; lane < 32; ++lane) {
-                const int t = w0 + lane, r1 = t / S1, c1 = t & (S1 - 1);
-                const uint32_t base1 = r32_p1_base<CL>(t);
-                cf xr[32];
-                for (int b = 0; b < 32; ++b) {
-                    const uint32_t off = base1 + r32_p1_off<CL>(t, b);
-                    CHECK(off == r32_swz<SWSH>((uint32_t)(r1 * L + b * S1 + c1)), "pass 1 address CL=%d t=%d b=%d", CL, t, b);
-                    xr[b] = ld(c, off);
-                    addr[b][lane] = off;
+                const int t = w0 + lane;
+                for (int i = 0; i < NB1; ++i) {
+                    const int id = t + i * T, r1 = id / S1, c1 = id & (S1 - 1);
+                    const uint32_t base1 = r32_p1_base<G>(t, i);
+                    cf xr[32];
+                    for (int b = 0; b < R1; ++b) {
+                        const uint32_t off = base1 + r32_p1_off<G>(t, b);
+                        CHECK(off == r32_swz<SWSH>((uint32_t)(r1 * L + b * S1 + c1)), "pass 1 address N=%d t=%d b=%d", N, t, b);
+                        xr[b] = ld(c, off);
+                        addr[i][b][lane] = off;
+                    }
+                    cf pw[5];
+                    for (int q = 0; q < 5; ++q) pw[q] = tw[(((unsigned)c1 << q) * 32u) & (N - 1)];
+                    if (R1 == 32) {
+                        dft32(xr);
+                        twiddle_dfs32(xr, pw, [&](int k1, cf v) { st(c, base1 + r32_p1_off<G>(t, k1), v); });
+                    } else {
+                        dft16(xr);
+                        twiddle_dfs16(xr, pw, [&](int k1, cf v) { st(c, base1 + r32_p1_off<G>(t, k1), v); });
+                    }
                 }
-                dft32(xr);
-                cf pw[5];
-                for (int q = 0; q < 5; ++q) pw[q] = tw[(((unsigned)c1 << q) * 32u) & (N - 1)];
-                twiddle_dfs32(xr, pw);
-                for (int b = 0; b < 32; ++b) st(c, base1 + r32_p1_off<CL>(t, b), xr[b]);
             }
-            for (int b = 0; b < 32; ++b) check_banks(addr[b], 8, "pass 1");
+            for (int i = 0; i < NB1; ++i)
+                for (int b = 0; b < R1; ++b) check_banks(addr[i][b], 8, "pass 1");
         }
     }
 
@@ -146,12 +154,14 @@ static void run(unsigned seed) {
             uint32_t addr[32][32];
             for (int lane = 0; lane < 32; ++lane) {
                 const int t = w0 + lane;
-                if constexpr (CL == 1) {
+                if constexpr (S1 == 16) {
                     for (int i = 0; i < 2; ++i) {
                         cf yy[16];
+                        int row, k1;
+                        r32_p2_block<G>(t, i, row, k1);
                         for (int ch = 0; ch < 8; ++ch) {
-                            const uint32_t off = r32_p2_addr<CL>(t, i, ch);
-                            CHECK(off == r32_swz<SWSH>((uint32_t)((2 * (t >> 5) + i) * L + lane * 16 + 2 * ch)), "pass 2 address t=%d", t);
+                            const uint32_t off = r32_p2_addr<G>(t, i, ch);
+                            CHECK(off == r32_swz<SWSH>((uint32_t)(row * L + k1 * 16 + 2 * ch)), "pass 2 address t=%d", t);
                             yy[2 * ch] = ld(c, off);
                             yy[2 * ch + 1] = ld(c, off + 8);
                             addr[i * 8 + ch][lane] = off;
@@ -159,10 +169,10 @@ static void run(unsigned seed) {
                         dft16(yy);
                         for (int j = 0; j < 16; ++j) acc[t][16 * i + j] = fmaf(yy[j].x, yy[j].x, yy[j].y * yy[j].y);
                     }
-                } else if constexpr (CL == 2) {
+                } else if constexpr (S1 == 32) {
                     cf yy[32];
                     for (int ch = 0; ch < 16; ++ch) {
-                        const uint32_t off = r32_p2_addr<CL>(t, 0, ch);
+                        const uint32_t off = r32_p2_addr<G>(t, 0, ch);
                         CHECK(off == r32_swz<SWSH>((uint32_t)((t >> 5) * L + lane * 32 + 2 * ch)), "pass 2 address t=%d", t);
                         yy[2 * ch] = ld(c, off);
                         yy[2 * ch + 1] = ld(c, off + 8);
@@ -173,7 +183,7 @@ static void run(unsigned seed) {
                 } else {
                     const int r2 = t >> 6, k1 = (t & 63) >> 1, e = t & 1;
                     for (int d = 0; d < 32; ++d) {
-                        const uint32_t off = r32_p2_addr<CL>(t, 0, d);
+                        const uint32_t off = r32_p2_addr<G>(t, 0, d);
                         CHECK(off == r32_swz<SWSH>((uint32_t)(r2 * L + 64 * k1 + 2 * d + e)), "pass 2 address t=%d", t);
                         y[t][d] = ld(c, off);
                         addr[d][lane] = off;
@@ -181,10 +191,10 @@ static void run(unsigned seed) {
                     dft32(y[t].data());
                 }
             }
-            const int ninstr = (CL == 1) ? 16 : (CL == 2) ? 16 : 32;
-            for (int i = 0; i < ninstr; ++i) check_banks(addr[i], CL == 4 ? 8 : 16, "pass 2");
+            const int ninstr = (S1 == 64) ? 32 : 16;
+            for (int i = 0; i < ninstr; ++i) check_banks(addr[i], S1 == 64 ? 8 : 16, "pass 2");
         }
-        if constexpr (CL == 4) {
+        if constexpr (S1 == 64) {
             for (int t = 0; t < T; ++t) {
                 const int e = t & 1;
                 for (int i = 0; i < 16; ++i) {
@@ -201,9 +211,9 @@ static void run(unsigned seed) {
         for (int t = 0; t < T; ++t)
             for (int ai = 0; ai < 32; ++ai) {
                 int r, m;
-                r32_acc_bin<CL>(t, ai, r, m);
+                r32_acc_bin<G>(t, ai, r, m);
                 const int freq = (c * NR + r) + 32 * m;
-                CHECK(freq >= 0 && freq < N && power[freq] < 0.f, "bin map CL=%d t=%d ai=%d -> %d", CL, t, ai, freq);
+                CHECK(freq >= 0 && freq < N && power[freq] < 0.f, "bin map N=%d t=%d ai=%d -> %d", N, t, ai, freq);
                 power[freq] = acc[t][ai];
             }
         for (int w0 = 0; w0 < T; w0 += 32)
@@ -211,10 +221,10 @@ static void run(unsigned seed) {
                 uint32_t addr[32];
                 for (int lane = 0; lane < 32; ++lane) {
                     int r, m;
-                    r32_acc_bin<CL>(w0 + lane, ai, r, m);
+                    r32_acc_bin<G>(w0 + lane, ai, r, m);
                     addr[lane] = 4u * (uint32_t)(r * G::RS + ((m + N / 64) & (N / 32 - 1)));
                 }
-                if (CL != 4) check_banks(addr, 4, "epilogue staging store");  // CL = 4: two-way by design (lane pairs 512 floats apart)
+                if (S1 != 64 && R1 == 32) check_banks(addr, 4, "epilogue staging store");  // S1 = 64 and R1 = 16: two-way by design (once per work item)
             }
     }
 
@@ -229,15 +239,18 @@ static void run(unsigned seed) {
         worst = std::max(worst, fabs((double)power[k] - p) / peak);
         if (p > 1e-3 * peak) worst_rel = std::max(worst_rel, fabs((double)power[k] - p) / p);
     }
-    printf("CL=%d N=%d: max |err| / peak = %.3g, max rel err (bins > -30 dB) = %.3g\n", CL, N, worst, worst_rel);
-    CHECK(worst < 2e-6, "CL=%d: error %.3g", CL, worst);
-    CHECK(worst_rel < 1e-5, "CL=%d: relative error %.3g", CL, worst_rel);
+    printf("N=%d T=%d CL=%d: max |err| / peak = %.3g, max rel err (bins > -30 dB) = %.3g\n", N, T, CL, worst, worst_rel);
+    CHECK(worst < 2e-6, "N=%d: error %.3g", N, worst);
+    CHECK(worst_rel < 1e-5, "N=%d: relative error %.3g", N, worst_rel);
 }
 
 int main() {
-    run<1>(1);
-    run<2>(2);
-    run<4>(3);
+    run<13, 256>(1);
+    run<14, 512>(2);
+    run<14, 256>(3);
+    run<15, 512>(4);
+    run<15, 256>(5);
+    run<16, 512>(6);
     printf(g_fail ? "FAILED (%d)\n" : "OK\n", g_fail);
     return g_fail ? 1 : 0;
 }

@@ -5,6 +5,8 @@ Runs the same pass structure -- in-place mixed-radix DIF, per-pass twiddle table
 against ``np.fft.fft`` for every radix set the library registers.  This pins the addressing on the
 CPU so GPU time is spent on numerics and speed, not on index bugs.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -223,3 +225,24 @@ def test_whole16_plan_16x2x16x2x16():
             npp = 128 * m + 16 * (u >> 5) + (lane & 15)
             seen[npp + 512 * (lane >> 4)] += 1
     assert (seen == 1).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# radix-32 whole-frame kernels (sti_r32.cuh): CPU replay with the kernel's own math header
+# ---------------------------------------------------------------------------------------------
+def test_r32_kernels_replayed_on_the_cpu(tmp_path):
+    """tests/c/r32_emu.cu includes csrc/r32_math.cuh (butterflies, twiddle recurrences, address functions and the
+    accumulator-to-bin map are __host__ __device__ and bit-identical on the host) and walks the three passes of
+    every geometry (8192 ... 65536, one CTA to a cluster of four) thread by thread: bins against a float64 FFT,
+    every address against the generic swizzle, every warp-wide shared-memory access bank-conflict free."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = str(tmp_path / "r32_emu")
+    subprocess.run([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", exe, os.path.join(here, "c", "r32_emu.cu")],
+                   check=True, capture_output=True)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0 and res.stdout.strip().endswith("OK"), res.stdout + res.stderr

@@ -38,7 +38,9 @@ def torch():
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name,noise_like", [
     ("sti_r_64x7", False), ("sti_r_256x10x3", False), ("sti_r_1024x100", False), ("sti_r_4096x4", True),
-    ("sti_r_hdr2048", False), ("sti_r_impulse16", True), ("sti_r_tone1024", False)])
+    ("sti_r_hdr2048", False), ("sti_r_impulse16", True), ("sti_r_tone1024", False),
+    # pure noise through the reference at the large FFT lengths: every bin is held to the per-bin criterion
+    ("sti_r_noise8192x4", True), ("sti_r_noise16384x3", True), ("sti_r_noise32768x2", True), ("sti_r_noise65536x2", True)])
 def test_sti_proc_data_matches_reference_golden(dp, name, noise_like):
     g = load(name)
     f, sxx, med = dp.sti_proc_data(g["d1"], float(g["sr"]), int(g["nfft"]))
@@ -406,11 +408,11 @@ def test_whole_frame_path(torch, nfft, nfr, ncol, nsub, kind):
 
 
 def test_large_nfft_defaults_and_fallback(torch):
-    """16384 runs the whole-frame kernel, 32768 its two-CTA cluster form, 65536 the split path (measured
-    defaults); a recording whose base is not 16-byte aligned cannot use bulk copies and takes the split
-    path at every size."""
+    """16384 / 32768 / 65536 run the three-pass radix-32 kernels (one CTA, a pair, a cluster of four: the measured
+    defaults); a recording whose base is not 16-byte aligned cannot use bulk copies and takes the split path at
+    every size."""
     from pyspectrogram_b200 import engine
-    for nfft, want in ((16384, "whole4x4096_s4"), (32768, "whole8x4096_c2"), (65536, "split16x4096")):
+    for nfft, want in ((16384, "r32_32x32x16_t512c1"), (32768, "r32_32x32x32_t512c2"), (65536, "r32_32x32x2x32_t512c4")):
         x = torch.from_numpy(_recording(np.random.default_rng(nfft), nfft * 9)).cuda()
         starts = torch.from_numpy(np.arange(4, dtype=np.int64) * 2 * nfft).cuda()
         plan = engine.StiPlan(nfft)
@@ -427,7 +429,8 @@ def test_large_nfft_defaults_and_fallback(torch):
 
 
 @pytest.mark.parametrize("nfft", [256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536, (16384, "cluster"), (32768, "cluster_dsmem"),
-                                  (65536, "cluster_ldg"), (65536, "cluster_dsmem"), (16384, "whole"), (8192, "whole"), (32768, "whole"), (65536, "whole"), (16384, "whole_r2"), (65536, "whole_r2"), (16384, "whole_f")])
+                                  (65536, "cluster_ldg"), (65536, "cluster_dsmem"), (16384, "whole"), (8192, "whole"), (32768, "whole"), (65536, "whole"), (16384, "whole_r2"), (65536, "whole_r2"), (16384, "whole_f"),
+                                  (8192, "r32")])
 def test_repeated_runs_are_bit_identical(torch, nfft):
     """Race canary (compute-sanitizer is not available on the GPU pool): no atomic touches data (the
     whole-frame kernel counts stage readers with one, which only decides WHO issues the next copy) and

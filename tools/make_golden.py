@@ -123,6 +123,16 @@ def main():
         save(name, x=x, sr=np.float64(sr), nfft=np.int64(nfft), dt=np.float64(dtv),
              t_out=t_out, f=f, sxx=sxx, med=med)
 
+    # --- sti_proc_data on pure noise at the large FFT lengths (per-bin criterion of tests/parity.py: every bin of
+    # a noise-like column within 1e-5 at the 99.9th percentile and 1e-3 dB).  A generator of their own, so that the
+    # fixtures above stay bit-identical when cases are added here.
+    rng_big = np.random.default_rng(20261018)
+    for name, (nfft, ntime) in {"sti_r_noise8192x4": (8192, 4), "sti_r_noise16384x3": (16384, 3),
+                                "sti_r_noise32768x2": (32768, 2), "sti_r_noise65536x2": (65536, 2)}.items():
+        d1 = iq(rng_big, (nfft, ntime), dtype=np.complex64)
+        f, sxx, med = ref["sti_proc_data"](d1, 25.0e6, nfft)
+        save(name, d1=d1, sr=np.float64(25.0e6), nfft=np.int64(nfft), f=f, sxx=sxx, med=med)
+
     # --- get_ref ----------------------------------------------------------------------------
     props = [
         {"H5Tget_class": 1, "H5Tget_precision": 32, "H5Tget_size": 4},

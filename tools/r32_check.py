@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def check(nfft, torch, engine):
+def check(nfft, torch, engine, variant=None):
     from oracle import np_oracle
     from tests.parity import psd_errors
     ok = True
@@ -45,8 +45,12 @@ def check(nfft, torch, engine):
             xo = (raw[:, 0].astype(np.float64) + 1j * raw[:, 1].astype(np.float64)) * scale
         starts = (np.arange(ncol) * span + (np.arange(ncol) % 2 if odd else 0) * (1 if dt != "i8" else 1)).astype(np.int64)
         plan = engine.StiPlan(nfft)
-        lin, db = plan.run(xd, torch.from_numpy(starts).to(dev), nfr, hop, in_scale=scale, want_lin=True, want_db=True)
-        torch.cuda.synchronize()
+        engine.set_variant(variant)
+        try:
+            lin, db = plan.run(xd, torch.from_numpy(starts).to(dev), nfr, hop, in_scale=scale, want_lin=True, want_db=True)
+            torch.cuda.synchronize()
+        finally:
+            engine.set_variant(None)
         got = lin.cpu().numpy()[0]
         gdb = db.cpu().numpy()[0]
         pick = sorted(set([0, 1, ncol // 2, ncol - 1]))
@@ -102,6 +106,7 @@ def main():
     ap.add_argument("--skip-time", action="store_true")
     ap.add_argument("--skip-check", action="store_true")
     ap.add_argument("--old", default="whole,whole,split", help="variant override of the kernels being replaced, per nfft")
+    ap.add_argument("--variant", default=None, help="variant override for the kernel under test (e.g. r32 at 8192)")
     args = ap.parse_args()
     import torch
     from pyspectrogram_b200 import engine
@@ -113,13 +118,13 @@ def main():
     for i, nfft in enumerate(nffts):
         if not args.skip_check:
             print(f"parity nfft={nfft}", flush=True)
-            allok = check(nfft, torch, engine) and allok
+            allok = check(nfft, torch, engine, args.variant) and allok
         if not args.skip_time:
             print(f"timing nfft={nfft}", flush=True)
-            bench(nfft, args.gb, 1000, None, torch, engine, peak)
+            bench(nfft, args.gb, 1000, args.variant, torch, engine, peak)
             bench(nfft, args.gb, 1000, olds[min(i, len(olds) - 1)], torch, engine, peak)
             nt = int(min(args.gb, 2.0) * 1e9 / 8) // nfft  # one frame per column (Mode R rate)
-            bench(nfft, min(args.gb, 2.0), nt, None, torch, engine, peak)
+            bench(nfft, min(args.gb, 2.0), nt, args.variant, torch, engine, peak)
     print("ALL OK" if allok else "FAILURES")
     return 0 if allok else 1
 

@@ -33,6 +33,8 @@ def main():
     nint = n // ntime // args.nfft
     starts = torch.from_numpy(engine.frame_starts(0, n, args.nfft, nint, ntime).astype(np.int64)).to(dev)
     plan = engine.StiPlan(args.nfft)
+    if args.nfft == 8192:
+        engine.set_variant("r32")
     for _ in range(2):
         plan.run(iq, starts, nint, args.nfft, want_lin=False, want_db=True)
     torch.cuda.synchronize()
