@@ -130,7 +130,9 @@ int psg_sti_host_typed(psg_plan* plan, const void* iq_host, int iq_type, int64_t
  * Median over the time axis of a finished linear-power image (np.median(sxx, axis=1),
  * drfProc.py:401 / :451): img_dev is [nsub][ncol][nfft]; med_lin_dev / med_db_dev are
  * [nsub][nfft] (either may be NULL).  Even ncol gives the fp32 mean of the two middle values,
- * exactly like numpy.  Exact order statistic (radix select), no approximation.
+ * exactly like numpy.  Exact order statistic, no approximation: a bit-by-bit search for the key of the middle
+ * rank (one warp per bin, keys in shared memory, the candidate set compacted every four bits; csrc/sti_kernels.cuh,
+ * median_select_kernel), bit-identical to np.median for finite inputs.
  */
 int psg_median_time(psg_plan* plan, const float* img_dev, int nsub, int ncol, int nfft,
                     float eps, float* med_lin_dev, float* med_db_dev, void* cuda_stream);

@@ -1750,8 +1750,46 @@ extern "C" int psg_median_time(psg_plan* p, const float* img_dev, int nsub, int 
     if (!img_dev || (!med_lin_dev && !med_db_dev)) return fail(PSG_ERR_ARG, "psg_median_time: NULL pointer");
     if (nsub < 1 || ncol < 1 || nfft < 1) return fail(PSG_ERR_ARG, "psg_median_time: bad shape");
     CUDA_TRY(cudaSetDevice(p->device));
-    // bins per CTA: the widest tile of [ncol][bpc] keys that fits in shared memory and still gives
-    // every SM a CTA; when even 8 bins do not fit (ncol > ~6900) the columns are re-read from L2.
+    // Default: warp-per-bin selection (median_select_kernel).  Rows padded to a multiple of 128 keys + 4 (the
+    // transposing load is then bank-conflict free).  Bins per CTA (= warps per CTA): what keeps the most warps
+    // resident -- all the keys of a bin stay in shared memory, so at 3600 columns an SM holds 15 bins.
+    {
+        const int rowlen = ((ncol + 127) / 128) * 128 + 4;  // whole trips of 32 x 128-bit loads over a complete row
+        const size_t row_bytes = (size_t)rowlen * 4, sm_total = 227 * 1024;
+        int bpc = 0;
+        long long best = 0;
+        for (int cand_b : {8, 4, 2}) {
+            const size_t smem = cand_b * row_bytes;
+            if (smem > 220 * 1024) continue;
+            const long long ctas = std::min<long long>(32, (long long)(sm_total / (smem + 1024)));
+            // rows of two floats read a quarter of every 32-byte sector (four CTAs share it through L2): only when
+            // that buys clearly more resident warps
+            const long long warps = std::min<long long>(64, ctas * cand_b) * (cand_b == 2 ? 4 : 5);
+            if (warps > best) { best = warps; bpc = cand_b; }
+        }
+        if (bpc && !g_force_generic.load()) {
+            const size_t smem = bpc * row_bytes;
+            const void* fn = bpc == 8 ? (const void*)median_select_kernel<8>
+                             : bpc == 4 ? (const void*)median_select_kernel<4>
+                                        : (const void*)median_select_kernel<2>;
+            static thread_local const void* q_fn = nullptr;
+            static thread_local int q_dev = -1;
+            if (q_fn != fn || q_dev != p->device) {
+                CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                q_fn = fn;
+                q_dev = p->device;
+            }
+            const long long blocks = (long long)nsub * ((nfft + bpc - 1) / bpc);
+            void* args[] = {(void*)&img_dev, (void*)&nsub, (void*)&ncol, (void*)&nfft, (void*)&rowlen, (void*)&eps,
+                            (void*)&med_lin_dev, (void*)&med_db_dev};
+            CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(bpc * 32), args, smem, (cudaStream_t)cuda_stream));
+            g_launches++;
+            CUDA_TRY(cudaGetLastError());
+            return PSG_OK;
+        }
+    }
+    // Fallback (more columns than a tile holds; also what psg_set_force_generic selects, as the cross-check of
+    // the selection kernel): CTA-wide bisection, tiled while [ncol][8] keys fit, else re-reading L2.
     const size_t smem_max = 222 * 1024;
     const size_t hdr = 3 * 256 * sizeof(unsigned);
     int bpc = 8;

@@ -685,6 +685,202 @@ __global__ void __launch_bounds__(256) median_time_kernel(const float* __restric
     }
 }
 
+// ---- time-median, warp-per-bin selection (the default; median_time_kernel above is the fallback for column
+// counts whose tile does not fit shared memory) -------------------------------------------------------------
+// The bisection kernel above runs 32 CTA-wide steps -- a CTA barrier each, eight warps per SM at thousands of
+// columns -- and reaches 4-5 % of the HBM peak: it is bound by latency, not by its ~96 instructions per key.
+// Here a WARP owns a bin: its ncol keys sit bin-major in shared memory and nothing but the tile load
+// synchronises the CTA.  The selection is the same exact bit-by-bit search for the key of rank (ncol-1)/2
+// ("largest K with count(key < K) <= rank"), made cheaper four ways:
+//   1. it starts at the highest bit in which the bin's keys differ (min ^ max; powers of one bin share sign and
+//      most of the exponent), and a constant bin is answered at once;
+//   2. after every LEVEL_BITS steps only the keys that match the decided prefix can still change a count: they are
+//      compacted in place to the front of the row (ballot + popc; a write never passes the read position) and
+//      the next steps run on those few per cent of the keys; keys below the prefix range are remembered as a
+//      count, keys above it as their minimum.  (Measured alternative: every lane compacting its own strided keys
+//      without ballots -- fewer instructions, 15 % slower: its scalar loads and divergent stores are latency-bound);
+//   3. once at most 32 keys are left (two levels at 3600 columns) they are ranked against one another in
+//      registers with shuffles -- the per-level overhead of ~500 warp instructions a bin is what the small sets
+//      cost, not their keys;
+//   4. even ncol: count(key <= K) and the next larger key -- numpy's mean of the two middle values in float32 --
+//      come out of the same bookkeeping, no further pass over the row.
+// Result: bit-identical to median_time_kernel and to np.median for the finite, non-NaN powers this path produces.
+template <int BPC>
+__global__ void __launch_bounds__(BPC * 32) median_select_kernel(const float* __restrict__ img, int nsub, int ncol, int nfft,
+                                                                int rowlen, float eps, float* med_lin, float* med_db) {
+    constexpr int LEVEL_BITS = 4;
+    extern __shared__ __align__(16) unsigned msel_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int blocks_per_sub = (nfft + BPC - 1) / BPC;
+    const int sub = blockIdx.x / blocks_per_sub;
+    const int bin0 = (blockIdx.x - sub * blocks_per_sub) * BPC;
+    {
+        // rows of BPC floats per column (coalesced per row; adjacent CTAs share sectors through L2), copied
+        // asynchronously (LDGSTS, 4 bytes each) straight to their bin-major place: every load of the tile is in
+        // flight at once and no register waits for it -- with a dozen resident warps per SM a register-staged
+        // load spent a third of the kernel on DRAM latency.  Pads are 0xffffffff (never below a candidate).
+        const int b = tid % BPC, s0 = tid / BPC;
+        const int bin = min(bin0 + b, nfft - 1);
+        const float* src = img + (size_t)sub * ncol * nfft + bin + (size_t)s0 * nfft;
+        const size_t step = (size_t)32 * nfft;
+        unsigned* row = msel_smem + (size_t)b * rowlen;
+        uint32_t dst = smem_u32(row + s0);
+        int c = s0;
+#pragma unroll 4
+        for (; c < ncol; c += 32, src += step, dst += 128)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+        for (; c < rowlen; c += 32) row[c] = 0xffffffffu;
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const int bin = bin0 + w;
+    if (bin >= nfft) return;
+    unsigned* const row = msel_smem + (size_t)w * rowlen;
+    const unsigned klo = (unsigned)((ncol - 1) >> 1);  // 0-based rank of the lower middle
+    // raw floats -> order-preserving keys in place, minimum and maximum on the way
+    unsigned mn = 0xffffffffu, mx = 0u;
+    {
+        uint4* const row4 = reinterpret_cast<uint4*>(row);
+        const int full = ncol >> 2;  // groups of four that hold no pad
+        for (int i = lane; i < full; i += 32) {
+            uint4 k = row4[i];
+            k.x = f2key(__uint_as_float(k.x));
+            k.y = f2key(__uint_as_float(k.y));
+            k.z = f2key(__uint_as_float(k.z));
+            k.w = f2key(__uint_as_float(k.w));
+            row4[i] = k;
+            mn = min(mn, min(min(k.x, k.y), min(k.z, k.w)));
+            mx = max(mx, max(max(k.x, k.y), max(k.z, k.w)));
+        }
+        const int i = 4 * full + lane;
+        if (i < ncol) {
+            const unsigned k = f2key(__uint_as_float(row[i]));
+            row[i] = k;
+            mn = min(mn, k);
+            mx = max(mx, k);
+        }
+        __syncwarp();
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    unsigned key = mn, cnt_le = (unsigned)ncol, nxt = 0xffffffffu;  // a constant bin: every key is the answer
+    if (mn != mx) {
+        int bit = 31 - __clz((int)(mn ^ mx));                    // highest differing bit
+        key = (bit == 31) ? 0u : (mx >> (bit + 1)) << (bit + 1);  // the bits every key shares
+        unsigned below = 0;  // count(row < key)
+        unsigned base = 0;   // keys below the range of the active ones (dropped at the last compaction)
+        int na = ncol;       // active keys: row[0 .. na)
+        bool done = false;
+        const unsigned lt = (1u << lane) - 1u;
+        while (bit >= 0) {
+            if (na <= 32) {
+                // one key per lane left: rank them against one another in registers (ties broken by lane) and pick
+                // the one of rank klo - base: no more loops, per-bit reductions or compactions
+                const unsigned kv = (lane < na) ? row[lane] : 0xffffffffu;
+                unsigned rank = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const unsigned kj = __shfl_sync(0xffffffffu, kv, j);
+                    rank += (kj < kv || (kj == kv && j < lane)) ? 1u : 0u;
+                }
+                const unsigned sel = __ballot_sync(0xffffffffu, lane < na && rank == klo - base);
+                key = __shfl_sync(0xffffffffu, kv, __ffs((int)sel) - 1);
+                cnt_le = base + __popc(__ballot_sync(0xffffffffu, lane < na && kv <= key));
+                nxt = __reduce_min_sync(0xffffffffu, min(nxt, (lane < na && kv > key) ? kv : 0xffffffffu));
+                done = true;
+                break;
+            }
+            // up to LEVEL_BITS steps on the active keys (padded to a multiple of four with 0xffffffff)
+            const int stop = max(bit - LEVEL_BITS + 1, 0);
+            const int n4 = (na + 3) >> 2;
+            if (lane < ((4 - (na & 3)) & 3)) row[na + lane] = 0xffffffffu;
+            __syncwarp();
+            const uint4* const row4 = reinterpret_cast<const uint4*>(row);
+            // whole trips of 32 x uint4 while the row is complete (its pads reach a multiple of 128 keys)
+            const bool whole = na == ncol;
+            const int trips = rowlen >> 7;
+            for (; bit >= stop; --bit) {
+                const unsigned cand = key | (1u << bit);
+                unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+                if (whole) {
+#pragma unroll 4
+                    for (int j = 0; j < trips; ++j) {
+                        const uint4 k = row4[lane + 32 * j];
+                        c0 += k.x < cand;
+                        c1 += k.y < cand;
+                        c2 += k.z < cand;
+                        c3 += k.w < cand;
+                    }
+                } else {
+                    for (int i = lane; i < n4; i += 32) {
+                        const uint4 k = row4[i];
+                        c0 += k.x < cand;
+                        c1 += k.y < cand;
+                        c2 += k.z < cand;
+                        c3 += k.w < cand;
+                    }
+                }
+                const unsigned cnt = base + __reduce_add_sync(0xffffffffu, (c0 + c1) + (c2 + c3));
+                if (cnt <= klo) { key = cand; below = cnt; }
+            }
+            // keep the keys that equal `key` in the bits above `bit`; the ones above that range only matter as
+            // "the next larger key", the ones below it are counted in `below`
+            const int sh = bit + 1;  // <= 28 (a level decides at least four bits), 0 after the last one
+            const unsigned want = key >> sh;
+            unsigned nc = 0;
+            int i0 = 0;
+            // four groups of 32 keys per trip: their loads are in flight together; all of them are in registers
+            // before the first survivor is written (writes stay below i0 + 128)
+            for (; i0 + 128 <= na; i0 += 128) {
+                unsigned k[4], m[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) k[g] = row[i0 + 32 * g + lane];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const unsigned top = k[g] >> sh;
+                    if (top > want) nxt = min(nxt, k[g]);
+                    m[g] = __ballot_sync(0xffffffffu, top == want);
+                }
+                if ((m[0] | m[1] | m[2] | m[3]) == 0u) continue;  // the common case once the prefix is long
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if ((m[g] >> lane) & 1u) row[nc + __popc(m[g] & lt)] = k[g];
+                    nc += __popc(m[g]);
+                }
+            }
+            for (; i0 < na; i0 += 32) {
+                const int i = i0 + lane;
+                const unsigned k = (i < na) ? row[i] : 0u;
+                const unsigned top = k >> sh;
+                const bool hit = i < na && top == want;
+                if (i < na && top > want) nxt = min(nxt, k);
+                const unsigned m = __ballot_sync(0xffffffffu, hit);  // (every lane has read its key before anyone overwrites the row)
+                if (hit) row[nc + __popc(m & lt)] = k;
+                nc += __popc(m);
+            }
+            __syncwarp();
+            na = (int)nc;
+            base = below;
+        }
+        if (!done) {
+            // every bit decided by counting: the survivors all equal key
+            cnt_le = below + (unsigned)na;
+            nxt = __reduce_min_sync(0xffffffffu, nxt);
+        }
+    }
+    float m = key2f(key);
+    if ((ncol & 1) == 0) {
+        // upper middle: the same value if it is repeated, else the smallest key above it
+        const float hi = (cnt_le >= klo + 2u) ? m : key2f(nxt);
+        m = (m + hi) * 0.5f;  // numpy: mean of the two middle values in float32
+    }
+    if (lane == 0) {
+        const size_t o = (size_t)sub * nfft + bin;
+        if (med_lin) med_lin[o] = m;
+        if (med_db) med_db[o] = power_to_db(m, eps);
+    }
+}
+
 // ---- viewer-side reductions on the finished image ----------------------
 // Minimum and maximum over the time axis, the two spectra proc_data's docstring promises next to the
 // median (drfProc.py:430-433).  img [nsub][ncol][nfft]; a CTA owns 32 adjacent bins x 8 column slices,
