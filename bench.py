@@ -8,12 +8,22 @@ A step = one pass of the hot path over one batch of synthetic IQ: per GPU, BASEL
 (1 channel, 25 MS/s, 60 s = 1.5e9 complex64 samples, nfft=4096, 1000 STI bins, every sample
 read once: nint=366, Mode A) -> dB image + time-median.  N > 1 is weak scaling: one such channel
 per GPU (the channel sharding of SURVEY.md section 8(e)), each rank computes its own columns and one
-NCCL gather assembles the dB image (and the per-channel median rows) on rank 0 inside the timed region.
+NCCL gather assembles the dB image (and the per-channel median rows) on rank 0 inside the timed region -- on a
+side stream, under the kernel of the next step (double-buffered outputs).
 
 Prints ONE JSON line (rank 0).  ``value`` = Msamples/s with inputs resident in HBM; ``e2e`` = the same
 metric through the host-buffer C-ABI call (pinned host IQ -> H2D -> kernels -> D2H of the image);
 ``roofline`` = algorithmic bytes of the fused kernel / its CUDA-event time vs the measured HBM
 peak; ``cpu_baseline`` = the oracle port of the reference path timed on this box's host cores.
+
+Extra keys (not part of the driver's contract, recorded with the line):
+  ``configs``      the other BASELINE configs on the same box: cfg1 through the drop-in call (Modes R and A),
+                   cfg5 (nfft 256..2048, 2^30 samples), cfg3- and cfg4-shaped single-GPU runs; at N > 1 a cfg3 leg
+                   (one channel per rank, weak) and a cfg4 leg (time bins of ONE channel sharded, strong) with
+                   kernel / gather / median times reported separately (max over ranks)
+  ``parity_spot``  32 random columns of the timed cfg2 output against the float64 oracle (outside the timed region)
+  ``cpu_baseline_mode_r``  the reference's sti_proc_data exactly as shipped (Mode R), columns/s, 1 core
+  ``e2e_raw_int16`` / ``e2e_raw_int8``  the stored-integer ingest path, on every rank at every N
 """
 from __future__ import annotations
 
@@ -217,7 +227,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-raw", action="store_true", help="skip the extra raw-int16 ingest e2e measurement")
+    ap.add_argument("--no-raw", action="store_true", help="skip the raw int16 / int8 ingest e2e measurements")
+    ap.add_argument("--no-spot", action="store_true", help="skip the oracle spot check of the timed output")
+    ap.add_argument("--no-peer", action="store_true", help="assemble the image with the NCCL gather instead of peer-memory stores")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs (cfg1, cfg3, cfg4, cfg5)")
     ap.add_argument("--variant", default=None, help="force a kernel variant (tuning)")
     ap.add_argument("--items-per-slot", type=int, default=0, help="column split target (tuning)")
     args = ap.parse_args()
@@ -249,40 +262,65 @@ def main():
     iq = synth_iq_device(torch, nsamp, 20240112 + rank, dev)
     starts_np = engine.frame_starts(0, nsamp, NFFT, nint, NTIME)  # drfProc.py:158-159
     starts = torch.from_numpy(starts_np.astype(np.int64)).to(dev)
-    out_db = torch.empty((1, NTIME, NFFT), dtype=torch.float32, device=dev)
-    out_lin = torch.empty((1, NTIME, NFFT), dtype=torch.float32, device=dev)
-    gathered = None
+    # two sets of outputs.  N > 1: the dB image and the median rows of all channels are assembled on rank 0 by the
+    # kernels themselves -- their output pointers are this rank's rows of rank 0's buffers (dist.PeerImage: symmetric
+    # memory over NVLink), so no gather runs at all; a barrier on a side stream, under the next step's kernel,
+    # publishes step i.  Without peer memory the NCCL gather takes the barrier's place (same side stream).
+    out_lin = [torch.empty((1, NTIME, NFFT), dtype=torch.float32, device=dev) for _ in range(2)]
+    img = [pdist.PeerImage([NTIME] * world, NFFT, device=dev, allow_peer=not args.no_peer) for _ in range(2)]
+    med = [pdist.PeerImage([1] * world, NFFT, device=dev, allow_peer=not args.no_peer) for _ in range(2)]
+    out_db = [im.rows.view(1, NTIME, NFFT) for im in img]
+    main_stream = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    step_no = 0
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
     def step(evs=None):
-        nonlocal gathered
+        """evs: (kernel begin, kernel end, median end) timing events of this step, or None"""
+        nonlocal step_no
+        b = step_no & 1
+        step_no += 1
+        if world > 1 and step_no > 2:
+            main_stream.wait_event(ev_free[b])  # step i - 2, which wrote this buffer, has been published
         if evs:
             evs[0].record()
-        plan.run(iq, starts, nint, NFFT, want_lin=True, want_db=True, out_lin=out_lin, out_db=out_db)
+        plan.run(iq, starts, nint, NFFT, want_lin=True, want_db=True, out_lin=out_lin[b], out_db=out_db[b])
         if evs:
             evs[1].record()
         # the time-median is per channel: with one channel per rank it needs no other rank's columns
-        _, med_db = plan.median(out_lin, want_lin=False, want_db=True)
+        plan.median(out_lin[b], want_lin=False, want_db=True, out_db=med[b].rows)
+        if evs:
+            evs[2].record()
         if world > 1:
-            # one gather of the [ncol_local][nfft] dB slabs assembles the N-channel image on rank 0
-            # (plus the N median rows)
-            gathered = pdist.gather_columns(out_db[0], [NTIME] * world, dst=0)
-            pdist.gather_columns(med_db, [1] * world, dst=0)
+            ev_done[b].record(main_stream)
+            with torch.cuda.stream(side):
+                side.wait_event(ev_done[b])
+                img[b].publish()
+                med[b].publish()
+                ev_free[b].record(side)
+
+    def drain():
+        if world > 1:
+            main_stream.wait_stream(side)
 
     for _ in range(max(args.warmup, 3)):
         step()
+    drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     launches0 = engine.launch_count()
-    kev = [(ev(), ev()) for _ in range(args.steps)]
+    kev = [(ev(), ev(), ev()) for _ in range(args.steps)]
     t_beg, t_end = ev(), ev()
     with ClockSampler(local_rank) as clk:
         torch.cuda.synchronize()
         t_beg.record()
         for i in range(args.steps):
             step(kev[i])
+        drain()  # the last gather is inside the timed region
         t_end.record()
         torch.cuda.synchronize()
         launches_timed = engine.launch_count() - launches0
@@ -294,16 +332,31 @@ def main():
             for _ in range(8):
                 step()
             extra_steps += 8
+            drain()
             torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     launches = launches_timed
     total_ms = t_beg.elapsed_time(t_end)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in kev]))
+    med_ms = float(np.mean([b.elapsed_time(c) for _, b, c in kev]))
+    gather_ms = 0.0
     if world > 1:
-        tt = torch.tensor([total_ms, kern_ms], device=dev, dtype=torch.float64)
+        # the gather alone, not overlapped (what the side stream hides): events around it on the side stream
+        g0, g1 = ev(), ev()
+        torch.cuda.synchronize()
+        dist.barrier()
+        with torch.cuda.stream(side):
+            g0.record()
+            for _ in range(4):
+                img[0].publish()
+                med[0].publish()
+            g1.record()
+        torch.cuda.synchronize()
+        gather_ms = g0.elapsed_time(g1) / 4
+        tt = torch.tensor([total_ms, kern_ms, med_ms, gather_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        total_ms, kern_ms = float(tt[0]), float(tt[1])
+        total_ms, kern_ms, med_ms, gather_ms = (float(v) for v in tt)
     ms_per_step = total_ms / args.steps
     samples_per_step = nint * NFFT * NTIME * world
     value = samples_per_step / (ms_per_step * 1e-3) / 1e6
@@ -316,6 +369,13 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "kernel": plan.variant, "kernel_ms": kern_ms,
                 "algorithmic_bytes": alg_bytes}
+    timing = {"kernel_ms_max_rank": kern_ms, "median_ms_max_rank": med_ms, "gather_ms_max_rank": gather_ms,
+              "ms_per_step": ms_per_step,
+              "assembly": img[0].mode,
+              "note": "kernel = fused STFT->PSD->STI (+ finalize), CUDA events per step; assembly 'peer': the kernels store "
+                      "their columns into rank 0's image over NVLink (no gather; gather_ms = the publishing barrier); "
+                      "'gather': NCCL gather of the dB slabs and median rows; either runs on a side stream under the next "
+                      "step's kernel and is timed alone here"}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
@@ -332,25 +392,32 @@ def main():
                                "outputs: linear + dB image, dB time-median",
                    "parallelism": f"channel-per-GPU x{world}" if world > 1 else "single GPU",
                    "l2": f"inputs ({8 * nsamp / 1e9:.1f} GB per step) exceed the 126 MB L2; no flush needed"},
-        "roofline": roofline, "gpu_launches": int(launches), "clocks": clk.summary(),
+        "roofline": roofline, "timing": timing, "gpu_launches": int(launches), "clocks": clk.summary(),
     }
 
     if not args.no_e2e:
         # every rank pushes its own channel through the host-buffer entry point at the same time
-        e2e = e2e_measure(torch, plan, iq, starts_np, nint, args, dist if world > 1 else None)
+        dd = dist if world > 1 else None
+        line["e2e"] = e2e_all_ranks(torch, dd, dev, world, nint,
+                                    e2e_measure(torch, plan, iq, starts_np, nint, args, dd))
+        if not args.no_raw:
+            # the recording as Digital RF stores it (complex int16 / int8): half / a quarter of the PCIe bytes
+            for key, kind in (("e2e_raw_int16", "int16"), ("e2e_raw_int8", "int8")):
+                line[key] = e2e_all_ranks(torch, dd, dev, world, nint,
+                                          e2e_raw_int(torch, plan, iq, starts_np, nint, args, kind, dd))
+    if not args.no_spot:
+        # 32 random columns of the output the timed steps produced, against the float64 oracle (untimed)
+        spot = parity_spot(torch, iq, starts_np, nint, out_lin[(step_no - 1) & 1], out_db[(step_no - 1) & 1].clone(), seed=rank)
         if world > 1:
-            tt = torch.tensor([e2e.get("ms_per_step") or 1e30], device=dev, dtype=torch.float64)
+            tt = torch.tensor([spot["col_err_max"], spot["bin_rel_p999"], spot["db_err_max_strong"]], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            if float(tt[0]) < 1e29:
-                e2e["ms_per_step"] = float(tt[0])
-                e2e["value"] = nint * NFFT * NTIME * world / (float(tt[0]) * 1e-3) / 1e6
-                e2e["h2d_bytes_per_step"] *= world
-                e2e["d2h_bytes_per_step"] *= world
-            else:
-                e2e = {"value": None, "unit": "Msamples/s", "error": "pinned host allocation failed on a rank"}
-        line["e2e"] = e2e
-        if world == 1 and not args.no_raw:
-            line["e2e_raw_int16"] = e2e_raw_int16(torch, plan, iq, starts_np, nint, args)
+            spot.update(col_err_max=float(tt[0]), bin_rel_p999=float(tt[1]), db_err_max_strong=float(tt[2]),
+                        note=spot["note"] + "; max over ranks (every rank checks its own channel)")
+        line["parity_spot"] = spot
+    if not args.no_configs:
+        del iq
+        torch.cuda.empty_cache()
+        line["configs"] = other_configs(torch, engine, pdist, dist if world > 1 else None, dev, rank, world, peak, args)
     if rank == 0 and world == 1 and not args.no_cpu:
         ref = CpuReference(1, 32)
         ref.step()
@@ -362,11 +429,214 @@ def main():
                                           f"({ref.nsamp / 1e6:.0f} Msamples, {dt:.1f} s per pass, data resident before "
                                           "timing), oracle.ref_port.sti_mode_a + median + dB, 1 process "
                                           "(scipy.fft workers=1, the reference's default)"}
+        ref.close()
+        line["cpu_baseline_mode_r"] = cpu_mode_r()
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def e2e_all_ranks(torch, dist, dev, world, nint, e2e):
+    """Whole-job figure of an end-to-end leg: max of the ranks' times, bytes and samples of all ranks."""
+    if world == 1:
+        return e2e
+    tt = torch.tensor([e2e.get("ms_per_step") or 1e30], device=dev, dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    if float(tt[0]) > 1e29:
+        return {"value": None, "unit": "Msamples/s", "error": "pinned host allocation failed on a rank"}
+    ms = float(tt[0])
+    per_gpu = e2e["h2d_bytes_per_step"] / (ms * 1e-3) / 1e9
+    e2e.update(ms_per_step=ms, value=nint * NFFT * NTIME * world / (ms * 1e-3) / 1e6,
+               h2d_bytes_per_step=e2e["h2d_bytes_per_step"] * world, d2h_bytes_per_step=e2e["d2h_bytes_per_step"] * world,
+               h2d_gbs_per_gpu=per_gpu)
+    return e2e
+
+
+def parity_spot(torch, iq, starts_np, nint, lin, db, seed=0, ncheck=32):
+    """copy the frames of >= 32 random columns of the benchmark-sized output back and run
+    the oracle on them.  The input has a tone 20 dB above the noise, so dB is checked on the bins within 60 dB of
+    each column's peak (tests/parity.py); the per-bin figure is reported for information."""
+    from oracle import np_oracle
+    from tests.parity import psd_errors
+    rng = np.random.default_rng(1234 + seed)
+    cols = np.sort(rng.choice(NTIME, size=ncheck, replace=False))
+    t0 = time.perf_counter()
+    got = lin[0][torch.from_numpy(cols).to(lin.device)].cpu().numpy()
+    got_db = db[0][torch.from_numpy(cols).to(db.device)].cpu().numpy()
+    ref = np.empty((ncheck, NFFT))
+    for i, c in enumerate(cols):
+        x = iq[int(starts_np[c]): int(starts_np[c]) + nint * NFFT].cpu().numpy()
+        ref[i] = np_oracle.column_power(x, NFFT, nint, NFFT)
+    e = psd_errors(got.T, ref.T)
+    strong = ref >= ref.max(axis=1, keepdims=True) * 1e-6
+    ddb = np.abs(got_db.astype(np.float64) - 10 * np.log10(ref + 1e-15))
+    return {"columns": int(ncheck), "col_err_max": e["col"], "bin_rel_p999": e["bin_p999"], "bin_rel_max": e["bin_max"],
+            "db_err_max_strong": float(ddb[strong].max()), "db_err_max_all": float(ddb.max()),
+            "tolerances": {"col": 1e-5, "db": 1e-3},
+            "pass": bool(e["col"] <= 1e-5 and float(ddb[strong].max()) <= 1e-3), "seconds": time.perf_counter() - t0,
+            "note": f"{ncheck} random columns of the timed cfg2 output (linear and dB image) vs oracle.np_oracle (float64) on "
+                    "the same device-generated samples"}
+
+
+def cpu_mode_r(ncols=16):
+    """BASELINE.md section 4 line (i): the reference's sti_proc_data exactly as shipped (scipy's periodogram keeps
+    only the first nfft rows of each bin: Mode R), cfg2-shaped input, 1 core, columns/s."""
+    from oracle import ref_port
+    rng = np.random.default_rng(99)
+    d1 = np.empty((NINT * NFFT, ncols), np.complex64)
+    for c in range(ncols):
+        d1[:, c] = ((rng.standard_normal(NINT * NFFT, dtype=np.float32)
+                     + 1j * rng.standard_normal(NINT * NFFT, dtype=np.float32)) * np.float32(7e-3))
+    ref_port.sti_mode_r(d1, FS, NFFT)
+    reps, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < 3.0:
+        f, sxx, med = ref_port.sti_mode_r(d1, FS, NFFT)
+        ref_port.to_dbfs(sxx)
+        reps += 1
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": ncols / dt, "unit": "STI columns/s", "cores": 1, "kind": "port",
+            "msamples_per_s_transformed": ncols * NFFT / dt / 1e6,
+            "sample": f"{ncols} time bins of the cfg2 array ({NINT * NFFT} rows each; the shipped function transforms the "
+                      f"first {NFFT}), {reps} passes of {dt * 1e3:.1f} ms, oracle.ref_port.sti_mode_r (drfProc.py:364-403) + dB"}
+
+
+def _noise_device(torch, n, seed, dev):
+    iq = torch.empty(n, dtype=torch.complex64, device=dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    torch.view_as_real(iq).normal_(0.0, 10 ** (-40 / 20) / np.sqrt(2), generator=gen)
+    return iq
+
+
+def _time_leg(torch, fn, reps=3, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+
+def other_configs(torch, engine, pdist, dist, dev, rank, world, peak, args):
+    """The BASELINE configs bench.py's headline does not cover (see the module docstring).  Device-resident inputs
+    (-40 dBFS noise), CUDA events, median of 3 after 2 warm runs; roofline fraction of the fused kernel from the
+    algorithmic bytes of SURVEY.md section 8(d)."""
+    out = {}
+    dev_index = dev.index
+
+    def resident(nfft, ntime, nint, seed, shard=None):
+        """One channel's STI (or the time bins [lo, hi) of it) on resident samples: buffers and the kernel time."""
+        lo, hi = (0, ntime) if shard is None else shard
+        n = (hi - lo) * nint * nfft
+        iq = _noise_device(torch, n + 8, seed, dev)
+        starts = torch.from_numpy((np.arange(hi - lo, dtype=np.int64) * nint * nfft)).to(dev)
+        plan = engine.StiPlan(nfft, device=dev_index)
+        lin = torch.empty((1, hi - lo, nfft), dtype=torch.float32, device=dev)
+        ncols = [hi - lo] * world if shard is None else [pdist.shard_range(ntime, r, world)[1] - pdist.shard_range(ntime, r, world)[0]
+                                                      for r in range(world)]
+        img = pdist.PeerImage(ncols, nfft, device=dev, allow_peer=not args.no_peer)  # the dB image, assembled on rank 0
+        db = img.rows.view(1, hi - lo, nfft)
+        k_ms = _time_leg(torch, lambda: plan.run(iq, starts, nint, nfft, want_lin=True, want_db=True, out_lin=lin, out_db=db))
+        return plan, iq, starts, lin, db, img, ncols, k_ms
+
+    def summarize(nfft, ntime, nint, k_ms, plan, extra=None, nimg=2):
+        alg = 8 * nfft * nint * ntime + nimg * 4 * nfft * ntime
+        d = {"nfft": nfft, "ntime": ntime, "nint": nint, "kernel_ms": k_ms, "msamples_per_s": nfft * nint * ntime / k_ms / 1e3,
+             "columns_per_s": ntime / (k_ms * 1e-3), "roofline_frac": alg / (k_ms * 1e-3) / 1e9 / peak, "kernel": plan.variant}
+        if extra:
+            d.update(extra)
+        return d
+
+    if world == 1:
+        # ---- cfg1 through the drop-in call: host array in, images and median out ----
+        from pyspectrogram_b200 import drfProc as dp
+        rng = np.random.default_rng(7)
+        nfft1, ntime1, nint1 = 1024, 100, 97
+        d1 = ((rng.standard_normal((nfft1 * nint1, ntime1), dtype=np.float32)
+               + 1j * rng.standard_normal((nfft1 * nint1, ntime1), dtype=np.float32)) * np.float32(7e-3)).astype(np.complex64)
+        for mode, integrate, nsmp in (("R", False, nfft1 * ntime1), ("A", True, nfft1 * nint1 * ntime1)):
+            dp.sti_proc_data_db(d1, 1.0e6, nfft1, integrate=integrate)
+            ts = []
+            for _ in range(5):
+                t0 = time.perf_counter()
+                dp.sti_proc_data_db(d1, 1.0e6, nfft1, integrate=integrate)
+                ts.append(time.perf_counter() - t0)
+            dt = float(np.median(ts))
+            out[f"cfg1_mode_{mode}"] = {"nfft": nfft1, "ntime": ntime1, "nint": 1 if mode == "R" else nint1, "ms": dt * 1e3,
+                                        "msamples_per_s": nsmp / dt / 1e6, "columns_per_s": ntime1 / dt,
+                                        "path": "drfProc.sti_proc_data_db (pageable host array -> H2D -> kernels -> D2H), wall clock",
+                                        "kernel": engine.get_plan(nfft1).variant}
+        # ---- cfg5: nfft 256 .. 2048 on 2^30 samples, 1000 bins ----
+        n5 = 1 << 30
+        iq5 = _noise_device(torch, n5 + 8, 5, dev)
+        for nfft in (256, 512, 1024, 2048):
+            nint = n5 // 1000 // nfft
+            starts = torch.from_numpy(engine.frame_starts(0, n5, nfft, nint, 1000).astype(np.int64)).to(dev)
+            plan = engine.StiPlan(nfft, device=dev_index)
+            db = torch.empty((1, 1000, nfft), dtype=torch.float32, device=dev)
+            k_ms = _time_leg(torch, lambda: plan.run(iq5, starts, nint, nfft, want_lin=False, want_db=True, out_db=db))
+            out[f"cfg5_nfft{nfft}"] = summarize(nfft, 1000, nint, k_ms, plan, nimg=1)
+        del iq5
+        torch.cuda.empty_cache()
+    # ---- cfg3: nfft 16384, 3600 bins x nint 64, one 30 GB channel per GPU (weak) ----
+    # ---- cfg4: nfft 65536, 3600 bins x nint 16 of ONE channel, time bins sharded over the ranks (strong) ----
+    for name, nfft, ntime, nint, sharded in (("cfg3", 16384, 3600, 64, False), ("cfg4", 65536, 3600, 16, True)):
+        shard = pdist.shard_range(ntime, rank, world) if sharded else None
+        plan, iq, starts, lin, db, img, ncols, k_ms = resident(nfft, ntime, nint, 100 * nfft + (0 if sharded else rank), shard)
+        resharded = sharded and world > 1
+
+        def med_fn(im):
+            return plan.median(im.contiguous(), want_lin=False, want_db=True)
+
+        def median():
+            if resharded:  # the median needs every time bin of a frequency row: re-shard by frequency (dist.py)
+                pdist.median_over_time_sharded(lin[0], ncols, med_fn, dst=0)
+            else:
+                plan.median(lin, want_lin=False, want_db=True)
+
+        def whole():
+            plan.run(iq, starts, nint, nfft, want_lin=True, want_db=True, out_lin=lin, out_db=db)
+            median()
+            img.publish()
+
+        if dist is not None:
+            dist.barrier()
+        m_ms = _time_leg(torch, median)
+        g_ms = _time_leg(torch, img.publish) if world > 1 else 0.0
+        if dist is not None:
+            dist.barrier()
+        s_ms = _time_leg(torch, whole)
+        vals = [k_ms, m_ms, g_ms, s_ms]
+        if dist is not None:
+            tt = torch.tensor(vals, device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            vals = [float(v) for v in tt]
+        k_ms, m_ms, g_ms, s_ms = vals
+        total_cols = ntime if sharded else ntime * world
+        my_cols = ncols[rank]
+        d = summarize(nfft, my_cols, nint, k_ms, plan,
+                      {"median_ms_max_rank": m_ms, "gather_ms_max_rank": g_ms, "step_ms": s_ms, "assembly": img.mode,
+                       "scaling": "strong (time bins of one channel over the ranks)" if sharded else "weak (one channel per rank)",
+                       "aggregate_msamples_per_s": nfft * nint * total_cols / s_ms / 1e3,
+                       "aggregate_columns_per_s": total_cols / (s_ms * 1e-3),
+                       "kernel_ms_max_rank": k_ms,
+                       "note": "kernel, median and image assembly timed apart (CUDA events, max over ranks); step = kernel + median + "
+                               "publish back to back on one stream; assembly 'peer': the kernel stores its dB columns into rank 0's "
+                               "image over NVLink and gather_ms is the publishing barrier, 'gather': NCCL gather of the slabs" + ("; median re-sharded by frequency (the path's one exchange)"
+                                                                     if resharded else "")})
+        d["columns_per_rank"] = my_cols
+        out[f"{name}_n{world}"] = d
+        del iq, lin, db, plan, img
+        torch.cuda.empty_cache()
+    return out
 
 
 def e2e_measure(torch, plan, iq_dev, starts_np, nint, args, dist=None):
@@ -399,39 +669,52 @@ def e2e_measure(torch, plan, iq_dev, starts_np, nint, args, dist=None):
     return {"value": nint * NFFT * NTIME / dt / 1e6, "unit": "Msamples/s", "ms_per_step": dt * 1e3,
             "h2d_bytes_per_step": int(8 * (starts_np[-1] + nint * NFFT - starts_np[0]) + 8 * NTIME),
             "d2h_bytes_per_step": int(d2h), "steps": len(times),
+            "h2d_gbs_per_gpu": 8 * (starts_np[-1] + nint * NFFT - starts_np[0]) / dt / 1e9,
             "path": "psg_sti_host (pinned host complex64 recording + int64 start table -> dB image + dB median), "
                     "one channel per rank, all ranks at once"}
 
 
-def e2e_raw_int16(torch, plan, iq_dev, starts_np, nint, args):
-    """Extra (not the contract's ``e2e``): the same recording stored as Digital RF stores it --
-    complex int16 -- pushed through the typed host entry point with 1/ref folded into the kernel
-    (SURVEY.md section 8(f) N1).  Half the PCIe bytes of the complex64 path for the same samples."""
-    ref = 2.0 ** 15.5  # get_ref for int16 (drfProc.py:199-201)
+def e2e_raw_int(torch, plan, iq_dev, starts_np, nint, args, kind, dist=None):
+    """Extra (not the contract's ``e2e``): the same recording stored as Digital RF stores it -- complex int16 or
+    int8 -- pushed through the typed host entry point with 1/ref folded into the kernel:
+    half / a quarter of the PCIe bytes of the complex64 path for the same samples.  All ranks at once."""
+    bits, dt_t, lim = (16, torch.int16, 32767) if kind == "int16" else (8, torch.int8, 127)
+    ref = 2.0 ** (bits - 0.5)  # get_ref (drfProc.py:199-201)
     nsamp = iq_dev.numel()
+    host, err = None, ""
     try:
-        host = torch.empty((nsamp, 2), dtype=torch.int16, pin_memory=True)
+        host = torch.empty((nsamp, 2), dtype=dt_t, pin_memory=True)
     except Exception as exc:
-        return {"value": None, "unit": "Msamples/s", "error": f"pinned host allocation failed: {exc}"}
+        err = str(exc)
+    ok = torch.tensor([1 if host is not None else 0], device=iq_dev.device)
+    if dist is not None:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok[0]) == 0:
+        return {"value": None, "unit": "Msamples/s", "error": f"pinned host allocation failed: {err}"}
     view = torch.view_as_real(iq_dev)
+    gain = ref * (1.0 if kind == "int16" else 8.0)  # int8: lift the -20 dBFS tone / -40 dBFS noise above one count
     chunk = 1 << 26
     for lo in range(0, nsamp, chunk):
         hi = min(nsamp, lo + chunk)
-        host[lo:hi].copy_((view[lo:hi] * ref).round_().clamp_(-32767, 32767).to(torch.int16))
+        host[lo:hi].copy_((view[lo:hi] * gain).round_().clamp_(-lim, lim).to(dt_t))
     torch.cuda.synchronize()
     h = host.numpy()
     times = []
     for i in range(1 + max(1, args.e2e_steps)):
+        if dist is not None:
+            dist.barrier()
         t0 = time.perf_counter()
-        res = plan.host(h, starts_np, nint, NFFT, in_scale=1.0 / ref, want=("db", "med_db"))
+        res = plan.host(h, starts_np, nint, NFFT, in_scale=1.0 / gain, want=("db", "med_db"))
         dt = time.perf_counter() - t0
         if i:
             times.append(dt)
     dt = float(np.mean(times))
+    h2d = int((bits // 4) * (starts_np[-1] + nint * NFFT - starts_np[0]) + 8 * NTIME)
     return {"value": nint * NFFT * NTIME / dt / 1e6, "unit": "Msamples/s", "ms_per_step": dt * 1e3,
-            "h2d_bytes_per_step": int(4 * (starts_np[-1] + nint * NFFT - starts_np[0]) + 8 * NTIME),
-            "d2h_bytes_per_step": int(res["db"].nbytes + res["med_db"].nbytes), "steps": len(times),
-            "path": "psg_sti_host_typed(PSG_IQ_CI16): pinned host complex-int16 recording -> dB image + dB median"}
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(res["db"].nbytes + res["med_db"].nbytes),
+            "h2d_gbs_per_gpu": h2d / dt / 1e9, "steps": len(times),
+            "path": f"psg_sti_host_typed(PSG_IQ_CI{bits}): pinned host complex-{kind} recording -> dB image + dB median, "
+                    "one channel per rank, all ranks at once"}
 
 
 if __name__ == "__main__":

@@ -124,14 +124,18 @@ class StiPlan:
                 C.c_void_p(out_db.data_ptr() if out_db is not None else None), C.c_void_p(stream)))
         return out_lin, out_db
 
-    def median(self, img, *, eps=DB_EPS, want_lin=True, want_db=False):
-        """``np.median(sxx, axis=1)`` (drfProc.py:401) of a ``[nsub][ncol][nfft]`` linear image."""
+    def median(self, img, *, eps=DB_EPS, want_lin=True, want_db=False, out_lin=None, out_db=None):
+        """``np.median(sxx, axis=1)`` (drfProc.py:401) of a ``[nsub][ncol][nfft]`` linear image.  ``out_lin`` /
+        ``out_db``: optional contiguous float32 ``[nsub][nfft]`` destinations (e.g. rows of a ``dist.PeerImage``)."""
         torch = _torch()
         if not img.is_cuda or img.dtype != torch.float32 or not img.is_contiguous() or img.dim() != 3:
             raise ValueError("img must be a contiguous CUDA float32 [nsub][ncol][nfft] tensor")
         nsub, ncol, nfft = (int(v) for v in img.shape)
-        lin = torch.empty((nsub, nfft), dtype=torch.float32, device=img.device) if want_lin else None
-        db = torch.empty((nsub, nfft), dtype=torch.float32, device=img.device) if want_db else None
+        for o in (out_lin, out_db):
+            if o is not None and (o.dtype != torch.float32 or not o.is_contiguous() or o.numel() != nsub * nfft):
+                raise ValueError("median outputs must be contiguous float32 [nsub][nfft]")
+        lin = out_lin if out_lin is not None else (torch.empty((nsub, nfft), dtype=torch.float32, device=img.device) if want_lin else None)
+        db = out_db if out_db is not None else (torch.empty((nsub, nfft), dtype=torch.float32, device=img.device) if want_db else None)
         stream = torch.cuda.current_stream(img.device).cuda_stream
         with self._lock:
             _lib.check(self._lib.psg_median_time(

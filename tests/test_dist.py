@@ -130,3 +130,46 @@ def test_median_over_time_sharded_two_gloo_ranks(ncols, nfft):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(results)
+
+
+def _peer_image_worker(rank, world, port, ncols, nfft, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        full = torch.arange(sum(ncols) * nfft, dtype=torch.float32).reshape(sum(ncols), nfft)
+        lo = sum(ncols[:rank])
+        img = pdist.PeerImage(ncols, nfft, device="cpu")  # no CUDA peers here: local slab + gather on publish()
+        ok = img.mode == "gather" and tuple(img.rows.shape) == (ncols[rank], nfft)
+        img.rows.copy_(full[lo:lo + ncols[rank]])  # stands for the kernel writing its columns
+        out = img.publish()
+        q.put(bool(ok and (torch.equal(out, full) if rank == 0 else out is None)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ncols", [[5, 5], [4, 3]])
+def test_peer_image_falls_back_to_the_gather(ncols):
+    """dist.PeerImage without peer memory (gloo, CPU tensors): every rank writes its rows into a local slab and
+    publish() assembles the image on rank 0 with the gather -- same result as the peer-memory form, which the
+    multi-GPU bench exercises (rows aliasing rank 0's buffer over NVLink)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_image_worker, args=(r, 2, port, ncols, 8, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(results)
+
+
+def test_peer_image_single_process():
+    import torch
+    img = pdist.PeerImage([7], 12, device="cpu")
+    assert img.mode == "local" and img.publish() is img.rows and tuple(img.rows.shape) == (7, 12)
+    assert img.rows.dtype == torch.float32
