@@ -254,7 +254,7 @@ def main():
         engine.set_variant(args.variant)
     if args.items_per_slot:
         from pyspectrogram_b200 import _lib
-        _lib.check(_lib.load().psg_set_items_per_slot(args.items_per_slot))
+        _lib.check(_lib.load().psg_debug_set_items_per_slot(args.items_per_slot))
 
     nsamp = int(FS * args.seconds)
     nint = nsamp // NTIME // NFFT

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define PSG_ABI_VERSION 1
+#define PSG_ABI_VERSION 2
 
 typedef struct psg_plan psg_plan; /* opaque */
 
@@ -118,6 +118,22 @@ int psg_sti_run_typed(psg_plan* plan, const void* iq_dev, int iq_type,
                       int frames_per_col, int64_t hop,
                       float in_scale, float eps,
                       float* out_lin_dev, float* out_db_dev, void* cuda_stream);
+
+/*
+ * The same with a bound on what the kernels may address: iq_elems complex elements are readable from iq_dev
+ * (the recording's extent travels with it).  psg_sti_run[_typed] trust the offset table;
+ * here a one-CTA kernel first clamps every col_offset into [0, iq_elems - column extent] (the table stays on the
+ * device: no host round trip, ~2 us) and writes 1 to *oob_flag_dev when it had to move one, 0 otherwise, then
+ * the transform runs on the clamped table -- a stale or wrong table gives a flagged image, not an out-of-bounds
+ * read.  A column extent larger than iq_elems is refused on the host (PSG_ERR_ARG).  oob_flag_dev: int32 on the
+ * device, valid when the stream has passed this call.
+ */
+int psg_sti_run_checked(psg_plan* plan, const void* iq_dev, int iq_type, int64_t iq_elems,
+                        int64_t sample_stride, int64_t sub_stride, int nsub,
+                        const int64_t* col_offset_dev, int ncol,
+                        int frames_per_col, int64_t hop,
+                        float in_scale, float eps,
+                        float* out_lin_dev, float* out_db_dev, int32_t* oob_flag_dev, void* cuda_stream);
 int psg_sti_host_typed(psg_plan* plan, const void* iq_host, int iq_type, int64_t iq_host_elems,
                        int64_t sample_stride, int64_t sub_stride, int nsub,
                        const int64_t* col_offset_host, int ncol,
@@ -160,7 +176,7 @@ int psg_gather_bins(psg_plan* plan, const float* img_dev, int64_t rows, int nfft
 /*
  * Host-buffer entry point (what drfProc.sti_proc_data / proc_data call): takes the IQ array in
  * host memory, copies the span the columns touch to the device -- in one piece up to
- * psg_set_host_chunk bytes (1 GiB), beyond that in groups of consecutive columns, the copy of
+ * 1 GiB (psg_debug_set_host_chunk), beyond that in groups of consecutive columns, the copy of
  * group j+1 on a second stream overlapping the kernels of group j through two staging buffers, so
  * recordings larger than device memory work -- runs psg_sti_run + psg_median_time and copies the
  * results back.  Synchronous: results are valid on return.
@@ -179,32 +195,31 @@ int psg_sti_host(psg_plan* plan, const void* iq_host, int64_t iq_host_elems,
                  float* out_lin_host, float* out_db_host,
                  float* med_lin_host, float* med_db_host);
 
-/* Force the simple generic kernel (debug / cross-check) for subsequent psg_sti_run calls. */
-int psg_set_force_generic(int on);
-
 /*
- * Kernel-variant table (tuning / cross-checks).  psg_set_variant(name) makes psg_sti_run prefer the
- * named variant for its FFT length when the layout allows it; NULL or "" restores the automatic
- * choice.  Path names for the large lengths: "split" (two-phase path, nfft = 8192..65536), "cluster_ldg" /
- * "cluster" / "cluster_dsmem" (one CTA per 4096-point row, nfft = 8192..65536), "whole" (whole-frame kernels:
- * 8192 / 16384 in one CTA, 32768 / 65536 on clusters of 2 / 4 CTAs), "whole_r2" (two rows per CTA: clusters
- * of 2 / 4 / 8 for 16384 / 32768 / 65536), "whole_r4", "whole_s2" / "whole_s8" (ring depth of the single-CTA
- * kernel), "whole_f" (16384 as 16 x 2 x 16 x 2 x 16 with both radix-2 passes in registers, sti_whole16.cuh); "bluestein" / "bluestein_r2" select the Bluestein kernels (mixed-radix passes / radix 2) for non
- * powers of two.  Process-wide.
+ * Debugging and tuning knobs.  NOT part of the stable surface a viewer binds: they exist for the parity tests
+ * (cross-checking one kernel against another) and for measurement scripts.  Each applies to the CALLING THREAD
+ * only (thread-local state; a new thread starts with the defaults), so one of the viewer's worker threads
+ * (drfview.py:177-178) cannot change the kernel another one launches.
+ *
+ *   psg_debug_set_force_generic   the simple radix-2 kernel (and the CTA-wide median) for subsequent calls
+ *   psg_debug_set_variant(name)   prefer the named variant for its FFT length when the layout allows it; NULL or ""
+ *       restores the automatic choice.  Path names for the large lengths: "r32" (three-pass radix-32 kernels,
+ *       sti_r32.cuh: the default at 16384 / 32768 / 65536, and at 8192 with one frame per column), "split"
+ *       (two-phase path through an HBM scratch, 8192..65536), "cluster_ldg" / "cluster" / "cluster_dsmem" (one CTA
+ *       per 4096-point row), "whole" (four-pass whole-frame kernels: 8192 / 16384 in one CTA, 32768 / 65536 on
+ *       clusters of 2 / 4), "whole_r2", "whole_r4", "whole_s2" / "whole_s8", "whole_f" (16 x 2 x 16 x 2 x 16,
+ *       sti_whole16.cuh); "bluestein" / "bluestein_r2" for non powers of two
+ *   psg_debug_set_split_scratch   bytes of scratch per chunk of the split path (default cap 2 GiB)
+ *   psg_debug_set_host_chunk      psg_sti_host streams spans above this many bytes in column chunks (default 1 GiB)
+ *   psg_debug_set_mode_r_multi    0: one-frame-per-column launches use the one-column-per-CTA kernels
+ *   psg_debug_set_items_per_slot  work items per resident CTA slot the column split aims for (default 24)
  */
-int psg_set_variant(const char* name);
-/* Bytes of the L2-resident scratch the large-nfft split path (nfft >= 16384) works through per
- * chunk (default 2 GiB cap; only what a call needs is allocated).  Process-wide; tuning / tests. */
-int psg_set_split_scratch(int64_t bytes);
-/* psg_sti_host streams recordings whose touched span exceeds this many bytes in column chunks of about
- * this size (default 1 GiB; two staging buffers of that size instead of the whole span on the device).
- * Process-wide; tuning / tests. */
-int psg_set_host_chunk(int64_t bytes);
-/* One-frame-per-column launches (Mode R) use kernels that run several columns per CTA (default on;
- * 0 selects the one-column-per-CTA kernels).  Tuning / cross-checks. */
-int psg_set_mode_r_multi(int on);
-/* Work items per resident CTA slot that the column split aims for (default 24).  Tuning. */
-int psg_set_items_per_slot(int n);
+int psg_debug_set_force_generic(int on);
+int psg_debug_set_variant(const char* name);
+int psg_debug_set_split_scratch(int64_t bytes);
+int psg_debug_set_host_chunk(int64_t bytes);
+int psg_debug_set_mode_r_multi(int on);
+int psg_debug_set_items_per_slot(int n);
 int psg_variant_count(void);
 const char* psg_variant_name(int index);
 int psg_variant_logn(int index);

@@ -53,6 +53,8 @@ _SIGS = {
                               C.c_float, C.c_float, _P, _P, _P]),
     "psg_sti_run_typed": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int64, C.c_int, _P, C.c_int, C.c_int, C.c_int64,
                                     C.c_float, C.c_float, _P, _P, _P]),
+    "psg_sti_run_checked": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int, _P, C.c_int, C.c_int,
+                                      C.c_int64, C.c_float, C.c_float, _P, _P, _P, _P]),
     "psg_sti_host_typed": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int, _P, C.c_int, C.c_int,
                                      C.c_int64, C.c_float, C.c_float, _P, _P, _P, _P]),
     "psg_median_time": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P]),
@@ -60,12 +62,12 @@ _SIGS = {
     "psg_gather_bins": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, C.c_int, C.c_float, C.c_float, _P, _P]),
     "psg_sti_host": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, _P, C.c_int, C.c_int,
                                C.c_int64, C.c_float, C.c_float, _P, _P, _P, _P]),
-    "psg_set_force_generic": (C.c_int, [C.c_int]),
-    "psg_set_variant": (C.c_int, [C.c_char_p]),
-    "psg_set_split_scratch": (C.c_int, [C.c_int64]),
-    "psg_set_mode_r_multi": (C.c_int, [C.c_int]),
-    "psg_set_host_chunk": (C.c_int, [C.c_int64]),
-    "psg_set_items_per_slot": (C.c_int, [C.c_int]),
+    "psg_debug_set_force_generic": (C.c_int, [C.c_int]),
+    "psg_debug_set_variant": (C.c_int, [C.c_char_p]),
+    "psg_debug_set_split_scratch": (C.c_int, [C.c_int64]),
+    "psg_debug_set_mode_r_multi": (C.c_int, [C.c_int]),
+    "psg_debug_set_host_chunk": (C.c_int, [C.c_int64]),
+    "psg_debug_set_items_per_slot": (C.c_int, [C.c_int]),
     "psg_variant_count": (C.c_int, []),
     "psg_variant_name": (C.c_char_p, [C.c_int]),
     "psg_variant_logn": (C.c_int, [C.c_int]),

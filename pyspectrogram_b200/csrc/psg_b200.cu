@@ -29,18 +29,31 @@
 // ------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
-static std::atomic<int> g_force_generic{0};
-static std::mutex g_variant_mu;
-static std::string g_variant_override;  // "" = automatic
-static std::atomic<int> g_items_per_slot{24};
-static std::atomic<int> g_use_multi{1};  // Mode R: use the multi-column twin kernels  // work items per resident CTA slot the column split aims for
+// Debugging / tuning knobs (psg_debug_set_*): they apply to the CALLING THREAD only -- the viewer runs up to seven
+// worker threads over one library (drfview.py:177-178), and one of them forcing a variant must not change the
+// kernel another one is about to launch.  (The wrappers keep the std::atomic / mutex interface of the code below.)
+template <class T>
+struct TlsKnob {
+    T v;
+    T load() const { return v; }
+    void store(T x) { v = x; }
+};
+struct NoMutex {
+    void lock() {}
+    void unlock() {}
+};
+static thread_local TlsKnob<int> g_force_generic{0};
+static thread_local NoMutex g_variant_mu;
+static thread_local std::string g_variant_override;  // "" = automatic
+static thread_local TlsKnob<int> g_items_per_slot{24};  // work items per resident CTA slot the column split aims for
+static thread_local TlsKnob<int> g_use_multi{1};        // Mode R: use the multi-column twin kernels
 // Scratch cap of the large-nfft split path.  Measured (profiles/r01_sweep_split_scratch*.txt): L2-sized
 // chunks (16..128 MiB) lose more to the three short dependent launches per chunk than they save in
 // HBM traffic; 1..4 GiB chunks run each phase at its own roofline.
-static std::atomic<long long> g_split_scratch_bytes{2048ll << 20};
+static thread_local TlsKnob<long long> g_split_scratch_bytes{2048ll << 20};
 // psg_sti_host: recordings whose touched span exceeds this are streamed in column chunks of about this size
-static std::atomic<long long> g_host_chunk_bytes{1024ll << 20};
-static std::atomic<int> g_cluster_rowtma{0};  // cluster path: 0 = rows loaded to registers (default), 1 = by bulk copy, 2 = DSMEM exchange
+static thread_local TlsKnob<long long> g_host_chunk_bytes{1024ll << 20};
+static thread_local TlsKnob<int> g_cluster_rowtma{0};  // cluster path: 0 = rows loaded to registers (default), 1 = by bulk copy, 2 = DSMEM exchange
 
 static int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -56,6 +69,24 @@ static int fail(int code, const char* fmt, ...) {
             return fail(PSG_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
                         __FILE__, __LINE__);                                                   \
     } while (0)
+
+// Every entry point works on the plan's device and leaves the caller's current device as it found it (torch
+// derives ITS current device from cudaGetDevice: a call for cuda:1 from a thread working on cuda:0 must not
+// redirect that thread's later allocations).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) ok = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define PSG_ON_DEVICE(dev)                                                                   \
+    DeviceGuard dev_guard_(dev);                                                             \
+    if (!dev_guard_.ok) return fail(PSG_ERR_CUDA, "cudaSetDevice(%d) failed (%s:%d)", (dev), __FILE__, __LINE__)
 
 // ------------------------------------------------------------------------------------------------
 // kernel variants
@@ -214,7 +245,7 @@ static const char* const g_default_tma_int[] = {"ldg5_4x8_f32", "ldg6_8x8_f32", 
 
 static const Variant* pick_variant(int logn, bool tma_ok, int iqt) {
     {
-        std::lock_guard<std::mutex> lk(g_variant_mu);
+        std::lock_guard<NoMutex> lk(g_variant_mu);
         if (!g_variant_override.empty()) {
             const Variant* v = variant_by_name(g_variant_override.c_str());
             if (v && v->logn == logn && v->iqt == iqt && (v->loader != PSG_LOADER_TMA || tma_ok)) return v;
@@ -281,6 +312,8 @@ struct psg_plan {
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     long long* d_off = nullptr;
     size_t off_elems = 0;
+    long long* d_offchk = nullptr;  // psg_sti_run_checked: the column offsets clamped to the addressable range
+    size_t offchk_elems = 0;
     float* d_out[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t out_elems[4] = {0, 0, 0, 0};
     cudaStream_t stream = nullptr;
@@ -332,12 +365,12 @@ extern "C" int psg_device_count(void) {
     return n;
 }
 extern "C" int64_t psg_launch_count(void) { return g_launches.load(); }
-extern "C" int psg_set_force_generic(int on) {
+extern "C" int psg_debug_set_force_generic(int on) {
     g_force_generic.store(on ? 1 : 0);
     return PSG_OK;
 }
-extern "C" int psg_set_variant(const char* name) {
-    std::lock_guard<std::mutex> lk(g_variant_mu);
+extern "C" int psg_debug_set_variant(const char* name) {
+    std::lock_guard<NoMutex> lk(g_variant_mu);
     g_variant_override = name ? name : "";
     if (!g_variant_override.empty()) {
         bool ok = g_variant_override == "split" || g_variant_override == "cluster" || g_variant_override == "cluster_ldg" ||
@@ -352,22 +385,22 @@ extern "C" int psg_set_variant(const char* name) {
     }
     return PSG_OK;
 }
-extern "C" int psg_set_split_scratch(int64_t bytes) {
-    if (bytes < (1 << 20)) return fail(PSG_ERR_ARG, "psg_set_split_scratch: at least 1 MiB");
+extern "C" int psg_debug_set_split_scratch(int64_t bytes) {
+    if (bytes < (1 << 20)) return fail(PSG_ERR_ARG, "psg_debug_set_split_scratch: at least 1 MiB");
     g_split_scratch_bytes.store(bytes);
     return PSG_OK;
 }
-extern "C" int psg_set_host_chunk(int64_t bytes) {
-    if (bytes < (1 << 16)) return fail(PSG_ERR_ARG, "psg_set_host_chunk: at least 64 KiB");
+extern "C" int psg_debug_set_host_chunk(int64_t bytes) {
+    if (bytes < (1 << 16)) return fail(PSG_ERR_ARG, "psg_debug_set_host_chunk: at least 64 KiB");
     g_host_chunk_bytes.store(bytes);
     return PSG_OK;
 }
-extern "C" int psg_set_mode_r_multi(int on) {
+extern "C" int psg_debug_set_mode_r_multi(int on) {
     g_use_multi.store(on ? 1 : 0);
     return PSG_OK;
 }
-extern "C" int psg_set_items_per_slot(int n) {
-    if (n < 1 || n > 1024) return fail(PSG_ERR_ARG, "psg_set_items_per_slot: 1..1024");
+extern "C" int psg_debug_set_items_per_slot(int n) {
+    if (n < 1 || n > 1024) return fail(PSG_ERR_ARG, "psg_debug_set_items_per_slot: 1..1024");
     g_items_per_slot.store(n);
     return PSG_OK;
 }
@@ -511,7 +544,7 @@ extern "C" int psg_plan_create(psg_plan** out, int nfft, int window_kind, double
     int sms = 0;
     int rc = check_device(device, &sms);
     if (rc) return rc;
-    CUDA_TRY(cudaSetDevice(device));
+    PSG_ON_DEVICE(device);
 
     psg_plan* p = new psg_plan();
     p->nfft = nfft;
@@ -568,7 +601,7 @@ extern "C" int psg_plan_create(psg_plan** out, int nfft, int window_kind, double
 
 extern "C" int psg_plan_destroy(psg_plan* p) {
     if (!p) return PSG_OK;
-    cudaSetDevice(p->device);
+    DeviceGuard dev_guard_(p->device);
     cudaFree(p->d_win);
     cudaFree(p->d_tw);
     cudaFree(p->d_twp);
@@ -596,6 +629,7 @@ extern "C" int psg_plan_destroy(psg_plan* p) {
         if (p->ev_free[i]) cudaEventDestroy(p->ev_free[i]);
     }
     cudaFree(p->d_off);
+    cudaFree(p->d_offchk);
     for (int i = 0; i < 4; ++i) cudaFree(p->d_out[i]);
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
@@ -1476,7 +1510,7 @@ static int run_bluestein(psg_plan* p, StiArgs a, int ncs, int frames_per_col, cu
     {
         bool force_r2 = false, force_bs = false;
         {
-            std::lock_guard<std::mutex> lk(g_variant_mu);
+            std::lock_guard<NoMutex> lk(g_variant_mu);
             force_r2 = g_variant_override == "bluestein_r2";
             force_bs = g_variant_override == "bluestein";
         }
@@ -1555,6 +1589,53 @@ extern "C" int psg_sti_run(psg_plan* p, const void* iq_dev, int64_t sample_strid
                              hop, in_scale, eps, out_lin_dev, out_db_dev, cuda_stream);
 }
 
+// column offsets -> [0, max_ok], and a flag when one had to be moved (one CTA; the table is a few thousand entries)
+__global__ void __launch_bounds__(256) check_offsets_kernel(const long long* __restrict__ off, int ncol, long long max_ok,
+                                                            long long* __restrict__ out, int* __restrict__ flag) {
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
+        const long long o = off[c];
+        const long long k = o < 0 ? 0 : (o > max_ok ? max_ok : o);
+        out[c] = k;
+        mine |= (k != o);
+    }
+    if (mine) bad = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) *flag = bad;
+}
+
+extern "C" int psg_sti_run_checked(psg_plan* p, const void* iq_dev, int iq_type, int64_t iq_elems, int64_t sample_stride,
+                                   int64_t sub_stride, int nsub, const int64_t* col_offset_dev, int ncol, int frames_per_col,
+                                   int64_t hop, float in_scale, float eps, float* out_lin_dev, float* out_db_dev,
+                                   int32_t* oob_flag_dev, void* cuda_stream) {
+    if (!p) return fail(PSG_ERR_ARG, "psg_sti_run_checked: plan is NULL");
+    if (!col_offset_dev || !oob_flag_dev) return fail(PSG_ERR_ARG, "psg_sti_run_checked: NULL pointer");
+    if (nsub < 1 || ncol < 1 || frames_per_col < 1 || sample_stride < 1 || sub_stride < 0 || (frames_per_col > 1 && hop < 1))
+        return fail(PSG_ERR_ARG, "psg_sti_run_checked: bad shape/stride");
+    // elements one column reads past its offset (as in psg_sti_host)
+    const long long col_extent = ((long long)(frames_per_col - 1) * hop + (p->nfft - 1)) * sample_stride +
+                                 (long long)(nsub - 1) * sub_stride + 1;
+    if (iq_elems < col_extent)
+        return fail(PSG_ERR_ARG, "psg_sti_run_checked: a column needs %lld elements, the array has %lld", col_extent,
+                    (long long)iq_elems);
+    PSG_ON_DEVICE(p->device);
+    {
+        size_t have = p->offchk_elems * 8;
+        const int rc = ensure_buffer((void**)&p->d_offchk, &have, (size_t)ncol * 8);
+        p->offchk_elems = have / 8;
+        if (rc) return rc;
+    }
+    check_offsets_kernel<<<1, 256, 0, (cudaStream_t)cuda_stream>>>((const long long*)col_offset_dev, ncol,
+                                                                   (long long)iq_elems - col_extent, p->d_offchk, oob_flag_dev);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return psg_sti_run_typed(p, iq_dev, iq_type, sample_stride, sub_stride, nsub, (const int64_t*)p->d_offchk, ncol,
+                             frames_per_col, hop, in_scale, eps, out_lin_dev, out_db_dev, cuda_stream);
+}
+
 extern "C" int psg_sti_run_typed(psg_plan* p, const void* iq_dev, int iq_type, int64_t sample_stride, int64_t sub_stride,
                                  int nsub, const int64_t* col_offset_dev, int ncol, int frames_per_col, int64_t hop,
                                  float in_scale, float eps, float* out_lin_dev, float* out_db_dev, void* cuda_stream) {
@@ -1572,7 +1653,7 @@ extern "C" int psg_sti_run_typed(psg_plan* p, const void* iq_dev, int iq_type, i
     if ((long long)ncol * nsub > (1ll << 30)) return fail(PSG_ERR_ARG, "psg_sti_run: too many columns");
     if (((reinterpret_cast<uintptr_t>(out_lin_dev) | reinterpret_cast<uintptr_t>(out_db_dev)) & 15) != 0 && p->nfft % 4 == 0)
         return fail(PSG_ERR_ARG, "psg_sti_run: output images must be 16-byte aligned");
-    CUDA_TRY(cudaSetDevice(p->device));
+    PSG_ON_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const int N = p->nfft;
     const int ncs = ncol * nsub;
@@ -1614,7 +1695,7 @@ extern "C" int psg_sti_run_typed(psg_plan* p, const void* iq_dev, int iq_type, i
         // three-launch split path stays ahead (27 % vs 25 %).
         int rowtma = g_cluster_rowtma.load();
         {
-            std::lock_guard<std::mutex> lk(g_variant_mu);
+            std::lock_guard<NoMutex> lk(g_variant_mu);
             force_split = g_variant_override == "split";
             force_cluster = g_variant_override == "cluster" || g_variant_override == "cluster_ldg" || g_variant_override == "cluster_dsmem";
             if (g_variant_override == "cluster") rowtma = 1;
@@ -1629,7 +1710,7 @@ extern "C" int psg_sti_run_typed(psg_plan* p, const void* iq_dev, int iq_type, i
         }
         bool force_r32 = false, other_path = false;
         {
-            std::lock_guard<std::mutex> lk(g_variant_mu);
+            std::lock_guard<NoMutex> lk(g_variant_mu);
             force_r32 = g_variant_override == "r32";
             other_path = !g_variant_override.empty() && !force_r32;
         }
@@ -1749,7 +1830,7 @@ extern "C" int psg_median_time(psg_plan* p, const float* img_dev, int nsub, int 
     if (!p) return fail(PSG_ERR_ARG, "psg_median_time: plan is NULL");
     if (!img_dev || (!med_lin_dev && !med_db_dev)) return fail(PSG_ERR_ARG, "psg_median_time: NULL pointer");
     if (nsub < 1 || ncol < 1 || nfft < 1) return fail(PSG_ERR_ARG, "psg_median_time: bad shape");
-    CUDA_TRY(cudaSetDevice(p->device));
+    PSG_ON_DEVICE(p->device);
     // Default: warp-per-bin selection (median_select_kernel).  Rows padded to a multiple of 128 keys + 4 (the
     // transposing load is then bank-conflict free).  Bins per CTA (= warps per CTA): what keeps the most warps
     // resident -- all the keys of a bin stay in shared memory, so at 3600 columns an SM holds 15 bins.
@@ -1788,7 +1869,7 @@ extern "C" int psg_median_time(psg_plan* p, const float* img_dev, int nsub, int 
             return PSG_OK;
         }
     }
-    // Fallback (more columns than a tile holds; also what psg_set_force_generic selects, as the cross-check of
+    // Fallback (more columns than a tile holds; also what psg_debug_set_force_generic selects, as the cross-check of
     // the selection kernel): CTA-wide bisection, tiled while [ncol][8] keys fit, else re-reading L2.
     const size_t smem_max = 222 * 1024;
     const size_t hdr = 3 * 256 * sizeof(unsigned);
@@ -1820,7 +1901,7 @@ extern "C" int psg_minmax_time(psg_plan* p, const float* img_dev, int nsub, int 
     if (!img_dev || (!min_lin_dev && !max_lin_dev && !min_db_dev && !max_db_dev))
         return fail(PSG_ERR_ARG, "psg_minmax_time: NULL pointer");
     if (nsub < 1 || ncol < 1 || nfft < 1) return fail(PSG_ERR_ARG, "psg_minmax_time: bad shape");
-    CUDA_TRY(cudaSetDevice(p->device));
+    PSG_ON_DEVICE(p->device);
     const long long blocks = (long long)nsub * ((nfft + 31) / 32);
     minmax_time_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(img_dev, nsub, ncol, nfft, eps, min_lin_dev,
                                                                                max_lin_dev, min_db_dev, max_db_dev);
@@ -1834,7 +1915,7 @@ extern "C" int psg_gather_bins(psg_plan* p, const float* img_dev, int64_t rows, 
     if (!p) return fail(PSG_ERR_ARG, "psg_gather_bins: plan is NULL");
     if (!img_dev || !idx_dev || !out_dev) return fail(PSG_ERR_ARG, "psg_gather_bins: NULL pointer");
     if (rows < 1 || nfft < 1 || count < 1) return fail(PSG_ERR_ARG, "psg_gather_bins: bad shape");
-    CUDA_TRY(cudaSetDevice(p->device));
+    PSG_ON_DEVICE(p->device);
     const size_t total = (size_t)rows * (size_t)count;
     const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)p->sms * 16);
     gather_bins_kernel<<<blocks, 256, 0, (cudaStream_t)cuda_stream>>>(img_dev, (size_t)rows, nfft, idx_dev, count, clamp_lo,
@@ -1877,7 +1958,7 @@ extern "C" int psg_sti_host_typed(psg_plan* p, const void* iq_host, int iq_type,
     if (lo < 0 || hi + col_extent > iq_host_elems)
         return fail(PSG_ERR_ARG, "psg_sti_host: columns reach [%lld, %lld) outside the %lld-element host array", lo,
                     hi + col_extent, (long long)iq_host_elems);
-    CUDA_TRY(cudaSetDevice(p->device));
+    PSG_ON_DEVICE(p->device);
     cudaStream_t st = p->stream;
     // keep the device copy 16-byte aligned relative to the host element parity so that aligned
     // host frames stay aligned on the device

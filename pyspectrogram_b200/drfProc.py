@@ -55,22 +55,37 @@ def _freq_axis(nfft, sr):
     return np.fft.fftshift(np.fft.fftfreq(nfft, 1 / sr))
 
 
-def _is_raw_iq(d1):
-    """Raw integer IQ: Digital RF's structured ('r', 'i') int16 / int8 dtype, or a plain int16 /
-    int8 array whose last axis is (re, im)."""
-    return isinstance(d1, np.ndarray) and (d1.dtype.fields is not None or d1.dtype in (np.int16, np.int8))
+def _is_raw_iq(d1, raw_pairs=False):
+    """Raw integer IQ: Digital RF's structured ('r', 'i') int16 / int8 dtype (detected), or -- only when the
+    caller says so with ``raw_pairs=True`` -- a plain int16 / int8 array whose last axis is (re, im).  A plain
+    integer array without the keyword is REAL samples, as it is for the reference (scipy casts it)."""
+    if not isinstance(d1, np.ndarray):
+        return False
+    if d1.dtype.fields is not None:
+        return True
+    if raw_pairs:
+        if d1.dtype not in (np.int16, np.int8):
+            raise TypeError("raw_pairs=True takes an int16 or int8 array with a last axis (re, im)")
+        return True
+    return False
 
 
-def _sti(d1, sr, nfft, integrate, device, want, ref=1.0):
+def _raw_view(d1):
+    """C-contiguous raw IQ array and its logical (complex) shape."""
+    arr = np.ascontiguousarray(d1)
+    shape = arr.shape if arr.dtype.fields is not None else arr.shape[:-1]
+    if arr.dtype.fields is None and arr.shape[-1] != 2:
+        raise ValueError("raw integer IQ must have a last axis of length 2 (re, im)")
+    return arr, shape
+
+
+def _sti(d1, sr, nfft, integrate, device, want, ref=1.0, raw_pairs=False):
     nfft = int(nfft)
-    if _is_raw_iq(d1):
+    if _is_raw_iq(d1, raw_pairs):
         # extension (SURVEY.md section 8(f) N1): the samples go to the GPU as stored; 1/ref is applied
         # to the power in the kernel epilogue instead of x/ref on the host (drfProc.py:129)
-        arr = np.ascontiguousarray(d1)
+        arr, shape = _raw_view(d1)
         out_dtype = np.float32
-        shape = arr.shape if arr.dtype.fields is not None else arr.shape[:-1]
-        if arr.dtype.fields is None and arr.shape[-1] != 2:
-            raise ValueError("raw integer IQ must have a last axis of length 2 (re, im)")
         in_scale = 1.0 / float(ref)
     else:
         arr, out_dtype = _as_c64(d1)
@@ -105,7 +120,7 @@ def _sti_core(arr, shape, out_dtype, in_scale, sr, nfft, integrate, device, want
     return _freq_axis(nfft, sr), out
 
 
-def sti_proc_data(d1, sr, nfft, *, integrate=False, device=0, ref=1.0):
+def sti_proc_data(d1, sr, nfft, *, integrate=False, device=0, ref=1.0, raw_pairs=False):
     """STI of ``d1`` shaped ``(nfft*nint, ntime[, nsub])`` -> ``(f, sxx, sxx_med)``.
 
     ``sxx`` is ``(nfft, ntime[, nsub])`` linear power (float32 for complex64 input), fftshifted;
@@ -113,21 +128,23 @@ def sti_proc_data(d1, sr, nfft, *, integrate=False, device=0, ref=1.0):
     ``integrate=False`` only the first ``nfft`` rows of each time bin are used, exactly like the
     reference; ``integrate=True`` averages ``floor(rows/nfft)`` back-to-back frames (Mode A).
 
-    ``d1`` may also be raw integer IQ (Digital RF's structured int16 / int8 dtype, or an integer array
-    with a last axis ``(re, im)``) together with ``ref`` = the full-scale level of ``get_ref``: the
-    result equals ``sti_proc_data(d1_as_complex / ref, ...)`` without the host-side cast and divide.
+    ``d1`` may also be raw integer IQ -- Digital RF's structured int16 / int8 ('r', 'i') dtype, or, with
+    ``raw_pairs=True``, a plain integer array with a last axis ``(re, im)`` -- together with ``ref`` = the
+    full-scale level of ``get_ref``: the result equals ``sti_proc_data(d1_as_complex / ref, ...)`` without the
+    host-side cast and divide.  A plain integer array WITHOUT ``raw_pairs`` is real-valued samples, as in the
+    reference.
     """
-    f, out = _sti(d1, sr, nfft, integrate, device, ("lin", "med"), ref)
+    f, out = _sti(d1, sr, nfft, integrate, device, ("lin", "med"), ref, raw_pairs)
     return f, out["lin"], out["med"]
 
 
-def sti_proc_data_db(d1, sr, nfft, *, integrate=False, device=0, eps=_EPS, ref=1.0):
-    """``sti_proc_data`` plus the worker loop's dB step (drfProc.py:308-310) fused on the GPU.
+def sti_proc_data_db(d1, sr, nfft, *, integrate=False, device=0, ref=1.0, raw_pairs=False):
+    """``sti_proc_data`` plus the worker loop's dB step (drfProc.py:308-310, ``10*log10(x + 1e-15)``) fused on
+    the GPU.
 
     Returns ``(f, sxx_dbfs, sxx_med_dbfs)``.
     """
-    assert eps == _EPS
-    f, out = _sti(d1, sr, nfft, integrate, device, ("db", "med_db"), ref)
+    f, out = _sti(d1, sr, nfft, integrate, device, ("db", "med_db"), ref, raw_pairs)
     return f, out["db"], out["med_db"]
 
 
@@ -195,19 +212,27 @@ def plot_indices(freqs, cfrange_khz, max_nfreqs=2 ** 15):
 
 
 def sti_plot_data(d1, sr, nfft, cfrange_khz, *, max_nfreqs=2 ** 15, crange=None, integrate=False, device=0, eps=_EPS,
-                  ref=1.0):
+                  ref=1.0, raw_pairs=False):
     """What the viewer draws from one ``sti_proc_data`` call, reduced on the GPU before the copy back.
 
     The viewer converts the STI and its median to dB (drfProc.py:308-310), keeps ``plotindices``
     (drfview.py:1005-1023, indexing at :1289-1295) and, for the PNG export, clips to the colour range
     (drfview.py:1515-1518).  Returns ``(plotfreqs, sxx_db[:, plotindices...], med_db[plotindices...])``
     with the reference's orientation ``(nfreq, ntime[, nsub])`` / ``(nfreq[, nsub])``; ``crange=None``
-    leaves the values unclipped (the on-screen plot clips through ``vmin``/``vmax``).
+    leaves the values unclipped (the on-screen plot clips through ``vmin``/``vmax``).  Raw integer IQ with
+    ``ref`` / ``raw_pairs`` as in ``sti_proc_data``.
     """
     import torch
     nfft = int(nfft)
-    arr, out_dtype = _as_c64(d1)
-    shape = arr.shape
+    if _is_raw_iq(d1, raw_pairs):
+        arr, shape = _raw_view(d1)
+        out_dtype = np.float32
+        if arr.dtype.fields is not None:  # ('r', 'i') -> trailing (re, im) axis of the base integer type
+            base = next(iter(arr.dtype.fields.values()))[0]
+            arr = arr.view(base).reshape(shape + (2,))
+    else:
+        arr, out_dtype = _as_c64(d1)
+        shape = arr.shape
     if len(shape) not in (2, 3):
         raise ValueError("d1 must be (rows, ntime) or (rows, ntime, nsub)")
     rows, ntime = int(shape[0]), int(shape[1])
@@ -225,7 +250,7 @@ def sti_plot_data(d1, sr, nfft, cfrange_khz, *, max_nfreqs=2 ** 15, crange=None,
     flat = arr[:span].reshape(-1)
     offs = torch.from_numpy(np.arange(ntime, dtype=np.int64) * nsub).to(dev)
     lin, db = plan.run(torch.from_numpy(flat).to(dev), offs, nfr, nfft, sample_stride=ntime * nsub, sub_stride=1, nsub=nsub,
-                       in_scale=1.0 / float(ref), eps=eps, want_lin=True, want_db=True)
+                       in_scale=1.0 / float(ref), eps=eps, want_lin=True, want_db=True, validate=True)
     _, med_db = plan.median(lin, eps=eps, want_lin=False, want_db=True)
     sel_db = plan.gather_bins(db, idx, clamp=crange)
     sel_med = plan.gather_bins(med_db, idx, clamp=crange)
@@ -533,7 +558,7 @@ class DrfProcessor(QRunnable):
         plan = engine.get_plan(nfft, self.device)
         offs = torch.from_numpy(((n_st - base) * nsub).astype(np.int64)).to(buf.device)
         lin, db = plan.run(buf, offs, frames, nfft, sample_stride=nsub, sub_stride=1, nsub=nsub, in_scale=in_scale,
-                           eps=_EPS, want_lin=True, want_db=True)
+                           eps=_EPS, want_lin=True, want_db=True, validate=True)
         _, mdb = plan.median(lin, eps=_EPS, want_lin=False, want_db=True)
         sxx_dbfs = db.permute(2, 1, 0).cpu().numpy()      # (nfft, ntime, nsub) as the viewer indexes it
         sxx_med_dbfs = mdb.t().cpu().numpy()               # (nfft, nsub)

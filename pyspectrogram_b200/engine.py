@@ -82,7 +82,7 @@ class StiPlan:
 
     # ---- device path -----------------------------------------------------------------------
     def run(self, iq, col_offsets, frames_per_col=1, hop=None, *, sample_stride=1, sub_stride=0, nsub=1,
-            in_scale=1.0, eps=DB_EPS, want_lin=True, want_db=False, out_lin=None, out_db=None):
+            in_scale=1.0, eps=DB_EPS, want_lin=True, want_db=False, out_lin=None, out_db=None, validate=False):
         """Fused frame->window->FFT->|X|^2->mean->fftshift->(dB) on device-resident IQ.
 
         ``iq``: CUDA tensor, complex64 (or float32 viewed as interleaved re/im), or raw integer IQ as
@@ -92,6 +92,12 @@ class StiPlan:
         ``col_offsets``: CUDA int64 tensor ``[ncol]`` of element offsets into ``iq``.
         Returns ``(lin, db)`` tensors ``[nsub][ncol][nfft]`` (``None`` for the one not requested).
         Work is enqueued on torch's current stream; nothing synchronises.
+
+        ``iq`` must be contiguous (the kernels address its storage through the strides given here, not the
+        tensor's own).  ``validate=True`` goes through ``psg_sti_run_checked``: the offset table is clamped on
+        the device to what ``iq`` holds, and a table that reached outside (e.g. offsets computed against an
+        old ``RecordingCache`` base) raises ``IndexError`` after the launch -- one 4-byte read back, so this
+        form synchronises.
         """
         torch = _torch()
         if not iq.is_cuda or not col_offsets.is_cuda:
@@ -102,6 +108,8 @@ class StiPlan:
             raise TypeError(f"iq must be complex64 (or its float32 view), or raw int16 / int8 (re, im) pairs; got {iq.dtype}")
         if col_offsets.dtype != torch.int64 or not col_offsets.is_contiguous():
             raise TypeError("col_offsets must be a contiguous int64 tensor")
+        if not iq.is_contiguous():
+            raise ValueError("iq must be contiguous (pass strides through sample_stride / sub_stride)")
         if iq.device.index != self.device or col_offsets.device.index != self.device:
             raise ValueError("tensors are not on the plan's device")
         ncol = int(col_offsets.numel())
@@ -116,12 +124,24 @@ class StiPlan:
             if o is not None and (o.dtype != torch.float32 or not o.is_contiguous() or o.numel() != nsub * ncol * self.nfft):
                 raise ValueError("output tensors must be contiguous float32 [nsub][ncol][nfft]")
         stream = torch.cuda.current_stream(dev).cuda_stream
+        p_lin = C.c_void_p(out_lin.data_ptr() if out_lin is not None else None)
+        p_db = C.c_void_p(out_db.data_ptr() if out_db is not None else None)
+        if validate:
+            iq_elems = int(iq.numel()) if iq.dtype == torch.complex64 else int(iq.numel()) // 2
+            flag = torch.zeros(1, dtype=torch.int32, device=dev)
+            with self._lock:
+                _lib.check(self._lib.psg_sti_run_checked(
+                    self._h, C.c_void_p(iq.data_ptr()), iq_type, iq_elems, int(sample_stride), int(sub_stride), int(nsub),
+                    C.c_void_p(col_offsets.data_ptr()), ncol, int(frames_per_col), hop, float(in_scale), float(eps),
+                    p_lin, p_db, C.c_void_p(flag.data_ptr()), C.c_void_p(stream)))
+            if int(flag.item()):
+                raise IndexError(f"col_offsets reach outside the {iq_elems}-element recording (columns were clamped)")
+            return out_lin, out_db
         with self._lock:
             _lib.check(self._lib.psg_sti_run_typed(
                 self._h, C.c_void_p(iq.data_ptr()), iq_type, int(sample_stride), int(sub_stride), int(nsub),
                 C.c_void_p(col_offsets.data_ptr()), ncol, int(frames_per_col), hop, float(in_scale), float(eps),
-                C.c_void_p(out_lin.data_ptr() if out_lin is not None else None),
-                C.c_void_p(out_db.data_ptr() if out_db is not None else None), C.c_void_p(stream)))
+                p_lin, p_db, C.c_void_p(stream)))
         return out_lin, out_db
 
     def median(self, img, *, eps=DB_EPS, want_lin=True, want_db=False, out_lin=None, out_db=None):
@@ -255,6 +275,7 @@ class RecordingCache:
         self.lo = self.hi = 0
         self.buf = None       # torch tensor [capacity, nsub(, 2)]
         self.samples_read = 0  # samples fetched from the reader so far (tests / stats)
+        self.appended_in_place = 0  # slides that fitted the slack (no reallocation, no copy of the kept part)
 
     def _upload(self, arr):
         torch = _torch()
@@ -281,14 +302,24 @@ class RecordingCache:
             # sliding window: keep [lo, self.hi), fetch only [self.hi, hi)
             new = self._upload(read(self.hi, hi - self.hi))
             self.samples_read += hi - self.hi
+            if hi - self.lo <= int(self.buf.shape[0]):
+                # the tail fits the slack behind the resident samples: appended in place, nothing moves and the
+                # base stays (the rows before lo are simply no longer asked for)
+                self.buf[self.hi - self.lo: hi - self.lo] = new
+                self.hi = hi
+                self.appended_in_place += 1
+                return self.buf, self.lo
             keep = self.buf[lo - self.lo: self.hi - self.lo]
-            cap = int((hi - lo) * (1.0 + self.slack))
+            cap = int((hi - lo) * (1.0 + self.slack)) + 1
             out = torch.empty((cap,) + tuple(keep.shape[1:]), dtype=keep.dtype, device=keep.device)
             out[: keep.shape[0]] = keep
             out[keep.shape[0]: keep.shape[0] + new.shape[0]] = new
             self.buf, self.lo, self.hi = out, lo, hi
             return self.buf, self.lo
-        self.buf = self._upload(read(lo, hi - lo))
+        new = self._upload(read(lo, hi - lo))
+        cap = int((hi - lo) * (1.0 + self.slack)) + 1
+        self.buf = torch.empty((cap,) + tuple(new.shape[1:]), dtype=new.dtype, device=new.device)
+        self.buf[: new.shape[0]] = new
         self.samples_read += hi - lo
         self.lo, self.hi = lo, hi
         return self.buf, self.lo
@@ -298,18 +329,27 @@ class RecordingCache:
         self.lo = self.hi = 0
 
 
-_plans = {}
-_plans_lock = threading.Lock()
+_plans = threading.local()
 
 
 def get_plan(nfft: int, device: int = 0, window=("kaiser", KAISER_BETA)) -> StiPlan:
-    """Process-wide plan cache keyed by (nfft, device, window)."""
+    """Plan cache keyed by (nfft, device, window), ONE CACHE PER THREAD.
+
+    A plan owns device scratch (partial sums, the split path's buffers, staging of the host path) that the
+    kernels of a call keep using after the call has returned to the host -- ``run`` / ``median`` / ``minmax``
+    enqueue on the caller's stream and do not synchronise.  ``StiPlan._lock`` serialises the enqueueing only, so
+    two of the viewer's worker threads (drfview.py:177-178) on different streams must not share a plan
+    (``include/psg_b200.h``: one plan per worker thread).  The cache lives in thread-local storage: a thread's
+    plans are destroyed with it.
+    """
     key = (int(nfft), int(device), tuple(window) if not isinstance(window, str) else (window,))
-    with _plans_lock:
-        plan = _plans.get(key)
-        if plan is None:
-            plan = _plans[key] = StiPlan(nfft, device, window)
-        return plan
+    cache = getattr(_plans, "cache", None)
+    if cache is None:
+        cache = _plans.cache = {}
+    plan = cache.get(key)
+    if plan is None:
+        plan = cache[key] = StiPlan(nfft, device, window)
+    return plan
 
 
 def frame_starts(st_sample, en_sample, nfft, nint, ntime) -> np.ndarray:
@@ -328,21 +368,21 @@ def launch_count() -> int:
 
 
 def set_variant(name=None):
-    _lib.check(_lib.load().psg_set_variant(name.encode() if name else None))
+    _lib.check(_lib.load().psg_debug_set_variant(name.encode() if name else None))
 
 
 def set_split_scratch(nbytes: int):
     """Scratch bytes per chunk of the large-nfft split path (default cap 2 GiB)."""
-    _lib.check(_lib.load().psg_set_split_scratch(int(nbytes)))
+    _lib.check(_lib.load().psg_debug_set_split_scratch(int(nbytes)))
 
 
 def set_host_chunk(nbytes: int):
     """Span above which ``StiPlan.host`` streams the recording in column chunks (default 1 GiB)."""
-    _lib.check(_lib.load().psg_set_host_chunk(int(nbytes)))
+    _lib.check(_lib.load().psg_debug_set_host_chunk(int(nbytes)))
 
 
 def set_force_generic(on: bool):
-    _lib.check(_lib.load().psg_set_force_generic(1 if on else 0))
+    _lib.check(_lib.load().psg_debug_set_force_generic(1 if on else 0))
 
 
 def variants():

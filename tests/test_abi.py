@@ -40,7 +40,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_variant_table():
     lib = _lib.load()
-    assert lib.psg_version() == 1
+    assert lib.psg_version() == 2  # PSG_ABI_VERSION: psg_sti_run_checked, psg_debug_* (thread-local) knobs
     names = [lib.psg_variant_name(i).decode() for i in range(lib.psg_variant_count())]
     assert len(names) == len(set(names)) and len(names) >= 20
     for i, name in enumerate(names):
@@ -105,7 +105,54 @@ def test_argument_errors_map_to_python_exceptions():
         _lib.check(_lib.PSG_ERR_UNSUPPORTED)
     with pytest.raises(ValueError):
         _lib.check(_lib.PSG_ERR_ARG)
-    assert lib.psg_set_split_scratch(1) == _lib.PSG_ERR_ARG
+    assert lib.psg_debug_set_split_scratch(1) == _lib.PSG_ERR_ARG
+    assert lib.psg_sti_run_checked(None, None, 0, 0, 1, 0, 1, None, 1, 1, 1, 1.0, 1e-15, None, None, None, None) == _lib.PSG_ERR_ARG
+
+
+def test_debug_knobs_are_per_thread():
+    """psg_debug_set_variant in one thread does not change what another thread's calls pick (the viewer's seven
+    workers share the library, drfview.py:177-178): a bad name fails only for its own call, and a knob set in a
+    worker thread is gone with the thread."""
+    import threading
+    lib = _lib.load()
+    seen = {}
+
+    def worker():
+        seen["set"] = lib.psg_debug_set_items_per_slot(7)
+        seen["bad"] = lib.psg_debug_set_variant(b"no_such_variant")
+        seen["msg"] = lib.psg_last_error()
+
+    th = threading.Thread(target=worker)
+    th.start()
+    th.join()
+    assert seen["set"] == 0 and seen["bad"] == _lib.PSG_ERR_ARG and b"no_such_variant" in seen["msg"]
+    # this thread's state is untouched: its own override is still the automatic choice (setting "" succeeds and
+    # the error message of the other thread is not visible here)
+    assert lib.psg_debug_set_variant(None) == 0
+
+
+def test_plan_cache_is_per_thread():
+    """engine.get_plan hands every thread its own plans (a plan's scratch is in use by enqueued
+    kernels after the call returns, so two threads on different streams must not share one)."""
+    import threading
+    got = {}
+
+    class FakePlan:
+        def __init__(self, nfft, device, window):
+            self.key = (nfft, device)
+
+    orig = engine.StiPlan
+    engine.StiPlan = FakePlan
+    try:
+        a = engine.get_plan(1024)
+        assert engine.get_plan(1024) is a and engine.get_plan(2048) is not a
+        th = threading.Thread(target=lambda: got.update(p=engine.get_plan(1024), q=engine.get_plan(1024)))
+        th.start()
+        th.join()
+        assert got["p"] is got["q"] and got["p"] is not a
+    finally:
+        engine.StiPlan = orig
+        engine._plans.cache = {}
 
 
 def test_host_side_input_checks_need_no_device():

@@ -529,9 +529,23 @@ def test_drop_in_accepts_raw_iq_and_processor_raw_ingest(dp):
     assert_psd_close(m1, m0, what="raw drop-in median")
     # plain integer array with a trailing (re, im) axis
     plain = np.stack([raw["r"], raw["i"]], axis=-1)
-    f2, s2, m2 = dp.sti_proc_data(plain, 1.0e6, nfft, ref=ref, integrate=True)
+    f2, s2, m2 = dp.sti_proc_data(plain, 1.0e6, nfft, ref=ref, integrate=True, raw_pairs=True)
     f3, s3, m3 = dp.sti_proc_data(xc, 1.0e6, nfft, integrate=True)
     assert_psd_close(s2, s3, what="raw drop-in mode A")
+    # without the keyword a plain integer array is REAL samples, as for the reference (scipy casts it): the
+    # (rows, ntime, 2) array above is two real sub-channels, float64 out (drfProc.py:387-396)
+    from oracle import ref_port
+    f4, s4, m4 = dp.sti_proc_data(plain, 1.0e6, nfft)
+    f5, s5, m5 = ref_port.sti_mode_r(plain, 1.0e6, nfft)
+    assert s4.shape == s5.shape == (nfft, ntime, 2) and s4.dtype == s5.dtype
+    assert_psd_close(s4, s5, noise_like=False, what="plain int array = real samples")
+    # the plot-data entry takes the raw forms too (same dispatch)
+    pf_a, sx_a, md_a = dp.sti_plot_data(raw, 1.0e6, nfft, (-200.0, 200.0), ref=ref)
+    pf_b, sx_b, md_b = dp.sti_plot_data(xc, 1.0e6, nfft, (-200.0, 200.0))
+    pf_c, sx_c, md_c = dp.sti_plot_data(plain, 1.0e6, nfft, (-200.0, 200.0), ref=ref, raw_pairs=True)
+    assert np.array_equal(pf_a, pf_b) and sx_a.shape == sx_b.shape == sx_c.shape
+    assert np.abs(sx_a - sx_b).max() <= 1e-3 and np.abs(md_a - md_b).max() <= 1e-3
+    assert np.array_equal(sx_a, sx_c) and np.array_equal(md_a, md_c)
 
     n = 1 << 17
     data = np.round((rng.standard_normal((n, nsub)) + 1j * rng.standard_normal((n, nsub))) * 3000).astype(np.complex64)
@@ -558,11 +572,11 @@ def test_mode_r_multi_column_kernels_match_single_column_kernels(torch, nfft):
     lin_m, db_m = plan.run(x, starts, 1, nfft, want_lin=True, want_db=True)
     name_m = plan.variant
     try:
-        _lib.check(_lib.load().psg_set_mode_r_multi(0))
+        _lib.check(_lib.load().psg_debug_set_mode_r_multi(0))
         lin_s, db_s = plan.run(x, starts, 1, nfft, want_lin=True, want_db=True)
         name_s = plan.variant
     finally:
-        _lib.check(_lib.load().psg_set_mode_r_multi(1))
+        _lib.check(_lib.load().psg_debug_set_mode_r_multi(1))
     # small nfft packs many columns into one CTA already: too few column blocks here to batch further
     assert name_m == name_s + "_m" or (nfft < 1024 and name_m == name_s), (name_m, name_s)
     assert torch.equal(lin_m, lin_s) and torch.equal(db_m, db_s)
@@ -724,6 +738,16 @@ def test_resident_recording_cache_matches_per_bin_reads(dp, nsub, raw_ingest):
         s0 = s0.reshape(s1.shape)
         m0 = m0.reshape(m1.shape)
         assert np.abs(s0 - s1).max() <= 1e-3 and np.abs(m0 - m1).max() <= 1e-3, (integrate, nsub, raw_ingest)
+        # oracle leg: the reference pipeline on the CPU (read_sti -> sti_proc_data / per-bin averaging -> dB)
+        from oracle import ref_port
+        sr = proc.drfIn.sr_dict["ch0"]
+        s_samp = dp._time_to_sample(proc.drfIn.time_bnds[0], sr)
+        e_samp = dp._time_to_sample(proc.drfIn.time_bnds[1], sr)
+        _, dout = ref_port.read_sti_from_array(data, s_samp, e_samp, 512, 4, 50, ref=2 ** 15.5, first_sample=reader.first)
+        fr, sr_, mr = (ref_port.sti_mode_a if integrate else ref_port.sti_mode_r)(dout.astype(np.complex64), sr, 512)
+        assert np.array_equal(f1, fr)
+        assert_db_close(s1, ref_port.to_dbfs(sr_).reshape(s1.shape), ref_lin=sr_.reshape(s1.shape), what="resident dB vs oracle")
+        assert_db_close(m1, ref_port.to_dbfs(mr).reshape(m1.shape), ref_lin=mr.reshape(m1.shape), what="resident median dB vs oracle")
 
 
 def test_resident_cache_sliding_window_reads_only_the_new_tail(torch):
@@ -748,6 +772,43 @@ def test_resident_cache_sliding_window_reads_only_the_new_tail(torch):
     buf, base = cache.ensure(read, 40000, 45000)  # disjoint: re-read
     assert base == 40000 and calls[-1] == (40000, 5000)
     assert np.array_equal(buf[:5000, 0].cpu().numpy(), rec[40000:45000])
+    # a small slide fits the slack behind the resident samples: appended in place, same storage, same base
+    ptr, before = buf.data_ptr(), cache.appended_in_place
+    buf, base = cache.ensure(read, 41000, 46000)
+    assert base == 40000 and calls[-1] == (45000, 1000) and buf.data_ptr() == ptr and cache.appended_in_place == before + 1
+    assert np.array_equal(buf[1000:6000, 0].cpu().numpy(), rec[41000:46000])
+
+
+def test_checked_run_clamps_and_flags_a_bad_offset_table(torch):
+    """psg_sti_run_checked (the recording's extent travels with it): a good table gives
+    the unchecked result bit for bit; a table that reaches outside the array is clamped on the device and
+    flagged (IndexError here), never read out of bounds; a column longer than the array is refused."""
+    from pyspectrogram_b200 import engine
+    rng = np.random.default_rng(77)
+    nfft, nfr = 1024, 3
+    x = _recording(rng, nfft * nfr * 5 + 100)
+    xd = torch.from_numpy(x).cuda()
+    good = torch.from_numpy((np.arange(5) * nfft * nfr + np.array([0, 3, 1, 100, 7])).astype(np.int64)).cuda()
+    plan = engine.StiPlan(nfft)
+    lin0, db0 = plan.run(xd, good, nfr, nfft, want_lin=True, want_db=True)
+    lin1, db1 = plan.run(xd, good, nfr, nfft, want_lin=True, want_db=True, validate=True)
+    assert torch.equal(lin0, lin1) and torch.equal(db0, db1)
+    for bad_off in (x.size - nfft * nfr + 1, -5, 1 << 40):
+        bad = good.clone()
+        bad[2] = bad_off
+        with pytest.raises(IndexError):
+            plan.run(xd, bad, nfr, nfft, validate=True)
+    with pytest.raises(ValueError):  # one column needs more samples than the array holds
+        plan.run(xd[: nfft * 2], good[:1], nfr, nfft, validate=True)
+    with pytest.raises(ValueError):  # a sliced view: the kernels address storage, not the tensor's strides
+        plan.run(xd[::2], good[:1], 1, nfft)
+    # raw integer pairs: the extent is counted in complex elements
+    raw = torch.from_numpy(np.stack([x.real, x.imag], axis=1) * 1000).to(torch.int16).cuda()
+    lin2, _ = plan.run(raw, good, nfr, nfft, validate=True)
+    bad = good.clone()
+    bad[4] = x.size - nfft * nfr + 1
+    with pytest.raises(IndexError):
+        plan.run(raw, bad, nfr, nfft, validate=True)
 
 
 def test_seven_worker_threads_share_the_library(dp):
@@ -780,6 +841,62 @@ def test_seven_worker_threads_share_the_library(dp):
     assert not errs, errs
     for (f0, s0, m0), (f1, s1, m1) in zip(expect, got):
         assert np.array_equal(f0, f1) and np.array_equal(s0, s1) and np.array_equal(m0, m1)
+
+
+def test_device_path_workers_at_one_nfft_do_not_share_scratch(dp, torch):
+    """the device-path calls (run / median / gather: enqueue, no sync) of two viewer workers at the SAME
+    nfft must not race on a shared plan's scratch.  Plans are per thread (engine.get_plan): threads mixing
+    sti_plot_data, the resident worker loop's path and sti_proc_data_db at one nfft -- a long integration whose
+    columns are split over CTAs (partial-sum scratch) -- reproduce the single-threaded results bit for bit."""
+    import threading
+    from pyspectrogram_b200 import engine
+    rng = np.random.default_rng(23)
+    nfft, nint, ntime = 4096, 96, 6   # few columns x many frames: split columns + finalize through plan scratch
+    cases = []
+    for k in range(6):
+        d1 = ((rng.standard_normal((nfft * nint, ntime)) + 1j * rng.standard_normal((nfft * nint, ntime))) * 1e-2).astype(np.complex64)
+        cases.append(d1)
+
+    def call(k):
+        d1 = cases[k]
+        if k % 3 == 0:
+            return dp.sti_plot_data(d1, 1.0e6, nfft, (-400.0, 400.0), integrate=True)
+        if k % 3 == 1:
+            return dp.sti_proc_data_db(d1, 1.0e6, nfft, integrate=True)
+        # the device path on a side stream, as a worker with its own stream would use it
+        plan = engine.get_plan(nfft)
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            x = torch.from_numpy(np.ascontiguousarray(d1.T).reshape(-1)).cuda()
+            offs = torch.arange(ntime, dtype=torch.int64, device="cuda") * (nfft * nint)
+            lin, db = plan.run(x, offs, nint, nfft, want_lin=True, want_db=True)
+            med, _ = plan.median(lin)
+            out = (lin.cpu().numpy(), db.cpu().numpy(), med.cpu().numpy())
+        return out
+
+    expect = [call(k) for k in range(len(cases))]
+    got = [None] * len(cases)
+    errs = []
+    plans = {}
+
+    def work(k):
+        try:
+            plans[k] = engine.get_plan(nfft)
+            for _ in range(6):
+                got[k] = call(k)
+        except Exception as exc:  # pragma: no cover
+            errs.append((k, exc))
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(cases))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs, errs
+    assert len({id(p) for p in plans.values()}) == len(cases)  # one plan per thread
+    for e, g in zip(expect, got):
+        for a, b in zip(e, g):
+            assert np.array_equal(a, b)
 
 
 def test_gui_maximum_counts(torch):

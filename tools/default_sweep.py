@@ -17,7 +17,7 @@ def main():
     ap.add_argument("--gb", type=float, default=4.0)
     ap.add_argument("--ntime", type=int, default=1000)
     ap.add_argument("--nffts", default="64,256,512,1000,1024,2048,4096,8192,16384,32768,65536")
-    ap.add_argument("--variant", default=None, help="force a kernel variant / path (psg_set_variant)")
+    ap.add_argument("--variant", default=None, help="force a kernel variant / path (psg_debug_set_variant)")
     args = ap.parse_args()
     import torch
     from pyspectrogram_b200 import engine

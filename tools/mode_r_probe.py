@@ -45,7 +45,7 @@ def main():
         out = torch.empty((1, ncol, nfft), dtype=torch.float32, device=dev)
         line = f"Mode A nfft={nfft:6d} nint={nint} ncol={ncol:6d}:"
         for multi in (1, 0):
-            _lib.check(_lib.load().psg_set_mode_r_multi(multi))
+            _lib.check(_lib.load().psg_debug_set_mode_r_multi(multi))
             run = lambda: plan.run(iq, starts, nint, nfft, want_lin=False, want_db=True, out_db=out)
             run(); torch.cuda.synchronize()
             ts = []
@@ -55,7 +55,7 @@ def main():
                 ts.append(e0.elapsed_time(e1))
             ms = float(np.median(ts))
             line += f"  [{plan.variant}] {ms:.4f} ms {n / ms / 1e6:6.1f} Gs/s"
-        _lib.check(_lib.load().psg_set_mode_r_multi(1))
+        _lib.check(_lib.load().psg_debug_set_mode_r_multi(1))
         print(line, flush=True)
         del iq, out
     # cfg1 through the drop-in API (host arrays, as the reference is called)
