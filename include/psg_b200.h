@@ -208,7 +208,8 @@ int psg_sti_host(psg_plan* plan, const void* iq_host, int64_t iq_host_elems,
  *       (two-phase path through an HBM scratch, 8192..65536), "cluster_ldg" / "cluster" / "cluster_dsmem" (one CTA
  *       per 4096-point row), "whole" (four-pass whole-frame kernels: 8192 / 16384 in one CTA, 32768 / 65536 on
  *       clusters of 2 / 4), "whole_r2", "whole_r4", "whole_s2" / "whole_s8", "whole_f" (16 x 2 x 16 x 2 x 16,
- *       sti_whole16.cuh); "bluestein" / "bluestein_r2" for non powers of two
+ *       sti_whole16.cuh); "bluestein" / "bluestein_r2" for non powers of two; "mixed_rt" (the run-time mixed-radix
+ *       kernel where a compile-time plan, sti_mixct.cuh, is the default)
  *   psg_debug_set_split_scratch   bytes of scratch per chunk of the split path (default cap 2 GiB)
  *   psg_debug_set_host_chunk      psg_sti_host streams spans above this many bytes in column chunks (default 1 GiB)
  *   psg_debug_set_mode_r_multi    0: one-frame-per-column launches use the one-column-per-CTA kernels

@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 # translation units (compiled in parallel, linked into one library); every header is a dependency of both
-UNITS = ["psg_b200.cu", "psg_r32.cu"]
-DEPS = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))] + [
+UNITS = ["psg_b200.cu", "psg_r32.cu", "psg_mixct.cu"]
+DEPS = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h", ".inc"))] + [
     os.path.join(HERE, "..", "include", "psg_b200.h")]
 OUT = os.path.join(HERE, "libpsgb200.so")
 OBJ_DIR = os.path.join(HERE, "build")
@@ -38,9 +38,12 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in DEPS if os.path.exists(d))
 
 
-# headers only psg_r32.cu includes (editing them does not rebuild the big unit)
-R32_ONLY = ("sti_r32.cuh", "r32_math.cuh")
-R32_HDRS = ("psg_r32.h", "sti_r32.cuh", "r32_math.cuh", "sti_common.cuh", "cplx.cuh")
+# headers only the small units include (editing them does not rebuild the big unit), and what each small unit sees
+SMALL_ONLY = ("sti_r32.cuh", "r32_math.cuh", "sti_mixct.cuh", "mixct_plans.inc")
+UNIT_HDRS = {
+    "psg_r32.cu": ("psg_r32.h", "sti_r32.cuh", "r32_math.cuh", "sti_common.cuh", "cplx.cuh"),
+    "psg_mixct.cu": ("psg_mixct.h", "sti_mixct.cuh", "mixct_plans.inc", "sti_common.cuh", "cplx.cuh"),
+}
 
 
 def _unit_stale(src: str, obj: str) -> bool:
@@ -48,10 +51,10 @@ def _unit_stale(src: str, obj: str) -> bool:
         return True
     t = os.path.getmtime(obj)
     hdrs = [d for d in DEPS if not d.endswith(".cu")]
-    if os.path.basename(src) == "psg_r32.cu":
-        hdrs = [d for d in hdrs if os.path.basename(d) in R32_HDRS]
+    if os.path.basename(src) in UNIT_HDRS:
+        hdrs = [d for d in hdrs if os.path.basename(d) in UNIT_HDRS[os.path.basename(src)]]
     else:
-        hdrs = [d for d in hdrs if os.path.basename(d) not in R32_ONLY]
+        hdrs = [d for d in hdrs if os.path.basename(d) not in SMALL_ONLY]
     return any(os.path.getmtime(d) > t for d in [src, *hdrs] if os.path.exists(d))
 
 

@@ -23,6 +23,7 @@
 #include "sti_whole16.cuh"
 #include "sti_bluestein.cuh"
 #include "psg_r32.h"
+#include "psg_mixct.h"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -376,7 +377,8 @@ extern "C" int psg_debug_set_variant(const char* name) {
         bool ok = g_variant_override == "split" || g_variant_override == "cluster" || g_variant_override == "cluster_ldg" ||
                   g_variant_override == "cluster_dsmem" || g_variant_override == "whole" || g_variant_override == "whole_s2" ||
                   g_variant_override == "whole_s8" || g_variant_override == "whole_f" || g_variant_override == "whole_r2" || g_variant_override == "whole_r4" ||
-                  g_variant_override == "bluestein_r2" || g_variant_override == "bluestein" || g_variant_override == "r32";
+                  g_variant_override == "bluestein_r2" || g_variant_override == "bluestein" || g_variant_override == "r32" ||
+                  g_variant_override == "mixed_rt";
         for (int i = 0; i < g_nvariants; ++i) ok = ok || g_variant_override == g_variants[i].name;
         if (!ok) {
             g_variant_override.clear();
@@ -1379,8 +1381,58 @@ static int run_split(psg_plan* p, StiArgs a, int ncs, int frames_per_col, cudaSt
 }
 
 // nfft = 2^a 3^b 5^c: direct mixed-radix transform in shared memory (sti_mixed_kernel)
+// Round lengths with a compile-time plan (sti_mixct.cuh, mixct_plans.inc): same work split, kernel from psg_mixct.cu
+static int run_mixct(psg_plan* p, StiArgs a, int ncs, int frames_per_col, const MixctInfo& mi, cudaStream_t st) {
+    const int N = p->nfft;
+    if (mi.occ < 1) return fail(PSG_ERR_CUDA, "mixed-radix kernel (nfft=%d) does not fit on an SM", N);
+    const long long slots = (long long)p->sms * mi.occ;
+    // items: at most ~1024 frames each; enough of them to fill the resident CTAs a few times over while a CTA's
+    // groups still have several frames each
+    int nsplit = std::max(1, (frames_per_col + 1023) / 1024);
+    if ((long long)ncs * nsplit < 4 * slots)
+        nsplit = (int)std::max<long long>(nsplit, std::min<long long>(std::max(1, frames_per_col / (8 * mi.groups)), (4 * slots + ncs - 1) / ncs));
+    const int chunk = (frames_per_col + nsplit - 1) / nsplit;
+    nsplit = (frames_per_col + chunk - 1) / chunk;
+    a.gpc = 1;
+    a.chunk = chunk;
+    a.nsplit = nsplit;
+    if (nsplit > 1) {
+        size_t have_b = p->partial_elems * sizeof(float);
+        int rc = ensure_buffer((void**)&p->d_partial, &have_b, (size_t)ncs * nsplit * N * sizeof(float));
+        p->partial_elems = have_b / sizeof(float);
+        if (rc) return rc;
+        a.partial = p->d_partial;
+    }
+    const long long items = (long long)ncs * nsplit;
+    const long long grid = std::min<long long>(items, slots);
+    a.tw = p->d_tw;
+    const int e = psg_mixct_launch(N, a.iq_type, frames_per_col, a, grid, st);
+    if (e) return fail(PSG_ERR_CUDA, "mixed-radix kernel launch (nfft=%d): %s", N, cudaGetErrorString((cudaError_t)e));
+    g_launches++;
+    if (nsplit > 1) {
+        const size_t total = (size_t)ncs * N;
+        const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)p->sms * 16);
+        sti_finalize_kernel<<<blocks, 256, 0, st>>>(a.partial, nsplit, N, (size_t)ncs, a.scale, a.eps, a.out_lin, a.out_db);
+        g_launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    snprintf(p->variant_name, sizeof(p->variant_name), "%s", mi.name);
+    return PSG_OK;
+}
+
 static int run_mixed(psg_plan* p, StiArgs a, int ncs, int frames_per_col, cudaStream_t st) {
     const int N = p->nfft;
+    {
+        bool force_rt = false;
+        {
+            std::lock_guard<NoMutex> lk(g_variant_mu);
+            force_rt = g_variant_override == "mixed_rt";
+        }
+        MixctInfo mi;
+        if (!force_rt && psg_mixct_query(N, a.iq_type, frames_per_col, &mi) == (int)cudaSuccess)
+            return run_mixct(p, a, ncs, frames_per_col, mi, st);
+        cudaGetLastError();
+    }
     const int tpf = std::min(512, std::max(32, ((N / 8 + 31) / 32) * 32));
     const size_t group_bytes = (size_t)((psg_pad(N) + 3) & ~1) * 8 + (size_t)((N + 3) & ~3) * 4;
     int groups = std::max(1, (N >= 4096 ? 512 : 256) / tpf);

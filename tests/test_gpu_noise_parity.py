@@ -90,6 +90,48 @@ def test_non_power_of_two_per_bin_on_noise(torch, nfft, mode):
     _assert_noise_like(got, gdb, _oracle(x, starts, nfft, nfr, nfft), f"nfft={nfft} mode {mode} {variant}")
 
 
+MIXCT_LENGTHS = [1000, 1200, 1500, 2000, 2400, 3000, 3600, 4000, 4800, 5000, 6000, 8000, 10000]
+
+
+@pytest.mark.parametrize("nfft", MIXCT_LENGTHS)
+@pytest.mark.parametrize("case", ["R", "A", "S", "long", "int16_strided"])
+def test_compile_time_mixed_radix_plans(torch, nfft, case):
+    """Round lengths with a compile-time plan (sti_mixct.cuh: prime-factor butterflies 6 / 10 / 12 / 15 / 20,
+    register-resident twiddles / window / accumulators): per-bin bar on noise against the float64 oracle in Modes
+    R / A / S, long columns split over CTAs (partial sums + finalize, several frame groups per CTA), integer
+    samples in an interleaved two-sub-channel layout -- and agreement with the run-time mixed-radix kernel."""
+    from pyspectrogram_b200 import engine
+    rng = np.random.default_rng(nfft * 11 + len(case))
+    nfr, hop, ncol = {"R": (1, nfft, 9), "A": (5, nfft, 7), "S": (4, nfft - nfft // 8, 6), "long": (301, nfft, 2),
+                      "int16_strided": (3, nfft, 5)}[case]
+    span = (nfr - 1) * hop + nfft
+    n = ncol * span + 8
+    starts = (np.arange(ncol) * span + np.arange(ncol) % 2).astype(np.int64)
+    plan = engine.StiPlan(nfft)
+    if case == "int16_strided":
+        raw = rng.integers(-3000, 3000, size=(n, 2, 2)).astype(np.int16)  # [sample][sub][re, im]
+        x = (raw[:, 1, 0].astype(np.float64) + 1j * raw[:, 1, 1].astype(np.float64)) / 32768.0
+        lin, db = plan.run(torch.from_numpy(raw).cuda(), torch.from_numpy(starts * 2).cuda(), nfr, hop, sample_stride=2,
+                           sub_stride=1, nsub=2, in_scale=1.0 / 32768.0, want_lin=True, want_db=True)
+        got, gdb = lin.cpu().numpy()[1], db.cpu().numpy()[1]
+    else:
+        x = _noise(rng, n)
+        xd = torch.from_numpy(x).cuda()
+        lin, db = plan.run(xd, torch.from_numpy(starts).cuda(), nfr, hop, want_lin=True, want_db=True)
+        got, gdb = lin.cpu().numpy()[0], db.cpu().numpy()[0]
+    assert plan.variant.startswith(f"mixct{nfft}_"), plan.variant
+    _assert_noise_like(got, gdb, _oracle(x, starts, nfft, nfr, hop), f"nfft={nfft} {case} {plan.variant}")
+    if case in ("A", "long"):
+        try:
+            engine.set_variant("mixed_rt")
+            lin_rt, _ = plan.run(xd, torch.from_numpy(starts).cuda(), nfr, hop)
+            assert plan.variant.startswith(f"mixed{nfft}_"), plan.variant
+        finally:
+            engine.set_variant(None)
+        e = psd_errors(got.T, lin_rt.cpu().numpy()[0].T.astype(np.float64))
+        assert e["col"] <= 2e-6 and e["bin_p999"] <= 1e-5, (nfft, case, e)
+
+
 # ---------------------------------------------------------------------------------------------
 # the persistent frame pipeline of the radix-32 kernels (sti_r32.cuh)
 # ---------------------------------------------------------------------------------------------

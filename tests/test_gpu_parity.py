@@ -108,7 +108,7 @@ def test_arbitrary_nfft_against_float64_oracle(torch, nfft, mode):
         while smooth % f == 0:
             smooth //= f
     if smooth == 1 and nfft <= 15000:
-        assert plan.variant.startswith(f"mixed{nfft}_"), plan.variant
+        assert plan.variant.startswith((f"mixed{nfft}_", f"mixct{nfft}_")), plan.variant
     else:
         assert plan.variant.startswith("bluestein")
         assert plan.variant.endswith("_r2") == (2 * nfft - 1 > 16384), plan.variant
@@ -130,7 +130,7 @@ def test_arbitrary_nfft_kernels_agree(torch, nfft, nfr, ncol):
     plan = engine.StiPlan(nfft)
     res = {}
     try:
-        for var, want in ((None, "mixed"), ("bluestein", "bluestein_m"), ("bluestein_r2", "bluestein_m")):
+        for var, want in ((None, ("mixed", "mixct")), ("mixed_rt", "mixed"), ("bluestein", "bluestein_m"), ("bluestein_r2", "bluestein_m")):
             engine.set_variant(var)
             lin, _ = plan.run(x, starts, nfr, nfft)
             torch.cuda.synchronize()
@@ -535,9 +535,10 @@ def test_drop_in_accepts_raw_iq_and_processor_raw_ingest(dp):
     # without the keyword a plain integer array is REAL samples, as for the reference (scipy casts it): the
     # (rows, ntime, 2) array above is two real sub-channels, float64 out (drfProc.py:387-396)
     from oracle import ref_port
-    f4, s4, m4 = dp.sti_proc_data(plain, 1.0e6, nfft)
-    f5, s5, m5 = ref_port.sti_mode_r(plain, 1.0e6, nfft)
-    assert s4.shape == s5.shape == (nfft, ntime, 2) and s4.dtype == s5.dtype
+    real2 = np.ascontiguousarray(plain[:, :, 0, :])
+    f4, s4, m4 = dp.sti_proc_data(real2, 1.0e6, nfft)
+    f5, s5, m5 = ref_port.sti_mode_r(real2, 1.0e6, nfft)
+    assert s4.shape == s5.shape == (nfft, ntime, 2) and s4.dtype.kind == "f"  # (scipy's own result dtype for int16 input varies with its version)
     assert_psd_close(s4, s5, noise_like=False, what="plain int array = real samples")
     # the plot-data entry takes the raw forms too (same dispatch)
     pf_a, sx_a, md_a = dp.sti_plot_data(raw, 1.0e6, nfft, (-200.0, 200.0), ref=ref)
@@ -577,6 +578,14 @@ def test_mode_r_multi_column_kernels_match_single_column_kernels(torch, nfft):
         name_s = plan.variant
     finally:
         _lib.check(_lib.load().psg_debug_set_mode_r_multi(1))
+    if name_m.startswith("r32_"):
+        # 8192 points, one frame per column: the persistent radix-32 kernel is the default (its frame pipeline runs
+        # across columns by construction); a different transform, so agreement within the parity tolerance
+        assert nfft == 8192 and name_s.startswith("tma13_"), (name_m, name_s)
+        a, b = lin_m[0].double(), lin_s[0].double()
+        assert float(((a - b).abs().amax(dim=1) / b.amax(dim=1)).max()) <= 2e-6
+        assert float((db_m - db_s).abs().max()) <= 1e-3
+        return
     # small nfft packs many columns into one CTA already: too few column blocks here to batch further
     assert name_m == name_s + "_m" or (nfft < 1024 and name_m == name_s), (name_m, name_s)
     assert torch.equal(lin_m, lin_s) and torch.equal(db_m, db_s)
