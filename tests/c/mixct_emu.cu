@@ -88,8 +88,9 @@ static double check_plan() {
     return err / nrm;
 }
 
-#define MIXCT_PLAN(N, R0, R1, R2, R3, T, PQ, PA, TWREG, FD) \
-    { const double e = check_plan<MixPlan<N, R0, R1, R2, R3, T, PQ, PA, TWREG>>(); printf("plan %6d %2dx%2dx%2dx%2d  err/peak %.2e\n", N, R0, R1, R2, R3, e); bad |= !(e < 3e-6); }
+#define MIXCT_ALT(ID, N, R0, R1, R2, R3, T, PQ, PA, TW, FD, MINB) MIXCT_PLAN(N, R0, R1, R2, R3, T, PQ, PA, TW, FD, MINB)
+#define MIXCT_PLAN(N, R0, R1, R2, R3, T, PQ, PA, TW, FD, MINB) \
+    { const double e = check_plan<MixPlan<N, R0, R1, R2, R3, T, PQ, PA, TW>>(); printf("plan %6d %2dx%2dx%2dx%2d  err/peak %.2e\n", N, R0, R1, R2, R3, e); bad |= !(e < 3e-6); }
 
 int main() {
     int bad = 0;

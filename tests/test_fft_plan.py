@@ -246,3 +246,25 @@ def test_r32_kernels_replayed_on_the_cpu(tmp_path):
                    check=True, capture_output=True)
     res = subprocess.run([exe], capture_output=True, text=True)
     assert res.returncode == 0 and res.stdout.strip().endswith("OK"), res.stdout + res.stderr
+
+
+# ---------------------------------------------------------------------------------------------
+# compile-time mixed-radix plans for round lengths (sti_mixct.cuh): CPU replay with the kernel's own header
+# ---------------------------------------------------------------------------------------------
+def test_mixct_plans_replayed_on_the_cpu(tmp_path):
+    """tests/c/mixct_emu.cu includes csrc/sti_mixct.cuh and csrc/mixct_plans.inc: the prime-factor butterflies
+    (6 / 10 / 12 / 15 / 20 from 2 / 3 / 4 / 5-point DFTs) against a float64 DFT, and for every plan of the list the
+    whole pass structure -- index algebra, twiddles (register form and rebuilt from powers), padded addresses, the
+    position -> frequency permutation of the epilogue -- against a float64 DFT of the same input."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = str(tmp_path / "mixct_emu")
+    subprocess.run([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-I", os.path.join(here, "..", "pyspectrogram_b200", "csrc"),
+                    "-o", exe, os.path.join(here, "c", "mixct_emu.cu")], check=True, capture_output=True)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0 and res.stdout.strip().endswith("ALL OK"), res.stdout + res.stderr
+    assert res.stdout.count("plan ") >= 13

@@ -584,7 +584,8 @@ def test_mode_r_multi_column_kernels_match_single_column_kernels(torch, nfft):
         assert nfft == 8192 and name_s.startswith("tma13_"), (name_m, name_s)
         a, b = lin_m[0].double(), lin_s[0].double()
         assert float(((a - b).abs().amax(dim=1) / b.amax(dim=1)).max()) <= 2e-6
-        assert float((db_m - db_s).abs().max()) <= 1e-3
+        strong = lin_s[0] >= lin_s[0].amax(dim=1, keepdim=True) * 1e-6  # bins within 60 dB of the column peak (tests/parity.py)
+        assert float((db_m[0] - db_s[0]).abs()[strong].max()) <= 1e-3
         return
     # small nfft packs many columns into one CTA already: too few column blocks here to batch further
     assert name_m == name_s + "_m" or (nfft < 1024 and name_m == name_s), (name_m, name_s)
