@@ -89,13 +89,13 @@ PSG_HD void mx_dft(cf* v) {
 
 // ---- plan -------------------------------------------------------------------------------------------------------
 // padded address of pos: pos + PA * (pos / PQ)  (PQ = 0: no padding)
-// TW_: 0 = twiddles rebuilt per frame from W^(2^q) loaded from the L1-resident table, 1 = all twiddles in registers,
-//      2 = LEAN: as 0, and neither the next frame's samples nor the window are kept in registers (the large plans:
-//      a radix-20 butterfly alone is 40 registers)
+// TW_: 0 = twiddles rebuilt per frame from W^(2^q) loaded from the L1-resident table, 1 = all twiddles in registers.
+// (A third form that kept neither the next frame's samples nor the window in registers -- no spills on the radix-20
+// plans -- measured 20 % slower than spilling: the exposed load latency costs more.  Removed.)
 template <int N_, int R0_, int R1_, int R2_, int R3_, int T_, int PQ_, int PA_, int TW_>
 struct MixPlan {
     static constexpr int N = N_, T = T_, PQ = PQ_, PA = PA_;
-    static constexpr bool TWREG = TW_ == 1, LEAN = TW_ == 2;
+    static constexpr bool TWREG = TW_ == 1;
     static constexpr int P = 2 + (R2_ > 1) + (R3_ > 1);
     static_assert(R0_ * R1_ * R2_ * R3_ == N_ && R1_ > 1 && (R3_ == 1 || R2_ > 1), "radices multiply to N; at least two passes");
     __host__ __device__ static constexpr int r(int p) { return p == 0 ? R0_ : p == 1 ? R1_ : p == 2 ? R2_ : R3_; }
@@ -209,17 +209,14 @@ __global__ void __launch_bounds__(F * PL::T, MINB) sti_mixct_kernel(const StiArg
     float2* const buf = mx_smem + (size_t)g * PL::BUF;
 
     // ---- loop-invariant per-thread tables: window, twiddles ----
-    constexpr bool LEAN = PL::LEAN;
-    float win[LEAN ? 1 : NB0 * R0];
-    if constexpr (!LEAN) {
+    float win[NB0 * R0];
 #pragma unroll
-        for (int i = 0; i < NB0; ++i)
+    for (int i = 0; i < NB0; ++i)
 #pragma unroll
-            for (int n = 0; n < R0; ++n) {
-                const int bf = t + i * T;
-                win[i * R0 + n] = (bf < S0) ? __ldg(a.win + bf + n * S0) : 0.f;
-            }
-    }
+        for (int n = 0; n < R0; ++n) {
+            const int bf = t + i * T;
+            win[i * R0 + n] = (bf < S0) ? __ldg(a.win + bf + n * S0) : 0.f;
+        }
     cf twr[PL::TWREG ? PL::NTW : 1];
     if constexpr (PL::TWREG) {
         mx_load_tw<PL, 0>(twr, t, a.tw);
@@ -238,8 +235,8 @@ __global__ void __launch_bounds__(F * PL::T, MINB) sti_mixct_kernel(const StiArg
         for (int i = 0; i < NBL * RL; ++i) acc[i] = 0.f;
         const int niter = (k1 - k0 + F - 1) / F;
         // samples of this thread's pass-0 butterflies of frame k (zeros for a group without a frame)
-        cf nx[LEAN ? 1 : NB0 * R0];
-        auto load_samples = [&](int k, cf* dst) {
+        cf nx[NB0 * R0];
+        auto load_frame = [&](int k) {
             const bool live = k < k1;
             const long long src = src0 + (long long)k * a.hop_elems;
 #pragma unroll
@@ -247,31 +244,16 @@ __global__ void __launch_bounds__(F * PL::T, MINB) sti_mixct_kernel(const StiArg
 #pragma unroll
                 for (int n = 0; n < R0; ++n) {
                     const int bf = t + i * T;
-                    dst[i * R0 + n] = (live && bf < S0) ? ldg_iq<IQT>(a.iq, src + (long long)(bf + n * S0) * a.sample_stride)
-                                                         : make_float2(0.f, 0.f);
+                    nx[i * R0 + n] = (live && bf < S0) ? ldg_iq<IQT>(a.iq, src + (long long)(bf + n * S0) * a.sample_stride)
+                                                        : make_float2(0.f, 0.f);
                 }
-        };
-        auto load_frame = [&](int k) {
-            if constexpr (!LEAN) load_samples(k, nx);
         };
         load_frame(k0 + g);
         for (int j = 0; j < niter; ++j) {
             // ---- pass 0: window, R0-point DFT, twiddle, store ----
             cf x[NB0 * R0];
-            if constexpr (LEAN) {
-                load_samples(k0 + j * F + g, x);
 #pragma unroll
-                for (int i = 0; i < NB0; ++i)
-#pragma unroll
-                    for (int n = 0; n < R0; ++n) {
-                        const int bf = t + i * T;
-                        const float w = (bf < S0) ? __ldg(a.win + bf + n * S0) : 0.f;
-                        x[i * R0 + n] = mul2(x[i * R0 + n], make_float2(w, w));
-                    }
-            } else {
-#pragma unroll
-                for (int i = 0; i < NB0 * R0; ++i) x[i] = mul2(nx[i], make_float2(win[i], win[i]));
-            }
+            for (int i = 0; i < NB0 * R0; ++i) x[i] = mul2(nx[i], make_float2(win[i], win[i]));
             if constexpr (P == 2) load_frame(k0 + (j + 1) * F + g);
             __syncthreads();  // the previous frame's last pass is done reading the buffer
 #pragma unroll
