@@ -581,16 +581,23 @@ extern "C" int psg_plan_create(psg_plan** out, int nfft, int window_kind, double
     if (logn < 0) {
         rc = build_bluestein(p);
         if (rc) { psg_plan_destroy(p); return rc; }
-        // 2^a 3^b 5^c that fits shared memory: radix plan of the direct transform (power-of-two part first)
-        int rem = nfft, a2 = 0, n3 = 0, n5 = 0;
+        // 2^a 3^b 5^c 7^d 11^e 13^f that fits shared memory: radix plan of the direct transform (power-of-two part
+        // first, then the primes from the largest down)
+        int rem = nfft, a2 = 0, n3 = 0, n5 = 0, n7 = 0, n11 = 0, n13 = 0;
         while (rem % 2 == 0) { rem /= 2; ++a2; }
         while (rem % 3 == 0) { rem /= 3; ++n3; }
         while (rem % 5 == 0) { rem /= 5; ++n5; }
-        const int np = (a2 % 4 ? 1 : 0) + a2 / 4 + n3 + n5;
+        while (rem % 7 == 0) { rem /= 7; ++n7; }
+        while (rem % 11 == 0) { rem /= 11; ++n11; }
+        while (rem % 13 == 0) { rem /= 13; ++n13; }
+        const int np = (a2 % 4 ? 1 : 0) + a2 / 4 + n3 + n5 + n7 + n11 + n13;
         if (rem == 1 && np <= 10 && (size_t)(psg_pad(nfft) + 4) * 8 + (size_t)(nfft + 4) * 4 <= 200 * 1024) {
             int k = 0;
             if (a2 % 4) p->mx_radix[k++] = 1 << (a2 % 4);
             for (int i = 0; i < a2 / 4; ++i) p->mx_radix[k++] = 16;
+            for (int i = 0; i < n13; ++i) p->mx_radix[k++] = 13;
+            for (int i = 0; i < n11; ++i) p->mx_radix[k++] = 11;
+            for (int i = 0; i < n7; ++i) p->mx_radix[k++] = 7;
             for (int i = 0; i < n5; ++i) p->mx_radix[k++] = 5;
             for (int i = 0; i < n3; ++i) p->mx_radix[k++] = 3;
             p->mx_npass = k;

@@ -222,10 +222,76 @@ PSG_DEV void dft5(cf* a) {
     a[2] = cadd(m2, mul_nj(n2));
     a[3] = csub(m2, mul_nj(n2));
 }
+// Odd prime radices 7, 11, 13 (round 2: lengths such as 1001, 1400, 7000, 9100 leave the Bluestein kernels):
+// X[k] = a0 + sum_j (a_j + a_{P-j}) cos(2 pi j k / P) - i sum_j (a_j - a_{P-j}) sin(2 pi j k / P), X[P-k] its mirror:
+// (P-1)^2 / 2 packed multiply-adds, no recursion.  cos / sin tables indexed by (j k) mod P fold to immediates.
+template <int P>
+struct PrimeTab;
+template <>
+struct PrimeTab<7> {
+    static __device__ __forceinline__ float c(int m) {
+        constexpr float t[7] = {1.0f, 0.623489802f, -0.222520934f, -0.900968868f, -0.900968868f, -0.222520934f, 0.623489802f};
+        return t[m];
+    }
+    static __device__ __forceinline__ float s(int m) {
+        constexpr float t[7] = {0.0f, 0.781831482f, 0.974927912f, 0.433883739f, -0.433883739f, -0.974927912f, -0.781831482f};
+        return t[m];
+    }
+};
+template <>
+struct PrimeTab<11> {
+    static __device__ __forceinline__ float c(int m) {
+        constexpr float t[11] = {1.0f, 0.841253533f, 0.415415013f, -0.142314838f, -0.654860734f, -0.959492974f, -0.959492974f, -0.654860734f, -0.142314838f, 0.415415013f, 0.841253533f};
+        return t[m];
+    }
+    static __device__ __forceinline__ float s(int m) {
+        constexpr float t[11] = {0.0f, 0.540640817f, 0.909631995f, 0.989821442f, 0.755749574f, 0.281732557f, -0.281732557f, -0.755749574f, -0.989821442f, -0.909631995f, -0.540640817f};
+        return t[m];
+    }
+};
+template <>
+struct PrimeTab<13> {
+    static __device__ __forceinline__ float c(int m) {
+        constexpr float t[13] = {1.0f, 0.885456026f, 0.568064747f, 0.12053668f, -0.354604887f, -0.748510748f, -0.970941817f, -0.970941817f, -0.748510748f, -0.354604887f, 0.12053668f, 0.568064747f, 0.885456026f};
+        return t[m];
+    }
+    static __device__ __forceinline__ float s(int m) {
+        constexpr float t[13] = {0.0f, 0.464723172f, 0.822983866f, 0.992708874f, 0.935016243f, 0.663122658f, 0.239315664f, -0.239315664f, -0.663122658f, -0.935016243f, -0.992708874f, -0.822983866f, -0.464723172f};
+        return t[m];
+    }
+};
+template <int P>
+PSG_DEV void dft_oddprime(cf* a) {
+    constexpr int H = (P - 1) / 2;
+    cf sm[H], df[H];
+#pragma unroll
+    for (int j = 1; j <= H; ++j) {
+        sm[j - 1] = cadd(a[j], a[P - j]);
+        df[j - 1] = csub(a[j], a[P - j]);
+    }
+    cf x0 = a[0];
+#pragma unroll
+    for (int j = 0; j < H; ++j) x0 = cadd(x0, sm[j]);
+    const cf a0 = a[0];
+    a[0] = x0;
+#pragma unroll
+    for (int k = 1; k <= H; ++k) {
+        cf A = a0, B = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 1; j <= H; ++j) {
+            const float c = PrimeTab<P>::c((j * k) % P), s = PrimeTab<P>::s((j * k) % P);
+            A = fma2(sm[j - 1], make_float2(c, c), A);
+            B = fma2(df[j - 1], make_float2(s, s), B);
+        }
+        a[k] = cadd(A, mul_nj(B));      // A - i B
+        a[P - k] = csub(A, mul_nj(B));  // A + i B
+    }
+}
 template <int R>
 PSG_DEV void dft_any(cf* v) {
     if constexpr (R == 3) dft3(v);
     else if constexpr (R == 5) dft5(v);
+    else if constexpr (R == 7 || R == 11 || R == 13) dft_oddprime<R>(v);
     else dftR<R>(v);
 }
 
@@ -309,6 +375,9 @@ __global__ void __launch_bounds__(512) sti_mixed_kernel(const StiArgs a, const M
                     case 3: mixed_pass<3>(buf, S, N, Nv, t, T, b.twf, first, last, a, src, accs); break;
                     case 4: mixed_pass<4>(buf, S, N, Nv, t, T, b.twf, first, last, a, src, accs); break;
                     case 5: mixed_pass<5>(buf, S, N, Nv, t, T, b.twf, first, last, a, src, accs); break;
+                    case 7: mixed_pass<7>(buf, S, N, Nv, t, T, b.twf, first, last, a, src, accs); break;
+                    case 11: mixed_pass<11>(buf, S, N, Nv, t, T, b.twf, first, last, a, src, accs); break;
+                    case 13: mixed_pass<13>(buf, S, N, Nv, t, T, b.twf, first, last, a, src, accs); break;
                     case 8: mixed_pass<8>(buf, S, N, Nv, t, T, b.twf, first, last, a, src, accs); break;
                     default: mixed_pass<16>(buf, S, N, Nv, t, T, b.twf, first, last, a, src, accs); break;
                 }

@@ -77,10 +77,11 @@ def test_integer_ingest_twins_per_bin_on_noise(torch, nfft, kind):
     _assert_noise_like(got, gdb, _oracle(x, starts, nfft, nfr, nfft), f"nfft={nfft} {kind} {variant}")
 
 
-@pytest.mark.parametrize("nfft", [96, 1000, 3000, 5000, 10000])
+@pytest.mark.parametrize("nfft", [96, 1000, 1001, 3000, 5000, 7000, 9100, 10000])
 @pytest.mark.parametrize("mode", ["R", "A"])
 def test_non_power_of_two_per_bin_on_noise(torch, nfft, mode):
-    """The lengths people type into the viewer (drfview.py:474-479): direct mixed-radix transforms."""
+    """The lengths people type into the viewer (drfview.py:474-479): direct mixed-radix transforms (compile-time plans,
+    and the run-time kernel with radices 2 ... 16, 3, 5, 7, 11, 13)."""
     rng = np.random.default_rng(nfft * 7 + ord(mode))
     nfr = 1 if mode == "R" else 4
     ncol = 6

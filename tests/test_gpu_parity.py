@@ -87,7 +87,8 @@ def test_non_power_of_two_matches_reference_golden(dp):
     assert_psd_close(med, g["med"], noise_like=False, what="nfft=96 median")
 
 
-@pytest.mark.parametrize("nfft", [3, 5, 7, 33, 100, 1000, 1023, 1025, 3000, 4095, 5000, 8191, 10000, 12000, 15000, 20000, 100000])
+@pytest.mark.parametrize("nfft", [3, 5, 7, 33, 100, 169, 1000, 1001, 1023, 1025, 3000, 4004, 4095, 5000, 7000, 8191, 10000, 12000, 15000,
+                                  20000, 100000])
 @pytest.mark.parametrize("mode", ["R", "A"])
 def test_arbitrary_nfft_against_float64_oracle(torch, nfft, mode):
     """Odd, even, prime and large non power-of-two lengths (work buffer in shared memory up to
@@ -101,10 +102,10 @@ def test_arbitrary_nfft_against_float64_oracle(torch, nfft, mode):
     starts = (np.arange(ncol) * nfft * nfr + np.arange(ncol) % 2).astype(np.int64)
     plan = engine.StiPlan(nfft)
     lin, db = plan.run(torch.from_numpy(x).cuda(), torch.from_numpy(starts).cuda(), nfr, nfft, want_lin=True, want_db=True)
-    # 2^a 3^b 5^c that fit shared memory run the direct mixed-radix transform; the rest Bluestein: convolution
-    # lengths up to 16384 with mixed-radix passes, longer ones with the radix-2 kernel
+    # 2^a 3^b 5^c 7^d 11^e 13^f that fit shared memory run the direct mixed-radix transform; the rest Bluestein:
+    # convolution lengths up to 16384 with mixed-radix passes, longer ones with the radix-2 kernel
     smooth = nfft
-    for f in (2, 3, 5):
+    for f in (2, 3, 5, 7, 11, 13):
         while smooth % f == 0:
             smooth //= f
     if smooth == 1 and nfft <= 15000:
@@ -118,7 +119,8 @@ def test_arbitrary_nfft_against_float64_oracle(torch, nfft, mode):
                     ref_lin=ref.T, what=f"nfft={nfft} dB")
 
 
-@pytest.mark.parametrize("nfft,nfr,ncol", [(1000, 700, 2), (96, 5, 300), (6000, 2, 3), (45, 9, 40), (7500, 3, 5)])
+@pytest.mark.parametrize("nfft,nfr,ncol", [(1000, 700, 2), (96, 5, 300), (6000, 2, 3), (45, 9, 40), (7500, 3, 5), (1001, 4, 9), (7000, 2, 3),
+                                           (77, 6, 50)])
 def test_arbitrary_nfft_kernels_agree(torch, nfft, nfr, ncol):
     """The three kernels for non powers of two on the same input: direct mixed-radix transform (default for
     2^a 3^b 5^c), Bluestein with mixed-radix passes ("bluestein"), Bluestein radix 2 ("bluestein_r2"),
