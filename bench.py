@@ -596,9 +596,20 @@ def other_configs(torch, engine, pdist, dist, dev, rank, world, peak, args):
         def med_fn(im):
             return plan.median(im.contiguous(), want_lin=False, want_db=True)
 
-        def median():
+        reshard = pdist.FreqReshard(ncols, nfft, device=dev) if (resharded and not args.no_peer) else None
+        reshard_check = None
+        if resharded and reshard is not None and reshard.available:
+            # the peer-memory exchange against the NCCL exchange on the same slab: bit-identical median rows
+            plan.run(iq, starts, nint, nfft, want_lin=True, want_db=False, out_lin=lin)
+            a = pdist.median_over_time_sharded(lin[0], ncols, med_fn, dst=0, reshard=reshard)
+            b = pdist.median_over_time_sharded(lin[0], ncols, med_fn, dst=0)
+            torch.cuda.synchronize()
+            if rank == 0:
+                reshard_check = bool(all(torch.equal(x, y) for x, y in zip(a, b) if x is not None))
+
+        def median(lin=lin):
             if resharded:  # the median needs every time bin of a frequency row: re-shard by frequency (dist.py)
-                pdist.median_over_time_sharded(lin[0], ncols, med_fn, dst=0)
+                pdist.median_over_time_sharded(lin[0], ncols, med_fn, dst=0, reshard=reshard)
             else:
                 plan.median(lin, want_lin=False, want_db=True)
 
@@ -633,8 +644,11 @@ def other_configs(torch, engine, pdist, dist, dev, rank, world, peak, args):
                                "image over NVLink and gather_ms is the publishing barrier, 'gather': NCCL gather of the slabs" + ("; median re-sharded by frequency (the path's one exchange)"
                                                                      if resharded else "")})
         d["columns_per_rank"] = my_cols
+        if resharded:
+            d["median_exchange"] = "peer memory (dist.FreqReshard)" if (reshard is not None and reshard.available) else "NCCL send/recv"
+            d["median_exchange_bit_identical_to_nccl"] = reshard_check
         out[f"{name}_n{world}"] = d
-        del iq, lin, db, plan, img
+        del iq, lin, db, plan, img, reshard
         torch.cuda.empty_cache()
     return out
 

@@ -92,6 +92,12 @@ class PeerImage:
     else runs, nothing is copied twice.  ``publish()`` orders the writes before the root's reads (a barrier on the
     symmetric-memory signal pads, on the current stream).
 
+    (Measured alternative for large slabs, removed: a local slab pushed into the root's image with one
+    ``cudaMemcpyAsync`` per rank -- the copy engines take no SM from the kernels -- costs 0.33 ms per 236 MB slab at two
+    GPUs where the fused stores cost 0.01 ms, and issued on a side stream under the next step's persistent radix-32
+    kernel its barrier kernel waits for that kernel to retire: 9.85 against 8.20 ms per cfg3 step,
+    ``profiles/r02_assembly_copy_engine_experiment.txt``.)
+
     Falls back to a local slab + ``gather_columns`` when symmetric memory is unavailable (gloo, one rank, no P2P):
     ``rows`` is then the local slab and ``publish()`` performs the gather.  ``image`` is the assembled tensor on
     ``dst`` (``None`` elsewhere; in the fallback it is valid after ``publish()``)."""
@@ -144,7 +150,59 @@ class PeerImage:
         return self.image
 
 
-def median_over_time_sharded(local, ncols_per_rank, median_fn, dst=0, group=None):
+class FreqReshard:
+    """Re-sharding of a time-sharded image by frequency over peer memory (the exchange of ``median_over_time_sharded``).
+
+    Every rank owns a symmetric ``[ntime][nfft / world]`` slab; ``exchange(local)`` writes this rank's columns' bins
+    ``shard_range(nfft, s, world)`` straight into rows ``[off_r, off_r + ncol_r)`` of rank ``s``'s slab -- strided
+    copy kernels whose stores cross NVLink, no staging copy, no NCCL send / receive pair per peer -- between two
+    barriers on the signal pads ("the slabs of the previous call have been read" / "every block has landed").
+    Needs ``nfft % world == 0`` and symmetric memory; ``available`` is False otherwise (the NCCL exchange is used)."""
+
+    def __init__(self, ncols_per_rank, nfft, dtype=None, device=None, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.ncols = list(ncols_per_rank)
+        self.nfft = int(nfft)
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.available = False
+        dtype = dtype or torch.float32
+        if self.world < 2 or device is None or torch.device(device).type != "cuda":
+            return
+        ok_local = self.nfft % self.world == 0
+        self.width = self.nfft // self.world
+        ntime = sum(self.ncols)
+        if ok_local:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                buf = symm_mem.empty(ntime, self.width, dtype=dtype, device=device)
+                self._hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+                self.slab = buf
+                self._peers = [self._hdl.get_buffer(s, (ntime, self.width), dtype) for s in range(self.world)]
+            except Exception as exc:
+                self._why = str(exc)
+                ok_local = False
+        ok = torch.tensor([1 if ok_local else 0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        self.available = bool(int(ok[0]))
+
+    def exchange(self, local):
+        """``local``: this rank's ``[ncol_r][nfft]`` slab.  Returns this rank's ``[ntime][nfft / world]`` slab, complete
+        when the current stream has passed this call."""
+        off = sum(self.ncols[: self.rank])
+        n = self.ncols[self.rank]
+        self._hdl.barrier(channel=0)  # every rank is done reading the slabs of the previous exchange
+        if n:
+            for k in range(self.world):  # staggered destinations: no two ranks start on the same peer
+                s = (self.rank + k) % self.world
+                self._peers[s][off: off + n].copy_(local[:, s * self.width: (s + 1) * self.width])
+        self._hdl.barrier(channel=1)  # every block has landed
+        return self.slab
+
+
+def median_over_time_sharded(local, ncols_per_rank, median_fn, dst=0, group=None, reshard=None):
     """Time-median of an image whose COLUMNS (time bins) are sharded over the ranks (BASELINE config 4).
 
     ``np.median(sxx, axis=1)`` (drfProc.py:401) needs every time bin of a frequency row.  Gathering the
@@ -156,6 +214,9 @@ def median_over_time_sharded(local, ncols_per_rank, median_fn, dst=0, group=None
     order -- runs ``median_fn`` on its ``[ntime][nfft / world]`` slab, and the median slabs are
     gathered on ``dst``.  A median is an order statistic of one frequency row, so the result is
     bit-identical to the median of the assembled image.
+
+    ``reshard``: a ``FreqReshard`` built once for this shape does the exchange over peer memory (no staging copies, no
+    NCCL kernels); without it, or when it is not ``available``, the blocks travel by NCCL ``batch_isend_irecv``.
 
     ``local``: this rank's ``[ncol_local][nfft]`` linear slab.  ``median_fn(img)`` maps a contiguous
     ``[1][ntime][w]`` tensor to a tuple of ``[1][w]`` tensors (e.g. ``StiPlan.median`` returning the
@@ -173,6 +234,9 @@ def median_over_time_sharded(local, ncols_per_rank, median_fn, dst=0, group=None
     f_lo, f_hi = shard_range(nfft, rank, world)
     width = f_hi - f_lo
     ntime = sum(ncols_per_rank)
+    if reshard is not None and reshard.available:
+        slab = reshard.exchange(local)
+        return _finish_sharded_median(slab, ntime, width, nfft, world, rank, median_fn, dst, group)
     slab = torch.empty((ntime, width), dtype=local.dtype, device=local.device)
     ops, keep = [], []
     off = 0
@@ -192,6 +256,10 @@ def median_over_time_sharded(local, ncols_per_rank, median_fn, dst=0, group=None
     if ops:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
+    return _finish_sharded_median(slab, ntime, width, nfft, world, rank, median_fn, dst, group)
+
+
+def _finish_sharded_median(slab, ntime, width, nfft, world, rank, median_fn, dst, group):
     meds = median_fn(slab.reshape(1, ntime, width))
     widths = [shard_range(nfft, r, world)[1] - shard_range(nfft, r, world)[0] for r in range(world)]
     out = []

@@ -104,7 +104,10 @@ def _median_worker(rank, world, port, ncols, nfft, q):
         def median_fn(img):  # [1][ntime][w] -> ([1][w] linear, None)
             return torch.from_numpy(np.median(img.numpy(), axis=1)), None
 
-        res = pdist.median_over_time_sharded(local, ncols, median_fn, dst=0)
+        # a FreqReshard without CUDA peers reports itself unavailable and the NCCL / gloo exchange runs
+        rs = pdist.FreqReshard(ncols, nfft, device="cpu")
+        assert not rs.available
+        res = pdist.median_over_time_sharded(local, ncols, median_fn, dst=0, reshard=rs)
         if rank == 0:
             q.put(bool(np.array_equal(res[0].numpy(), np.median(full, axis=0)) and res[1] is None))
         else:
