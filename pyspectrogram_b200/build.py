@@ -82,10 +82,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError("nvcc failed: " + " ".join(cmd) + "\n" + out)
         if verbose:
             print(out)
-    cmd = [nvcc, *LINK_FLAGS, "-o", OUT, *objs]
+    # link next to the target and rename: a reader (a test run, a snapshot of the tree) never sees a half-written library
+    tmp = OUT + ".tmp"
+    cmd = [nvcc, *LINK_FLAGS, "-o", tmp, *objs]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
+    os.replace(tmp, OUT)
     return OUT
 
 
