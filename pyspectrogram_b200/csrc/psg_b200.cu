@@ -1898,22 +1898,20 @@ extern "C" int psg_median_time(psg_plan* p, const float* img_dev, int nsub, int 
         const size_t row_bytes = (size_t)rowlen * 4, sm_total = 227 * 1024;
         int bpc = 0;
         long long best = 0;
-        for (int cand_b : {8, 4, 6, 5, 3, 2}) {
+        for (int cand_b : {8, 4, 2}) {
             const size_t smem = cand_b * row_bytes;
             if (smem > 220 * 1024) continue;
             const long long ctas = std::min<long long>(32, (long long)(sm_total / (smem + 1024)));
-            // rows of two or three floats read a fraction of every 32-byte sector (neighbouring CTAs share it through
-            // L2): only when that buys clearly more resident warps; ties go to the sector-aligned widths listed first
-            const long long warps = std::min<long long>(64, ctas * cand_b) * (cand_b <= 3 ? 4 : 5);
+            // rows of two floats read a quarter of every 32-byte sector (four CTAs share it through L2): only when
+            // that buys clearly more resident warps.  (3 / 5 / 6 bins per CTA -- 15 instead of 12 warps per SM at 3600
+            // columns -- measured slower: their rows straddle the sectors, profiles/r01_median_kernel_experiment.txt)
+            const long long warps = std::min<long long>(64, ctas * cand_b) * (cand_b == 2 ? 4 : 5);
             if (warps > best) { best = warps; bpc = cand_b; }
         }
         if (bpc && !g_force_generic.load()) {
             const size_t smem = bpc * row_bytes;
-            const void* fn = bpc == 8   ? (const void*)median_select_kernel<8>
-                             : bpc == 6 ? (const void*)median_select_kernel<6>
-                             : bpc == 5 ? (const void*)median_select_kernel<5>
+            const void* fn = bpc == 8 ? (const void*)median_select_kernel<8>
                              : bpc == 4 ? (const void*)median_select_kernel<4>
-                             : bpc == 3 ? (const void*)median_select_kernel<3>
                                         : (const void*)median_select_kernel<2>;
             static thread_local const void* q_fn = nullptr;
             static thread_local int q_dev = -1;
