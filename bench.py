@@ -249,7 +249,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # collectives here are barriers and tiny reductions between legs of a few seconds: a rank that is still
+        # missing after five minutes is not coming (the default would hold the box for ten before saying so)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
     if args.variant:
         engine.set_variant(args.variant)
     if args.items_per_slot:
