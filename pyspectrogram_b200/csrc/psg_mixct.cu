@@ -34,9 +34,9 @@ static int mixct_alt() {
 static bool mixct_pick(int n, int iqt, int frames_per_col, MixctPick* p) {
 #define MIXCT_STR2(x) #x
 #define MIXCT_STR(x) MIXCT_STR2(x)
-#define MIXCT_ALT(ID, N, R0, R1, R2, R3, T, PQ, PA, TW, FD, MINB)                                             \
+#define MIXCT_ALT(ID, N, R0, R1, R2, R3, T, PQ, PA, TW, FD, MINB, PQ2, PA2)                                           \
     if (n == N && mixct_alt() == ID && iqt == IQ_C64) {                                                          \
-        using PL = MixPlan<N, R0, R1, R2, R3, T, PQ, PA, TW>;                                                 \
+        using PL = MixPlan<N, R0, R1, R2, R3, T, PQ, PA, TW, PQ2, PA2>;                                                 \
         p->fn = (const void*)sti_mixct_kernel<PL, FD, IQ_C64, MINB>;                                             \
         p->groups = FD;                                                                                          \
         p->threads = FD * T;                                                                                     \
@@ -44,9 +44,9 @@ static bool mixct_pick(int n, int iqt, int frames_per_col, MixctPick* p) {
         p->name = "mixct" MIXCT_STR(N) "_alt" MIXCT_STR(ID);                                                     \
         return true;                                                                                             \
     }
-#define MIXCT_PLAN(N, R0, R1, R2, R3, T, PQ, PA, TW, FD, MINB)                                                \
+#define MIXCT_PLAN(N, R0, R1, R2, R3, T, PQ, PA, TW, FD, MINB, PQ2, PA2)                                          \
     if (n == N) {                                                                                                \
-        using PL = MixPlan<N, R0, R1, R2, R3, T, PQ, PA, TW>;                                                 \
+        using PL = MixPlan<N, R0, R1, R2, R3, T, PQ, PA, TW, PQ2, PA2>;                                                 \
         const bool one = FD == 1 || frames_per_col < FD;                                                         \
         p->fn = one ? mixct_fn<PL, 1, (FD == 1 ? MINB : mixct_minb1(T))>(iqt) : mixct_fn<PL, FD, MINB>(iqt);     \
         p->groups = one ? 1 : FD;                                                                                \

@@ -88,13 +88,18 @@ PSG_HD void mx_dft(cf* v) {
 }
 
 // ---- plan -------------------------------------------------------------------------------------------------------
-// padded address of pos: pos + PA * (pos / PQ)  (PQ = 0: no padding)
+// Padded address of pos: pos + PA * (pos / PQ) + PA2 * (pos / PQ2)  (a PQ of 0 switches its term off).  PQ is the last
+// radix or a multiple of it and PQ2 a product of trailing radices, so that inside one butterfly the padding is LINEAR:
+// every stride S_p is a multiple of PQ (and of PQ2, or the whole butterfly lies inside one PQ2 block), and the last
+// pass's run of consecutive positions stays inside one block.  A thread therefore pads its base once and reaches its R
+// elements with compile-time offsets (off()): LDS / STS with immediate offsets, no address arithmetic per element --
+// the first version divided per element, which cost more than the conflicts it removed (profiles/r02_mixct_alternatives.txt).
 // TW_: 0 = twiddles rebuilt per frame from W^(2^q) loaded from the L1-resident table, 1 = all twiddles in registers.
 // (A third form that kept neither the next frame's samples nor the window in registers -- no spills on the radix-20
 // plans -- measured 20 % slower than spilling: the exposed load latency costs more.  Removed.)
-template <int N_, int R0_, int R1_, int R2_, int R3_, int T_, int PQ_, int PA_, int TW_>
+template <int N_, int R0_, int R1_, int R2_, int R3_, int T_, int PQ_, int PA_, int TW_, int PQ2_ = 0, int PA2_ = 0>
 struct MixPlan {
-    static constexpr int N = N_, T = T_, PQ = PQ_, PA = PA_;
+    static constexpr int N = N_, T = T_, PQ = PQ_, PA = PA_, PQ2 = PQ2_, PA2 = PA2_;
     static constexpr bool TWREG = TW_ == 1;
     static constexpr int P = 2 + (R2_ > 1) + (R3_ > 1);
     static_assert(R0_ * R1_ * R2_ * R3_ == N_ && R1_ > 1 && (R3_ == 1 || R2_ > 1), "radices multiply to N; at least two passes");
@@ -104,8 +109,21 @@ struct MixPlan {
     }
     __host__ __device__ static constexpr int nb(int p) { return (N_ / r(p) + T_ - 1) / T_; }  // butterflies per thread in pass p
     static constexpr int RL = r(P - 1), NBL = nb(P - 1);
-    static constexpr int NPADDED = N_ + (PQ_ ? PA_ * ((N_ + PQ_ - 1) / PQ_) : 0);
+    static constexpr int NPADDED = N_ + (PQ_ ? PA_ * ((N_ + PQ_ - 1) / PQ_) : 0) + (PQ2_ ? PA2_ * ((N_ + PQ2_ - 1) / PQ2_) : 0);
     static constexpr int BUF = (NPADDED + 3) & ~3;  // complex per group buffer
+    // linearity of the padding inside the butterflies of pass p (see above)
+    __host__ __device__ static constexpr bool lin_ok(int p) {
+        const int sp = s(p), span = r(p) * s(p);
+        const bool t1 = PQ_ == 0 || (p == P - 1 ? PQ_ % r(p) == 0 : sp % PQ_ == 0);
+        const bool t2 = PQ2_ == 0 || (p == P - 1 ? PQ2_ % r(p) == 0 : (sp % PQ2_ == 0 || PQ2_ % span == 0));
+        return t1 && t2;
+    }
+    static_assert(lin_ok(0) && lin_ok(1) && (P < 3 || lin_ok(2)) && (P < 4 || lin_ok(3)), "padding must be linear inside a butterfly");
+    // padded offset of element n of a butterfly of pass p from the padded base
+    __host__ __device__ static constexpr int off(int p, int n) {
+        const int d = n * s(p);
+        return d + (PQ_ && d % PQ_ == 0 ? PA_ * (d / PQ_) : 0) + (PQ2_ && d % PQ2_ == 0 ? PA2_ * (d / PQ2_) : 0);
+    }
     // twiddle registers of a TWREG plan (complex values): passes 0 .. P-2
     __host__ __device__ static constexpr int tw_off(int p) {
         int c = 0;
@@ -114,8 +132,10 @@ struct MixPlan {
     }
     static constexpr int NTW = tw_off(P - 1);
     PSG_HD static int pad(int pos) {
-        if constexpr (PQ_ == 0) return pos;
-        else return pos + PA_ * (pos / PQ_);
+        int a = pos;
+        if constexpr (PQ_ != 0) a += PA_ * (pos / PQ_);
+        if constexpr (PQ2_ != 0) a += PA2_ * (pos / PQ2_);
+        return a;
     }
     // frequency held by position pos after the last pass
     PSG_HD static int freq(int pos) {
@@ -160,9 +180,10 @@ PSG_DEV void mx_pass(float2* __restrict__ buf, int t, const cf* twr, const float
         if (NBP * T == N / RR || bf < N / RR) {
             const int blk = bf / Sp, npr = bf - blk * Sp;
             const int base = blk * RR * Sp + npr;
+            float2* const pb = buf + PL::pad(base);
             cf v[RR];
 #pragma unroll
-            for (int n = 0; n < RR; ++n) v[n] = buf[PL::pad(base + n * Sp)];
+            for (int n = 0; n < RR; ++n) v[n] = pb[PL::off(PIDX, n)];
             mx_dft<RR>(v);
             if constexpr (LAST) {
 #pragma unroll
@@ -179,7 +200,7 @@ PSG_DEV void mx_pass(float2* __restrict__ buf, int t, const cf* twr, const float
                     mx_twiddle_from_powers<RR>(v, pw);
                 }
 #pragma unroll
-                for (int k = 0; k < RR; ++k) buf[PL::pad(base + k * Sp)] = v[k];
+                for (int k = 0; k < RR; ++k) pb[PL::off(PIDX, k)] = v[k];
             }
         }
     }
@@ -271,8 +292,9 @@ __global__ void __launch_bounds__(F * PL::T, MINB) sti_mixct_kernel(const StiArg
                         for (int q = 0; q < NPW; ++q) pw[q] = __ldg(a.tw + ((bf << q) % N));  // R0 S0 = N: W_N^{n' 2^q}
                         mx_twiddle_from_powers<R0>(&x[i * R0], pw);
                     }
+                    float2* const pb = buf + PL::pad(bf);
 #pragma unroll
-                    for (int k = 0; k < R0; ++k) buf[PL::pad(bf + k * S0)] = x[i * R0 + k];
+                    for (int k = 0; k < R0; ++k) pb[PL::off(0, k)] = x[i * R0 + k];
                 }
             }
             // ---- passes 1 .. P-1 in place; the next frame's loads go out before the last one ----

@@ -41,10 +41,10 @@ def accesses(N, radices, T):
     return out
 
 
-def wavefronts(acc, PQ, PA):
+def wavefronts(acc, PQ, PA, PQ2=0, PA2=0):
     tot = 0
     for pos in acc:
-        addr = pos + (PA * (pos // PQ) if PQ else 0)
+        addr = pos + (PA * (pos // PQ) if PQ else 0) + (PA2 * (pos // PQ2) if PQ2 else 0)
         # half-warps by lane position inside the warp-instruction (inactive lanes are at the end of a group only)
         for h in (addr[:16], addr[16:]):
             if h.size == 0:
@@ -55,19 +55,28 @@ def wavefronts(acc, PQ, PA):
 
 
 def main():
+    """Candidates are the paddings that stay LINEAR inside every butterfly (MixPlan::lin_ok): PQ = the last radix, PQ2 a
+    product of trailing radices; smallest buffer among equals."""
     for N, (radices, T) in PLANS.items():
         acc = accesses(N, radices, T)
         ideal = sum((1 if a.size <= 16 else 2) for a in acc)
+        RL = radices[-1]
+        q2s, q = [], RL
+        for r in reversed(radices[:-1]):
+            q *= r
+            if q < N:
+                q2s.append(q)
         best = None
-        cands = [(0, 0)] + [(pq, pa) for pq in sorted({radices[-1], 16, 32, radices[-1] * 2, N // radices[0], 8, 10, 20, 64})
-                            for pa in (1, 2, 3)]
-        for pq, pa in cands:
-            w = wavefronts(acc, pq, pa)
-            if best is None or w < best[0]:
-                best = (w, pq, pa)
+        for pa in range(0, 4):
+            for q2 in q2s + [0]:
+                for pa2 in (range(0, 17) if q2 else [0]):
+                    w = wavefronts(acc, RL if pa else 0, pa, q2 if pa2 else 0, pa2)
+                    size = N + pa * (N // RL) + (pa2 * (N // q2) if q2 else 0)
+                    if best is None or w < best[0] or (w == best[0] and size < best[1]):
+                        best = (w, size, RL if pa else 0, pa, q2 if pa2 else 0, pa2)
         w0 = wavefronts(acc, 0, 0)
-        print(f"N={N:6d} {'x'.join(map(str, radices)):12s} T={T:4d} ideal {ideal:6d}  unpadded {w0:6d} ({w0 / ideal:.2f}x)  "
-              f"best PQ={best[1]:3d} PA={best[2]}: {best[0]:6d} ({best[0] / ideal:.2f}x)")
+        print(f"N={N:6d} {'x'.join(map(str, radices)):12s} T={T:4d} ideal {ideal:6d}  unpadded {w0 / ideal:.2f}x  "
+              f"best PQ={best[2]:3d} PA={best[3]} PQ2={best[4]:4d} PA2={best[5]:2d}: {best[0] / ideal:.2f}x")
 
 
 if __name__ == "__main__":
