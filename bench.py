@@ -331,7 +331,17 @@ def main():
         # running (untimed) until the sampler has seen it for about a second
         t_load = time.perf_counter()
         extra_steps = 0
-        while len(clk.rows) < 6 and time.perf_counter() - t_load < 1.5:
+        while True:
+            more = len(clk.rows) < 6 and time.perf_counter() - t_load < 1.5
+            if world > 1:
+                # a step publishes through a barrier of all ranks: every rank must run the SAME number of steps (the
+                # samplers of different ranks do not fill at the same moment -- left to each rank, the counts differed
+                # now and then and the run deadlocked in the barrier below)
+                flag = torch.tensor([1 if more else 0], device=dev, dtype=torch.int32)
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+                more = bool(int(flag[0]))
+            if not more:
+                break
             for _ in range(8):
                 step()
             extra_steps += 8
