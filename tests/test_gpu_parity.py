@@ -40,7 +40,10 @@ def torch():
     ("sti_r_64x7", False), ("sti_r_256x10x3", False), ("sti_r_1024x100", False), ("sti_r_4096x4", True),
     ("sti_r_hdr2048", False), ("sti_r_impulse16", True), ("sti_r_tone1024", False),
     # pure noise through the reference at the large FFT lengths: every bin is held to the per-bin criterion
-    ("sti_r_noise8192x4", True), ("sti_r_noise16384x3", True), ("sti_r_noise32768x2", True), ("sti_r_noise65536x2", True)])
+    ("sti_r_noise8192x4", True), ("sti_r_noise16384x3", True), ("sti_r_noise32768x2", True), ("sti_r_noise65536x2", True),
+    # round lengths: compile-time mixed-radix plans (1000, 5000), radices 7 / 11 / 13 (1001, 7000), Bluestein (1009: prime)
+    ("sti_r_noise1000x4", True), ("sti_r_noise5000x3", True), ("sti_r_noise1001x4", True), ("sti_r_noise7000x2", True),
+    ("sti_r_noise1009x3", True)])
 def test_sti_proc_data_matches_reference_golden(dp, name, noise_like):
     g = load(name)
     f, sxx, med = dp.sti_proc_data(g["d1"], float(g["sr"]), int(g["nfft"]))

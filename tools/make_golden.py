@@ -133,6 +133,16 @@ def main():
         f, sxx, med = ref["sti_proc_data"](d1, 25.0e6, nfft)
         save(name, d1=d1, sr=np.float64(25.0e6), nfft=np.int64(nfft), f=f, sxx=sxx, med=med)
 
+    # --- round FFT lengths (the numbers people type into the viewer's nfft box, drfview.py:474-479; scipy transforms any
+    # length): pure noise through the reference for the compile-time mixed-radix plans (1000, 5000), the run-time
+    # mixed-radix kernel with radices 7 / 11 / 13 (1001, 7000) and Bluestein (1009 is prime).  Their own generator.
+    rng_round = np.random.default_rng(20261019)
+    for name, (nfft, ntime) in {"sti_r_noise1000x4": (1000, 4), "sti_r_noise5000x3": (5000, 3), "sti_r_noise1001x4": (1001, 4),
+                                "sti_r_noise7000x2": (7000, 2), "sti_r_noise1009x3": (1009, 3)}.items():
+        d1 = iq(rng_round, (nfft, ntime), dtype=np.complex64)
+        f, sxx, med = ref["sti_proc_data"](d1, 1.0e6, nfft)
+        save(name, d1=d1, sr=np.float64(1.0e6), nfft=np.int64(nfft), f=f, sxx=sxx, med=med)
+
     # --- get_ref ----------------------------------------------------------------------------
     props = [
         {"H5Tget_class": 1, "H5Tget_precision": 32, "H5Tget_size": 4},
