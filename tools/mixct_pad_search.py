@@ -14,6 +14,7 @@ PLANS = {
     2400: ((10, 15, 16), 240), 3000: ((10, 15, 20), 300), 3600: ((15, 15, 16), 240), 4000: ((10, 20, 20), 400),
     4800: ((15, 16, 20), 320), 5000: ((10, 10, 10, 5), 500), 6000: ((15, 20, 20), 400), 8000: ((20, 20, 20), 400),
     10000: ((10, 10, 10, 10), 500),
+    1600: ((10, 10, 16), 160), 2500: ((5, 10, 10, 5), 250), 3200: ((10, 16, 20), 320), 6400: ((16, 20, 20), 400),
 }
 
 
