@@ -267,4 +267,4 @@ def test_mixct_plans_replayed_on_the_cpu(tmp_path):
                     "-o", exe, os.path.join(here, "c", "mixct_emu.cu")], check=True, capture_output=True)
     res = subprocess.run([exe], capture_output=True, text=True)
     assert res.returncode == 0 and res.stdout.strip().endswith("ALL OK"), res.stdout + res.stderr
-    assert res.stdout.count("plan ") >= 17
+    assert res.stdout.count("plan ") >= 20

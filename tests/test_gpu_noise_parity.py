@@ -91,7 +91,7 @@ def test_non_power_of_two_per_bin_on_noise(torch, nfft, mode):
     _assert_noise_like(got, gdb, _oracle(x, starts, nfft, nfr, nfft), f"nfft={nfft} mode {mode} {variant}")
 
 
-MIXCT_LENGTHS = [1000, 1200, 1500, 1600, 2000, 2400, 2500, 3000, 3200, 3600, 4000, 4800, 5000, 6000, 6400, 8000, 10000]
+MIXCT_LENGTHS = [1000, 1200, 1500, 1600, 1800, 2000, 2400, 2500, 2700, 3000, 3200, 3600, 4000, 4500, 4800, 5000, 6000, 6400, 8000, 10000]
 
 
 @pytest.mark.parametrize("nfft", MIXCT_LENGTHS)

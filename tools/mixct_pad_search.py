@@ -11,10 +11,11 @@ import numpy as np
 
 PLANS = {
     1000: ((10, 10, 10), 100), 1200: ((10, 10, 12), 120), 1500: ((10, 10, 15), 150), 2000: ((10, 10, 20), 200),
-    2400: ((10, 15, 16), 240), 3000: ((10, 15, 20), 300), 3600: ((15, 15, 16), 240), 4000: ((10, 20, 20), 400),
+    2400: ((10, 15, 16), 240), 3000: ((10, 15, 20), 300), 3600: ((15, 15, 16), 240), 4000: ((10, 10, 10, 4), 400),
     4800: ((15, 16, 20), 320), 5000: ((10, 10, 10, 5), 500), 6000: ((15, 20, 20), 400), 8000: ((20, 20, 20), 400),
     10000: ((10, 10, 10, 10), 500),
     1600: ((10, 10, 16), 160), 2500: ((5, 10, 10, 5), 250), 3200: ((10, 16, 20), 320), 6400: ((16, 20, 20), 400),
+    1800: ((10, 12, 15), 180), 2700: ((12, 15, 15), 225), 4500: ((15, 15, 20), 300),
 }
 
 
