@@ -7,9 +7,10 @@
 A step = one pass of the hot path over one batch of synthetic IQ: per GPU, BASELINE config 2
 (1 channel, 25 MS/s, 60 s = 1.5e9 complex64 samples, nfft=4096, 1000 STI bins, every sample
 read once: nint=366, Mode A) -> dB image + time-median.  N > 1 is weak scaling: one such channel
-per GPU (the channel sharding of SURVEY.md section 8(e)), each rank computes its own columns and one
-NCCL gather assembles the dB image (and the per-channel median rows) on rank 0 inside the timed region -- on a
-side stream, under the kernel of the next step (double-buffered outputs).
+per GPU (the channel sharding of SURVEY.md section 8(e)); each rank computes its own columns and the dB image (and
+the per-channel median rows) is assembled on rank 0 inside the timed region: the kernels' epilogue stores go straight
+into rank 0's buffers over NVLink (dist.PeerImage, symmetric memory) and a barrier on a side stream, under the kernel
+of the next step (double-buffered outputs), publishes step i; an NCCL gather takes its place without peer memory.
 
 Prints ONE JSON line (rank 0).  ``value`` = Msamples/s with inputs resident in HBM; ``e2e`` = the same
 metric through the host-buffer C-ABI call (pinned host IQ -> H2D -> kernels -> D2H of the image);

@@ -3,16 +3,18 @@
 //
 // sti_mixed_kernel (sti_bluestein.cuh) covers every N = 2^a 3^b 5^c with run-time radices: integer divisions per
 // butterfly, twiddles and window loaded per element, accumulators read-modify-written in shared memory -- 11 % of
-// the HBM peak at nfft = 1000.  Here a plan is a template: <N, R0..R3, T> with radices up to 16 that may be
-// composite -- 6, 10, 12, 15 run as Good-Thomas prime-factor butterflies (two small DFTs, no internal twiddles) --
-// so 1000 = 10 x 10 x 10 takes three passes (five shared-memory accesses per sample) where 8 x 5 x 5 x 5 took four.
+// the HBM peak at nfft = 1000.  Here a plan is a template: <N, R0..R3, T> with radices up to 20 that may be
+// composite -- 6, 10, 12, 15, 20 run as Good-Thomas prime-factor butterflies (two small DFTs, no internal twiddles)
+// -- so 1000 = 10 x 10 x 10 takes three passes (five shared-memory accesses per sample) where 8 x 5 x 5 x 5 took four.
 //   * a frame group of T threads owns one frame; thread t runs butterflies bf = t + i T of every pass, the same
 //     ones for every frame, so its window values, its twiddles W_N^{n' k N / (R_p S_p)} (TWREG plans; the others
 //     load W^1, W^2, W^4, W^8 from the L1-resident table and multiply) and its |X|^2 accumulators live in registers;
 //   * pass 0 reads the samples with coalesced LDG (any layout and sample type), the next frame's loads are issued
 //     before the current frame's last pass; passes run in place on a padded shared-memory buffer (padding chosen
-//     per plan by tools/mixct_pad_search.py); one CTA barrier per pass;
-//   * F groups per CTA share the barriers and work on F frames of the same column; the epilogue sums their
+//     per plan by tools/mixct_pad_search.py, linear inside a butterfly: one padded base + immediate offsets); one
+//     CTA barrier per pass;
+//   * F groups per CTA share the barriers and work on F frames of the same column (the shipped plans use F = 1 and
+//     several resident CTAs: more independent barrier domains per SM measured faster); the epilogue sums their
 //     accumulators through shared memory, un-permutes the mixed-radix digit reversal, fftshifts (odd N included)
 //     and stores 10 log10 / linear power coalesced -- or raw partial sums for split columns (sti_finalize_kernel).
 // Pass structure (the same index algebra as sti_kernels.cuh, restated in numpy in tests/test_fft_plan.py):
